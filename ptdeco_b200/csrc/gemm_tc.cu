@@ -1,0 +1,485 @@
+// tcgen05 GEMM engine for sm_100a. See gemm_tc.cuh for what it computes and who uses it.
+//
+// Kernel anatomy (one CTA per SM, persistent over work units = output tile x k-split):
+//   warp 0        TMA producer: cp.async.bulk.tensor (128B swizzle) into a STAGES-deep smem ring
+//   warp 1        TMEM allocation + single-thread tcgen05.mma issue, tcgen05.commit to mbarriers
+//   warps 2..5    epilogue: tcgen05.ld TMEM -> registers -> global (store / red.add / bf16 / split)
+// Accumulators are double-buffered in TMEM (2 x TILE_N fp32 columns) so the epilogue of unit u
+// overlaps the main loop of unit u+1.
+#include "gemm_tc.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "ptx.cuh"
+
+namespace ptd {
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int BLOCK_K = 64;  // bf16 elements per k-block = one 128-byte swizzle span
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_PAIRS = 6;
+constexpr int A_BYTES = TILE_M * BLOCK_K * 2;
+constexpr int GROUP_BYTES = 64 * BLOCK_K * 2;  // one 64-wide MN group of an MN-major tile
+
+template <int TILE_N>
+struct Cfg {
+  static constexpr int B_BYTES = TILE_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (TILE_N == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * TILE_N;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct KArgs {
+  int M, N;
+  int kblocks;  // k-blocks per segment pair
+  int npairs;
+  int pair_a[MAX_PAIRS], pair_b[MAX_PAIRS];
+  int tiles_n, ntiles, splitk;
+  int lower, accumulate;
+  float alpha;
+  float* C;
+  long long ldc;
+  __nv_bfloat16* Cb;
+  long long ldcb;
+  __nv_bfloat16* Cs;
+  long long ldcs, cs_seg;
+  const float* bias;
+  uint32_t lbo_mn, sbo_mn, lbo_k, sbo_k;
+};
+
+template <int TILE_N>
+__device__ __forceinline__ void decode_tile(const KArgs& g, int t, int& m0, int& n0) {
+  if (!g.lower) {
+    m0 = (t / g.tiles_n) * TILE_M;
+    n0 = (t % g.tiles_n) * TILE_N;
+    return;
+  }
+  if (TILE_N == 128) {
+    // row block i holds tiles j = 0..i ; cumulative i(i+1)/2
+    int i = static_cast<int>((sqrtf(8.f * static_cast<float>(t) + 1.f) - 1.f) * 0.5f);
+    while (i * (i + 1) / 2 > t) --i;
+    while ((i + 1) * (i + 2) / 2 <= t) ++i;
+    m0 = i * TILE_M;
+    n0 = (t - i * (i + 1) / 2) * TILE_N;
+  } else {
+    // 256-wide column blocks: row blocks 2q and 2q+1 hold q+1 tiles each; cumulative q(q+1)
+    int q = static_cast<int>((sqrtf(4.f * static_cast<float>(t) + 1.f) - 1.f) * 0.5f);
+    while (q * (q + 1) > t) --q;
+    while ((q + 1) * (q + 2) <= t) ++q;
+    int rem = t - q * (q + 1);
+    int i = 2 * q, j = rem;
+    if (rem >= q + 1) {
+      i = 2 * q + 1;
+      j = rem - (q + 1);
+    }
+    m0 = i * TILE_M;
+    n0 = j * TILE_N;
+  }
+}
+
+template <bool A_MN, bool B_MN, int TILE_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const KArgs g) {
+  using C_ = Cfg<TILE_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_::STAGES * C_::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C_::STAGES;
+  uint64_t* acc_full = bars + 2 * C_::STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < C_::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C_::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nunits = g.ntiles * g.splitk;
+  const int kb_per_split = (g.kblocks + g.splitk - 1) / g.splitk;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+        int m0, n0;
+        decode_tile<TILE_N>(g, u / g.splitk, m0, n0);
+        const int sp = u % g.splitk;
+        const int kb0 = sp * kb_per_split;
+        const int kb1 = min(g.kblocks, kb0 + kb_per_split);
+        for (int p = 0; p < g.npairs; ++p) {
+          const int sa = g.pair_a[p], sb = g.pair_b[p];
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sA = smem + stage * C_::STAGE_BYTES;
+            uint8_t* sB = sA + A_BYTES;
+            mbar_expect_tx(&full[stage], C_::STAGE_BYTES);
+            if (A_MN) {
+#pragma unroll
+              for (int gi = 0; gi < TILE_M / 64; ++gi)
+                tma_load_3d(sA + gi * GROUP_BYTES, &tmA, &full[stage], m0 + 64 * gi, kb * BLOCK_K,
+                            sa);
+            } else {
+              tma_load_3d(sA, &tmA, &full[stage], kb * BLOCK_K, m0, sa);
+            }
+            if (B_MN) {
+#pragma unroll
+              for (int gi = 0; gi < TILE_N / 64; ++gi)
+                tma_load_3d(sB + gi * GROUP_BYTES, &tmB, &full[stage], n0 + 64 * gi, kb * BLOCK_K,
+                            sb);
+            } else {
+              tma_load_3d(sB, &tmB, &full[stage], kb * BLOCK_K, n0, sb);
+            }
+            if (++stage == C_::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, TILE_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+        const int sp = u % g.splitk;
+        const int kb0 = sp * kb_per_split;
+        const int kb1 = min(g.kblocks, kb0 + kb_per_split);
+        const int niter = g.npairs * max(0, kb1 - kb0);
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TILE_N;
+        for (int it = 0; it < niter; ++it) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * C_::STAGE_BYTES);
+          const uint32_t sB = sA + A_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
+            const uint64_t adesc =
+                A_MN ? umma_smem_desc_sw128(sA + ks * (UMMA_K * 128), g.lbo_mn, g.sbo_mn)
+                     : umma_smem_desc_sw128(sA + ks * (UMMA_K * 2), g.lbo_k, g.sbo_k);
+            const uint64_t bdesc =
+                B_MN ? umma_smem_desc_sw128(sB + ks * (UMMA_K * 128), g.lbo_mn, g.sbo_mn)
+                     : umma_smem_desc_sw128(sB + ks * (UMMA_K * 2), g.lbo_k, g.sbo_k);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // frees this smem stage once its MMAs retire
+          if (++stage == C_::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------- epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+      int m0, n0;
+      decode_tile<TILE_N>(g, u / g.splitk, m0, n0);
+      const int sp = u % g.splitk;
+      const int kb0 = sp * kb_per_split;
+      const int kb1 = min(g.kblocks, kb0 + kb_per_split);
+      const bool has_work = kb1 > kb0;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const int m = m0 + q * 32 + lane;
+      const uint32_t t_row = tmem_base + acc * TILE_N + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < TILE_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + c * 32, r);
+        tmem_ld_wait();
+        const int nb = n0 + c * 32;
+        if (m < g.M && nb < g.N && has_work) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * g.alpha;
+          if (g.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j < g.N) v[j] += __ldg(g.bias + nb + j);
+          }
+          if (g.C != nullptr) {
+            float* crow = g.C + static_cast<long long>(m) * g.ldc + nb;
+            if (vec_ok && nb + 32 <= g.N) {
+              if (g.accumulate) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) red_add_v4(crow + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              }
+            } else {
+              for (int j = 0; j < 32 && nb + j < g.N; ++j) {
+                if (g.accumulate)
+                  atomicAdd(crow + j, v[j]);
+                else
+                  crow[j] = v[j];
+              }
+            }
+          }
+          if (g.Cb != nullptr) {
+            __nv_bfloat16* brow = g.Cb + static_cast<long long>(m) * g.ldcb + nb;
+            for (int j = 0; j < 32 && nb + j < g.N; ++j) brow[j] = __float2bfloat16_rn(v[j]);
+          }
+          if (g.Cs != nullptr) {
+            __nv_bfloat16* srow = g.Cs + static_cast<long long>(m) * g.ldcs + nb;
+            for (int j = 0; j < 32 && nb + j < g.N; ++j) {
+              const float x = v[j];
+              const __nv_bfloat16 h = __float2bfloat16_rn(x);
+              const float r1 = x - __bfloat162float(h);
+              const __nv_bfloat16 mm = __float2bfloat16_rn(r1);
+              const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(mm));
+              srow[j] = h;
+              srow[g.cs_seg + j] = mm;
+              srow[2 * g.cs_seg + j] = l;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C_::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) !=
+          cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 3-D map {inner, rows, seg}; box {64, box_rows, 1}; 128B swizzle; zero fill out of bounds.
+int make_map(CUtensorMap* map, const GemmOperand& op, long long inner, long long rows,
+             int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return -38;  // ENOSYS
+  if ((reinterpret_cast<uintptr_t>(op.ptr) & 15) || (op.ld & 7) || (op.nseg > 1 && (op.seg_stride & 7)))
+    return -22;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(rows),
+                        static_cast<cuuint64_t>(op.nseg)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(op.ld) * 2,
+                           static_cast<cuuint64_t>(op.nseg > 1 ? op.seg_stride : op.ld * rows) * 2};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(op.ptr),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -static_cast<int>(1000 + r);
+}
+
+long long g_dbg[16] = {0};
+long long g_info[16] = {0};
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <bool A_MN, bool B_MN, int TILE_N>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const KArgs& g, int grid,
+           cudaStream_t stream) {
+  using C_ = Cfg<TILE_N>;
+  auto kern = gemm_tc_kernel<A_MN, B_MN, TILE_N>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES) !=
+        cudaSuccess)
+      return -12;
+    attr_done = true;
+  }
+  kern<<<grid, NUM_THREADS, C_::SMEM_BYTES, stream>>>(ta, tb, g);
+  return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
+
+}  // namespace
+
+void gemm_tc_debug_set(int key, long long value) {
+  if (key >= 0 && key < 16) g_dbg[key] = value;
+}
+long long gemm_tc_last_launch_info(int key) { return (key >= 0 && key < 16) ? g_info[key] : 0; }
+
+int gemm_tc(const GemmOperand& A, const GemmOperand& B, int M, int N, int K, int pair_order,
+            const GemmEpilogue& ep, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return -22;
+  if (ep.lower_only && M != N) return -22;
+  if ((A.nseg != 1 && A.nseg != 3) || (B.nseg != 1 && B.nseg != 3)) return -22;
+
+  // dbg[0]: force TILE_N (128/256); dbg[1]: force splitk; dbg[2..5]: lbo_mn, sbo_mn, lbo_k, sbo_k
+  int tile_n = (N > 128) ? 256 : 128;
+  if (g_dbg[0] == 128 || g_dbg[0] == 256) tile_n = static_cast<int>(g_dbg[0]);
+
+  KArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = M;
+  g.N = N;
+  g.kblocks = (K + BLOCK_K - 1) / BLOCK_K;
+  if (pair_order < 0) pair_order = (A.nseg == 3 || B.nseg == 3) ? 2 : 0;
+  g.npairs = 0;
+  for (int s = 0; s <= pair_order; ++s)  // most significant products first
+    for (int sa = 0; sa <= s; ++sa) {
+      const int sb = s - sa;
+      if (sa < A.nseg && sb < B.nseg && g.npairs < MAX_PAIRS) {
+        g.pair_a[g.npairs] = sa;
+        g.pair_b[g.npairs] = sb;
+        ++g.npairs;
+      }
+    }
+  const int tiles_m = (M + TILE_M - 1) / TILE_M;
+  g.tiles_n = (N + tile_n - 1) / tile_n;
+  if (ep.lower_only) {
+    long long nt = 0;
+    for (int i = 0; i < tiles_m; ++i) nt += (tile_n == 128) ? (i + 1) : (i / 2 + 1);
+    g.ntiles = static_cast<int>(nt);
+  } else {
+    g.ntiles = tiles_m * g.tiles_n;
+  }
+  g.lower = ep.lower_only;
+  g.accumulate = ep.accumulate;
+  g.alpha = ep.alpha;
+  g.C = ep.C;
+  g.ldc = ep.ldc;
+  g.Cb = ep.Cb;
+  g.ldcb = ep.ldcb;
+  g.Cs = ep.Cs;
+  g.ldcs = ep.ldcs;
+  g.cs_seg = ep.cs_seg;
+  g.bias = ep.bias;
+  g.lbo_mn = g_dbg[2] ? static_cast<uint32_t>(g_dbg[2]) : GROUP_BYTES;  // 64-wide MN group stride
+  g.sbo_mn = g_dbg[3] ? static_cast<uint32_t>(g_dbg[3]) : 1024;         // 8 k-rows x 128 B
+  g.lbo_k = g_dbg[4] ? static_cast<uint32_t>(g_dbg[4]) : 16;            // unused for swizzled K-major
+  g.sbo_k = g_dbg[5] ? static_cast<uint32_t>(g_dbg[5]) : 1024;          // 8 MN-rows x 128 B
+
+  // k-split: only when accumulating with atomics (a plain store cannot be split). Pick the split
+  // that best fills whole waves of SMs while keeping >= 4 k-blocks per unit.
+  const int sms = num_sms();
+  int splitk = 1;
+  if (ep.accumulate && ep.Cb == nullptr && ep.Cs == nullptr && ep.bias == nullptr) {
+    double best = -1.0;
+    const int max_split = std::max(1, std::min(g.kblocks / 4, 64));
+    for (int s = 1; s <= max_split; ++s) {
+      const long long units = static_cast<long long>(g.ntiles) * s;
+      const long long waves = (units + sms - 1) / sms;
+      const double eff = static_cast<double>(units) / static_cast<double>(waves * sms);
+      // prefer fewer splits on ties (less atomic traffic)
+      if (eff > best + 0.03) {
+        best = eff;
+        splitk = s;
+      }
+    }
+  }
+  if (g_dbg[1] > 0) splitk = static_cast<int>(std::min<long long>(g_dbg[1], g.kblocks));
+  if (!ep.accumulate) splitk = 1;
+  g.splitk = splitk;
+  // make every split non-empty
+  {
+    const int per = (g.kblocks + g.splitk - 1) / g.splitk;
+    g.splitk = (g.kblocks + per - 1) / per;
+  }
+
+  CUtensorMap ta, tb;
+  int rc;
+  // MN-major: inner = MN extent, rows = K. K-major: inner = K, rows = MN extent.
+  rc = A.mn_major ? make_map(&ta, A, M, K, BLOCK_K) : make_map(&ta, A, K, M, TILE_M);
+  if (rc) return rc;
+  rc = B.mn_major ? make_map(&tb, B, N, K, BLOCK_K) : make_map(&tb, B, K, N, tile_n);
+  if (rc) return rc;
+
+  const long long units = static_cast<long long>(g.ntiles) * g.splitk;
+  const int grid = static_cast<int>(std::min<long long>(units, sms));
+  g_info[0] = tile_n;
+  g_info[1] = g.splitk;
+  g_info[2] = g.ntiles;
+  g_info[3] = grid;
+  g_info[4] = g.npairs;
+
+#define PTD_LAUNCH(AM, BM)                                                      \
+  (tile_n == 256 ? launch<AM, BM, 256>(ta, tb, g, grid, stream)                 \
+                 : launch<AM, BM, 128>(ta, tb, g, grid, stream))
+  if (A.mn_major && B.mn_major) return PTD_LAUNCH(true, true);
+  if (!A.mn_major && !B.mn_major) return PTD_LAUNCH(false, false);
+  if (!A.mn_major && B.mn_major) return PTD_LAUNCH(false, true);
+  return PTD_LAUNCH(true, false);
+#undef PTD_LAUNCH
+}
+
+}  // namespace ptd
