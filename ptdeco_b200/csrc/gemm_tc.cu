@@ -3,9 +3,9 @@
 // Kernel anatomy (one CTA per SM, persistent over work units = output tile x k-split):
 //   warp 0        TMA producer: cp.async.bulk.tensor (128B swizzle) into a STAGES-deep smem ring
 //   warp 1        TMEM allocation + single-thread tcgen05.mma issue, tcgen05.commit to mbarriers
-//   warps 2..5    epilogue: tcgen05.ld TMEM -> registers -> global (store / red.add / bf16 / split)
-// Accumulators are double-buffered in TMEM (2 x TILE_N fp32 columns) so the epilogue of unit u
-// overlaps the main loop of unit u+1.
+//   warps 2..9    epilogue: tcgen05.ld TMEM -> fp32 register sums -> global (store / red.add / bf16)
+// Accumulators are double-buffered in TMEM (2 x TILE_N fp32 columns): the tensor core fills one
+// buffer for CHUNK_ITERS k-blocks while the epilogue warps drain the other into registers.
 #include "gemm_tc.cuh"
 
 #include <algorithm>
@@ -22,7 +22,13 @@ namespace {
 constexpr int TILE_M = 128;
 constexpr int BLOCK_K = 64;  // bf16 elements per k-block = one 128-byte swizzle span
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // producer + MMA + 8 epilogue warps
+// The tensor core adds into its fp32 TMEM accumulator with truncation, which biases long
+// reductions (measured 1.8e-5 relative at K = 8192). TMEM accumulation is therefore bounded to
+// CHUNK_ITERS k-blocks (64 MMA k-steps); completed chunks are summed in fp32 registers (RN) by
+// the epilogue warps while the tensor core fills the other TMEM buffer.
+constexpr int CHUNK_ITERS = 16;
 constexpr int MAX_PAIRS = 6;
 constexpr int A_BYTES = TILE_M * BLOCK_K * 2;
 constexpr int GROUP_BYTES = 64 * BLOCK_K * 2;  // one 64-wide MN group of an MN-major tile
@@ -42,6 +48,7 @@ struct KArgs {
   int npairs;
   int pair_a[MAX_PAIRS], pair_b[MAX_PAIRS];
   int tiles_n, ntiles, splitk;
+  int chunk_iters;
   int lower, accumulate;
   float alpha;
   float* C;
@@ -111,7 +118,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);  // one arrive per epilogue warp
+      mbar_init(&acc_empty[a], NUM_EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -182,40 +189,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb0 = sp * kb_per_split;
         const int kb1 = min(g.kblocks, kb0 + kb_per_split);
         const int niter = g.npairs * max(0, kb1 - kb0);
-        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * TILE_N;
-        for (int it = 0; it < niter; ++it) {
-          mbar_wait(&full[stage], phase);
+        for (int it0 = 0; it0 < niter; it0 += g.chunk_iters) {
+          const int it1 = min(niter, it0 + g.chunk_iters);
+          mbar_wait(&acc_empty[acc], acc_phase ^ 1);
           tc_fence_after();
-          const uint32_t sA = smem_u32(smem + stage * C_::STAGE_BYTES);
-          const uint32_t sB = sA + A_BYTES;
+          const uint32_t d_tmem = tmem_base + acc * TILE_N;
+          for (int it = it0; it < it1; ++it) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t sA = smem_u32(smem + stage * C_::STAGE_BYTES);
+            const uint32_t sB = sA + A_BYTES;
 #pragma unroll
-          for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
-            const uint64_t adesc =
-                A_MN ? umma_smem_desc_sw128(sA + ks * (UMMA_K * 128), g.lbo_mn, g.sbo_mn)
-                     : umma_smem_desc_sw128(sA + ks * (UMMA_K * 2), g.lbo_k, g.sbo_k);
-            const uint64_t bdesc =
-                B_MN ? umma_smem_desc_sw128(sB + ks * (UMMA_K * 128), g.lbo_mn, g.sbo_mn)
-                     : umma_smem_desc_sw128(sB + ks * (UMMA_K * 2), g.lbo_k, g.sbo_k);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
+              const uint64_t adesc =
+                  A_MN ? umma_smem_desc_sw128(sA + ks * (UMMA_K * 128), g.lbo_mn, g.sbo_mn)
+                       : umma_smem_desc_sw128(sA + ks * (UMMA_K * 2), g.lbo_k, g.sbo_k);
+              const uint64_t bdesc =
+                  B_MN ? umma_smem_desc_sw128(sB + ks * (UMMA_K * 128), g.lbo_mn, g.sbo_mn)
+                       : umma_smem_desc_sw128(sB + ks * (UMMA_K * 2), g.lbo_k, g.sbo_k);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, (it > it0 || ks > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty[stage]);  // frees this smem stage once its MMAs retire
+            if (++stage == C_::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
-          umma_commit(&empty[stage]);  // frees this smem stage once its MMAs retire
-          if (++stage == C_::STAGES) {
-            stage = 0;
-            phase ^= 1;
+          umma_commit(&acc_full[acc]);  // chunk complete -> epilogue
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
           }
-        }
-        umma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
         }
       }
     }
   } else {
-    // ------------------------------------------------------------- epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------- epilogue (warps 2..9)
+    constexpr int COLS = TILE_N / 2;           // columns owned by one epilogue warp
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;          // which column half of the tile
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool vec_ok = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
@@ -225,54 +237,90 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int sp = u % g.splitk;
       const int kb0 = sp * kb_per_split;
       const int kb1 = min(g.kblocks, kb0 + kb_per_split);
-      const bool has_work = kb1 > kb0;
-      mbar_wait(&acc_full[acc], acc_phase);
-      tc_fence_after();
+      const int niter = g.npairs * max(0, kb1 - kb0);
+      float sum[COLS];
+#pragma unroll
+      for (int j = 0; j < COLS; ++j) sum[j] = 0.f;
+      for (int it0 = 0; it0 < niter; it0 += g.chunk_iters) {
+        mbar_wait(&acc_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + acc * TILE_N + half * COLS +
+                               (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll
+        for (int c = 0; c < COLS / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sum[c * 32 + j] += __uint_as_float(r[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
       const int m = m0 + q * 32 + lane;
-      const uint32_t t_row = tmem_base + acc * TILE_N + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < TILE_N / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + c * 32, r);
-        tmem_ld_wait();
-        const int nb = n0 + c * 32;
-        if (m < g.M && nb < g.N && has_work) {
-          float v[32];
+      const int nbase = n0 + half * COLS;
+      if (m < g.M && nbase < g.N && niter > 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * g.alpha;
-          if (g.bias != nullptr) {
+        for (int j = 0; j < COLS; ++j) sum[j] *= g.alpha;
+        if (g.bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j < g.N) v[j] += __ldg(g.bias + nb + j);
-          }
-          if (g.C != nullptr) {
-            float* crow = g.C + static_cast<long long>(m) * g.ldc + nb;
-            if (vec_ok && nb + 32 <= g.N) {
-              if (g.accumulate) {
+          for (int j = 0; j < COLS; ++j)
+            if (nbase + j < g.N) sum[j] += __ldg(g.bias + nbase + j);
+        }
+        if (g.C != nullptr) {
+          float* crow = g.C + static_cast<long long>(m) * g.ldc + nbase;
+          if (vec_ok && nbase + COLS <= g.N) {
+            if (g.accumulate) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) red_add_v4(crow + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              }
+              for (int j = 0; j < COLS; j += 4)
+                red_add_v4(crow + j, sum[j], sum[j + 1], sum[j + 2], sum[j + 3]);
             } else {
-              for (int j = 0; j < 32 && nb + j < g.N; ++j) {
+#pragma unroll
+              for (int j = 0; j < COLS; j += 4)
+                *reinterpret_cast<float4*>(crow + j) =
+                    make_float4(sum[j], sum[j + 1], sum[j + 2], sum[j + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < COLS; ++j) {
+              if (nbase + j < g.N) {
                 if (g.accumulate)
-                  atomicAdd(crow + j, v[j]);
+                  atomicAdd(crow + j, sum[j]);
                 else
-                  crow[j] = v[j];
+                  crow[j] = sum[j];
               }
             }
           }
-          if (g.Cb != nullptr) {
-            __nv_bfloat16* brow = g.Cb + static_cast<long long>(m) * g.ldcb + nb;
-            for (int j = 0; j < 32 && nb + j < g.N; ++j) brow[j] = __float2bfloat16_rn(v[j]);
+        }
+        if (g.Cb != nullptr) {
+          __nv_bfloat16* brow = g.Cb + static_cast<long long>(m) * g.ldcb + nbase;
+          const bool bvec = ((g.ldcb & 7) == 0) && ((reinterpret_cast<uintptr_t>(g.Cb) & 15) == 0) &&
+                            nbase + COLS <= g.N;
+          if (bvec) {
+#pragma unroll
+            for (int j = 0; j < COLS; j += 8) {
+              __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = __float2bfloat16_rn(sum[j + e]);
+              *reinterpret_cast<uint4*>(brow + j) = *reinterpret_cast<const uint4*>(o);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < COLS; ++j)
+              if (nbase + j < g.N) brow[j] = __float2bfloat16_rn(sum[j]);
           }
-          if (g.Cs != nullptr) {
-            __nv_bfloat16* srow = g.Cs + static_cast<long long>(m) * g.ldcs + nb;
-            for (int j = 0; j < 32 && nb + j < g.N; ++j) {
-              const float x = v[j];
+        }
+        if (g.Cs != nullptr) {
+          __nv_bfloat16* srow = g.Cs + static_cast<long long>(m) * g.ldcs + nbase;
+#pragma unroll
+          for (int j = 0; j < COLS; ++j) {
+            if (nbase + j < g.N) {
+              const float x = sum[j];
               const __nv_bfloat16 h = __float2bfloat16_rn(x);
               const float r1 = x - __bfloat162float(h);
               const __nv_bfloat16 mm = __float2bfloat16_rn(r1);
@@ -283,13 +331,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
       }
     }
   }
@@ -424,25 +465,28 @@ int gemm_tc(const GemmOperand& A, const GemmOperand& B, int M, int N, int K, int
   g.ldcs = ep.ldcs;
   g.cs_seg = ep.cs_seg;
   g.bias = ep.bias;
+  g.chunk_iters = g_dbg[6] > 0 ? static_cast<int>(g_dbg[6]) : CHUNK_ITERS;
   g.lbo_mn = g_dbg[2] ? static_cast<uint32_t>(g_dbg[2]) : GROUP_BYTES;  // 64-wide MN group stride
   g.sbo_mn = g_dbg[3] ? static_cast<uint32_t>(g_dbg[3]) : 1024;         // 8 k-rows x 128 B
   g.lbo_k = g_dbg[4] ? static_cast<uint32_t>(g_dbg[4]) : 16;            // unused for swizzled K-major
   g.sbo_k = g_dbg[5] ? static_cast<uint32_t>(g_dbg[5]) : 1024;          // 8 MN-rows x 128 B
 
-  // k-split: only when accumulating with atomics (a plain store cannot be split). Pick the split
-  // that best fills whole waves of SMs while keeping >= 4 k-blocks per unit.
+  // k-split: only when accumulating with atomics (a plain store cannot be split). Cost model per
+  // unit: max(main loop, epilogue) with the epilogue (TILE_M x TILE_N red.add) worth ~E k-block
+  // times; pick the split minimising waves x unit cost.
   const int sms = num_sms();
   int splitk = 1;
   if (ep.accumulate && ep.Cb == nullptr && ep.Cs == nullptr && ep.bias == nullptr) {
-    double best = -1.0;
+    const double epi_kb = 40.0;  // measured: a 128x256 red.add epilogue ~ 20k cycles ~ 40 k-blocks
+    double best = 1e300;
     const int max_split = std::max(1, std::min(g.kblocks / 4, 64));
     for (int s = 1; s <= max_split; ++s) {
       const long long units = static_cast<long long>(g.ntiles) * s;
       const long long waves = (units + sms - 1) / sms;
-      const double eff = static_cast<double>(units) / static_cast<double>(waves * sms);
-      // prefer fewer splits on ties (less atomic traffic)
-      if (eff > best + 0.03) {
-        best = eff;
+      const double kb_unit = static_cast<double>((g.kblocks + s - 1) / s) * g.npairs;
+      const double cost = static_cast<double>(waves) * std::max(kb_unit, epi_kb) + epi_kb;
+      if (cost < best * 0.97) {  // prefer fewer splits on near-ties
+        best = cost;
         splitk = s;
       }
     }

@@ -1,0 +1,148 @@
+"""Torch-tensor front end of the C-ABI kernels (device memory + streams are torch's; the math is not).
+
+Everything here takes CUDA tensors, enqueues on torch's current stream and returns CUDA tensors
+without host synchronisation. There is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _native as nat
+
+
+def _check_2d(t: torch.Tensor, name: str) -> torch.Tensor:
+    nat.require_cuda(t, name)
+    if t.dim() != 2:
+        raise ValueError(f"{name} must be 2-D, got {tuple(t.shape)}")
+    if t.stride(1) != 1:
+        t = t.contiguous()
+    return t
+
+
+class CovarianceAccumulator:
+    """fp32 d x d accumulator of E[y y^T] (and E[y]) fed by the SYRK kernel (K1/K1b/K2).
+
+    Replaces the reference's `Eyyt` / `Ey` tensors and their updates (F:156-162, F:180-205,
+    D:147-152, D:166-208). `accumulate_in_float64` of the reference maps to the same fp32
+    accumulator: each per-batch product is formed with fp32-grade arithmetic (exact bf16 products or
+    bf16x3 split, fp32 adds with bounded tensor-core chunks), which measures within 1e-6 of the
+    reference's fp64 accumulator (parity section)."""
+
+    def __init__(self, d: int, device: torch.device, with_mean: bool = False):
+        self.d = int(d)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise nat.NativeError("CovarianceAccumulator needs a CUDA device (no CPU path)")
+        self.C = torch.zeros((self.d, self.d), dtype=torch.float32, device=self.device)
+        self.colsum = torch.zeros(self.d, dtype=torch.float32, device=self.device) if with_mean else None
+        self.steps = 0
+
+    def update(self, y: torch.Tensor, sub: Optional[torch.Tensor] = None) -> None:
+        """C += (y - sub)^T (y - sub) / N ; colsum += mean_rows(y - sub). y: [N, d] fp32 or bf16."""
+        y = _check_2d(y, "y")
+        if y.shape[1] != self.d:
+            raise ValueError(f"y has {y.shape[1]} features, accumulator has {self.d}")
+        if y.dtype not in (torch.float32, torch.bfloat16):
+            y = y.float()
+        n = y.shape[0]
+        if n == 0:
+            raise ValueError("empty activation batch")
+        if sub is not None:
+            sub = sub.detach().to(device=y.device, dtype=torch.float32).contiguous()
+        L = nat.lib()
+        need = L.ptdeco_syrk_workspace_bytes(nat.dtype_code(y), n, self.d)
+        ws = nat.WORKSPACE.get(y.device, need)
+        nat.check(
+            L.ptdeco_syrk_accumulate(y.data_ptr(), nat.dtype_code(y), n, self.d, y.stride(0),
+                                     nat.ptr(sub), self.C.data_ptr(), self.C.stride(0),
+                                     nat.ptr(self.colsum), 1.0 / n, ws.data_ptr(), ws.numel(),
+                                     nat.stream_ptr(y.device)), "ptdeco_syrk_accumulate")
+        self.steps += 1
+
+    def finalize(self, use_mean: bool, damp_factor: float) -> torch.Tensor:
+        """In place: /steps, optional centring, mirror to the upper triangle, damping. Returns C."""
+        if self.steps == 0:
+            raise ValueError("no batches accumulated")
+        if use_mean and self.colsum is None:
+            raise ValueError("accumulator was created without mean tracking")
+        nat.check(
+            nat.lib().ptdeco_cov_finalize(self.C.data_ptr(), self.C.stride(0), self.d,
+                                          nat.ptr(self.colsum), self.steps, int(bool(use_mean)),
+                                          float(damp_factor), None, nat.stream_ptr(self.device)),
+            "ptdeco_cov_finalize")
+        return self.C
+
+
+def eigh(cov: torch.Tensor, overwrite: bool = False) -> tuple[torch.Tensor, torch.Tensor]:
+    """Symmetric eigendecomposition (K3), ascending eigenvalues, eigenvectors in columns — the
+    layout of torch.linalg.eigh that the reference consumes (F:207, D:162)."""
+    cov = _check_2d(cov, "cov")
+    d = cov.shape[0]
+    if cov.shape[1] != d:
+        raise ValueError("cov must be square")
+    a = cov if (overwrite and cov.dtype == torch.float32 and cov.is_contiguous()) else cov.float().clone()
+    L = nat.lib()
+    evals = torch.empty(d, dtype=torch.float32, device=cov.device)
+    U = torch.empty((d, d), dtype=torch.float32, device=cov.device)
+    need = L.ptdeco_eigh_workspace_bytes(d)
+    ws = nat.WORKSPACE.get(cov.device, need)
+    nat.check(
+        L.ptdeco_eigh(a.data_ptr(), d, a.stride(0), evals.data_ptr(), U.data_ptr(), U.stride(0),
+                      ws.data_ptr(), ws.numel(), nat.stream_ptr(cov.device)), "ptdeco_eigh")
+    return evals, U
+
+
+def gemm(a: torch.Tensor, a_mn_major: bool, b: torch.Tensor, b_mn_major: bool, m: int, n: int, k: int,
+         out_dtype: torch.dtype = torch.float32, alpha: float = 1.0,
+         bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C[m,n] = alpha * op(a) op(b) (+ bias) on the tcgen05 engine. See ptdeco_gemm in the header."""
+    a = _check_2d(a, "a")
+    b = _check_2d(b, "b")
+    if a.dtype not in (torch.float32, torch.bfloat16):
+        a = a.float()
+    if b.dtype not in (torch.float32, torch.bfloat16):
+        b = b.float()
+    exp_a = (k, m) if a_mn_major else (m, k)
+    exp_b = (k, n) if b_mn_major else (n, k)
+    if tuple(a.shape) != exp_a or tuple(b.shape) != exp_b:
+        raise ValueError(f"operand shapes {tuple(a.shape)}, {tuple(b.shape)} do not match {exp_a}, {exp_b}")
+    out = torch.empty((m, n), dtype=out_dtype, device=a.device)
+    if bias is not None:
+        bias = bias.detach().to(device=a.device, dtype=torch.float32).contiguous()
+    L = nat.lib()
+    need = L.ptdeco_gemm_workspace_bytes(nat.dtype_code(a), nat.dtype_code(b), m, n, k)
+    ws = nat.WORKSPACE.get(a.device, need)
+    nat.check(
+        L.ptdeco_gemm(a.data_ptr(), nat.dtype_code(a), int(a_mn_major), a.stride(0), b.data_ptr(),
+                      nat.dtype_code(b), int(b_mn_major), b.stride(0), m, n, k, float(alpha),
+                      nat.ptr(bias), out.data_ptr(), nat.dtype_code(out), out.stride(0), 0,
+                      ws.data_ptr(), ws.numel(), nat.stream_ptr(a.device)), "ptdeco_gemm")
+    return out
+
+
+def factor_w1(weight: torch.Tensor, uk: torch.Tensor) -> torch.Tensor:
+    """K4: W1 = uk^T W, [k, in]. (`U = W^T uk` of F:347 / D:427 is its transpose.)
+    weight [out, in] and uk [out, k] are both MN-major operands of a contraction over `out`."""
+    out_f, in_f = weight.shape
+    k = uk.shape[1]
+    return gemm(uk, True, weight, True, k, in_f, out_f, out_dtype=weight.dtype
+                if weight.dtype in (torch.float32, torch.bfloat16) else torch.float32)
+
+
+def deco_weight(uk: torch.Tensor, w1: torch.Tensor) -> torch.Tensor:
+    """K5: effective weight uk (uk^T W) = (U V)^T, [out, in] (F:348, D:429)."""
+    out_f, k = uk.shape
+    in_f = w1.shape[1]
+    return gemm(uk, False, w1, True, out_f, in_f, k,
+                out_dtype=w1.dtype if w1.dtype in (torch.float32, torch.bfloat16) else torch.float32)
+
+
+def linear_nt(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+              out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """K0 / plain linear: y = x W^T (+ b); x [N, in], W [out, in] (both K-major)."""
+    n_rows, in_f = x.shape
+    return gemm(x, False, weight, False, n_rows, weight.shape[0], in_f,
+                out_dtype=out_dtype or (x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32),
+                bias=bias)

@@ -1,0 +1,90 @@
+"""Glue helpers with the semantics of the reference's src/ptdeco/utils/common.py (U/c)."""
+from __future__ import annotations
+
+import gc
+import logging
+from typing import Any, TypeVar
+
+import torch
+
+__all__ = [
+    "to_device",
+    "get_gpu_reserved_memory_gb",
+    "free_gpu_reserved_memory",
+    "get_num_params",
+    "is_compound_module",
+    "get_type_name",
+    "get_default_device",
+    "split_module_parent_child_name",
+    "replace_submodule_in_place",
+]
+
+logger = logging.getLogger("ptdeco.utils.common")
+
+T = TypeVar("T", torch.Tensor, dict)
+
+
+def to_device(o: T, device: torch.device) -> T:
+    """U/c:25-36: tensors move, dict values that are tensors move, anything else is a ValueError."""
+    if isinstance(o, torch.Tensor):
+        return o.to(device)
+    if isinstance(o, dict):
+        return {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in o.items()}
+    raise ValueError(f"Unsupported type {type(o)}")
+
+
+def get_gpu_reserved_memory_gb() -> float:
+    """U/c:39-43: summed over all visible devices."""
+    total = 0
+    for i in range(torch.cuda.device_count()):
+        total += torch.cuda.memory_reserved(device=i)
+    return total / (1024.0 ** 3)
+
+
+def free_gpu_reserved_memory() -> None:
+    """U/c:46-55."""
+    if not torch.cuda.is_available():
+        return
+    before = get_gpu_reserved_memory_gb()
+    gc.collect()
+    torch.cuda.empty_cache()
+    after = get_gpu_reserved_memory_gb()
+    logger.info(f"GPU memory: {before:.2f} -> {after:.2f} GB ({(after - before):.2f} GB)")
+
+
+def get_num_params(m: torch.nn.Module, only_trainable: bool = False) -> int:
+    """U/c:58-63: parameters de-duplicated by storage pointer (tied weights count once)."""
+    seen: dict[int, torch.nn.Parameter] = {}
+    for p in m.parameters():
+        if only_trainable and not p.requires_grad:
+            continue
+        seen[p.data_ptr()] = p
+    return sum(p.numel() for p in seen.values())
+
+
+def is_compound_module(m: torch.nn.Module) -> bool:
+    return next(m.children(), None) is not None
+
+
+def get_type_name(o: Any) -> str:
+    t = type(o)
+    return f"{t.__module__}.{t.__name__}"
+
+
+def get_default_device(module: torch.nn.Module) -> torch.device:
+    """U/c:75-80: device of the first parameter, cpu for parameter-less modules."""
+    for p in module.parameters():
+        return p.device
+    return torch.device("cpu")
+
+
+def split_module_parent_child_name(target: str) -> tuple[str, str]:
+    parent, _, child = target.rpartition(".")
+    return parent, child
+
+
+def replace_submodule_in_place(root_module: torch.nn.Module, submodule_name: str,
+                               new_submodule: torch.nn.Module) -> None:
+    """U/c:88-93: setattr on the parent (AttributeError from get_submodule on bad names)."""
+    parent_name, child_name = split_module_parent_child_name(submodule_name)
+    setattr(root_module.get_submodule(parent_name), child_name, new_submodule)

@@ -189,6 +189,10 @@ def main() -> None:
     rec("syrk_bf16_d4096_t128", "syrk", dict(n=8192, d=4096, time=True, dbg={"0": 128}))
     rec("syrk_f32_d4096", "syrk", dict(n=8192, d=4096, dtype="f32", time=True))
     rec("syrk_bf16_d14336", "syrk", dict(n=8192, d=14336, time=True, steps=1))
+    rec("syrk_bf16_d4096_n2048", "syrk", dict(n=2048, d=4096, time=True))
+    rec("syrk_bf16_d1024_n2048", "syrk", dict(n=2048, d=1024, time=True))
+    rec("syrk_bf16_d8192", "syrk", dict(n=8192, d=8192, time=True, steps=1))
+    rec("syrk_bf16_d14336_chunk1e6", "syrk", dict(n=8192, d=14336, time=True, steps=1, dbg={"6": 1000000}))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "gemm_check.json"), "w") as f:
         json.dump(results, f, indent=1)
