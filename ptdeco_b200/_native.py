@@ -44,6 +44,14 @@ SIGNATURES = {
         [c_void_p, c_int, c_int, c_ll, c_void_p, c_int, c_int, c_ll, c_int, c_int, c_int, c_float,
          c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p, c_size_t, c_void_p],
     ),
+    "ptdeco_eigh_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "ptdeco_eigh": (
+        c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_ll, c_void_p, c_size_t, c_void_p]),
+    "ptdeco_lowrank_workspace_bytes": (c_size_t, [c_int, c_ll, c_int, c_int, c_int]),
+    "ptdeco_lowrank_forward": (
+        c_int,
+        [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_ll,
+         c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "ptdeco_nsr_workspace_bytes": (c_size_t, [c_ll]),
     "ptdeco_nsr_metric": (
         c_int,

@@ -1,0 +1,149 @@
+"""Capture wrappers shared by falor and dwain (reference: F:29-153, D:19-144).
+
+A wrapper stands in for the target layer while it is analysed: it remembers the last input (the
+reference's contract, `get_last_input`), optionally the last output (what the covariance kernel
+consumes directly, so the projection y = x W^T is not recomputed outside the model), exposes the
+2-D weight, and builds the two-factor replacement module.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+
+class WrappedModule(torch.nn.Module):
+    """Method table of the reference's WrappedFALORModule / WrappedDWAINModule (F:29-48, D:19-38)."""
+
+    def __init__(self) -> None:
+        super().__init__()
+        self.input = torch.zeros(size=(0,))
+        self.output: Optional[torch.Tensor] = None
+        self.capture_output = False
+
+    def get_weight_copy(self) -> torch.Tensor:
+        raise NotImplementedError()
+
+    def set_weight(self, weights: torch.Tensor) -> None:
+        raise NotImplementedError()
+
+    def get_last_input(self) -> torch.Tensor:
+        raise NotImplementedError()
+
+    def get_orig_module(self) -> torch.nn.Module:
+        raise NotImplementedError()
+
+    def get_decomposed_module(self, u: torch.Tensor, v: torch.Tensor) -> torch.nn.Module:
+        raise NotImplementedError()
+
+    # --- additions over the reference's table -----------------------------------------------
+    def get_bias(self) -> Optional[torch.Tensor]:
+        return self.get_orig_module().bias
+
+    def get_last_output_rows(self) -> torch.Tensor:
+        """Last layer output as [N, out] rows (bias still included)."""
+        raise NotImplementedError()
+
+
+class WrappedLinear(WrappedModule):
+    def __init__(self, lin_orig: torch.nn.Module, name: Optional[str] = None):
+        super().__init__()
+        assert isinstance(lin_orig, torch.nn.Linear)
+        self.lin_orig = lin_orig
+        self.name = name
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        self.input = x
+        y = self.lin_orig(x)
+        if self.capture_output:
+            self.output = y
+        return y
+
+    def get_weight_copy(self) -> torch.Tensor:
+        return self.lin_orig.weight.detach().clone()
+
+    def set_weight(self, weights: torch.Tensor) -> None:
+        self.lin_orig.weight.copy_(weights)
+
+    def get_last_input(self) -> torch.Tensor:
+        return self.input.reshape(-1, self.lin_orig.in_features)
+
+    def get_last_output_rows(self) -> torch.Tensor:
+        assert self.output is not None, "no forward pass captured"
+        return self.output.reshape(-1, self.lin_orig.out_features)
+
+    def get_orig_module(self) -> torch.nn.Module:
+        return self.lin_orig
+
+    def get_decomposed_module(self, u: torch.Tensor, v: torch.Tensor) -> torch.nn.Module:
+        """u = W1 [k, in], v = W2 [out, k] -> Sequential(Linear(in->k, no bias), Linear(k->out, bias))
+        (F:76-95, D:66-85); the second layer carries the original bias."""
+        use_bias = self.lin_orig.bias is not None
+        k = u.shape[0]
+        lin_1 = torch.nn.Linear(self.lin_orig.in_features, k, bias=False)
+        lin_2 = torch.nn.Linear(k, self.lin_orig.out_features, bias=use_bias)
+        lin_1.weight.data = u.detach().contiguous()
+        lin_2.weight.data = v.detach().contiguous()
+        if use_bias:
+            lin_2.bias.data = self.lin_orig.bias.detach().clone()
+        return torch.nn.Sequential(lin_1, lin_2)
+
+
+class WrappedConv2d1x1(WrappedModule):
+    def __init__(self, conv_orig: torch.nn.Module, name: Optional[str] = None):
+        super().__init__()
+        assert (isinstance(conv_orig, torch.nn.Conv2d) and conv_orig.kernel_size[0] == 1
+                and conv_orig.kernel_size[1] == 1 and conv_orig.groups == 1)
+        self.conv_orig = conv_orig
+        self.name = name
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        self.input = x
+        y = self.conv_orig(x)
+        if self.capture_output:
+            self.output = y
+        return y
+
+    def get_weight_copy(self) -> torch.Tensor:
+        return self.conv_orig.weight.detach().data[..., 0, 0].clone()
+
+    def set_weight(self, weights: torch.Tensor) -> None:
+        self.conv_orig.weight.copy_(weights[:, :, None, None])
+
+    def get_last_input(self) -> torch.Tensor:
+        return self.input.permute(0, 2, 3, 1).reshape(-1, self.conv_orig.in_channels)
+
+    def get_last_output_rows(self) -> torch.Tensor:
+        assert self.output is not None, "no forward pass captured"
+        return self.output.permute(0, 2, 3, 1).reshape(-1, self.conv_orig.out_channels)
+
+    def get_orig_module(self) -> torch.nn.Module:
+        return self.conv_orig
+
+    def get_decomposed_module(self, u: torch.Tensor, v: torch.Tensor) -> torch.nn.Module:
+        """Two 1x1 convs built with default stride/padding/dilation, exactly like the reference
+        (F:128-153, D:118-144) -- a strided 1x1 target therefore changes shape, as it does there."""
+        use_bias = self.conv_orig.bias is not None
+        k = u.shape[0]
+        conv_1 = torch.nn.Conv2d(self.conv_orig.in_channels, k, kernel_size=1, bias=False)
+        conv_2 = torch.nn.Conv2d(k, self.conv_orig.out_channels, kernel_size=1, bias=use_bias)
+        conv_1.weight.data = u.detach()[:, :, None, None].contiguous()
+        conv_2.weight.data = v.detach()[:, :, None, None].contiguous()
+        if use_bias:
+            conv_2.bias.data = self.conv_orig.bias.detach().clone()
+        return torch.nn.Sequential(conv_1, conv_2)
+
+
+def is_decomposeable_module(module: torch.nn.Module) -> bool:
+    """F:402-408 / D:540-546: any nn.Linear (subclasses included) or a 1x1, groups=1 Conv2d."""
+    return isinstance(module, torch.nn.Linear) or (
+        isinstance(module, torch.nn.Conv2d) and module.kernel_size[0] == 1
+        and module.kernel_size[1] == 1 and module.groups == 1)
+
+
+def is_num_params_reduced(proportion: float, in_features: int, out_features: int) -> bool:
+    """F:273-281 / D:569-577."""
+    baseline = in_features * out_features
+    original_rank = min(in_features, out_features)
+    proposed = (in_features + out_features) * proportion * original_rank
+    return proposed < baseline

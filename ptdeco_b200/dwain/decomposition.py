@@ -1,0 +1,520 @@
+"""dwain (Decomposing Weights Algorithm - an Iterative techNique) on the sm_100a kernels.
+
+Drop-in for the reference's src/ptdeco/dwain/decomposition.py (cited as D:line): same public
+entry points, same private primitives the reference's tests import (`_wrap_in_place`,
+`_unwrap_in_place`, `_compute_covariance_matrix_decomposition`), reversed layer order, geometric
+rank descent where the smallest accepted rank wins, optional one-pass covariance precompute in
+splits, per-layer `finetune_fn`, same `decompose_config`.
+
+  D:152      Eyyt += einsum(y, y) / N          -> tcgen05 SYRK, fp32 accumulation of exact bf16
+                                                  products (the reference rounds each per-step
+                                                  product to bf16 for bf16 models)
+  D:158-162  damping + torch.linalg.eigh       -> ptdeco_cov_finalize + ptdeco_eigh (top-k)
+  D:193-204  CovarianceComputingLinearModule   -> layer forward on the tcgen05 GEMM engine + SYRK
+  D:427-429  U = W^T uk ; (U V)^T              -> ptdeco_gemm
+  D:269-277  NSR on logits                     -> ptdeco_nsr_metric
+
+Multi-GPU: when torch.distributed is initialised the calibration steps are sharded over ranks and
+only the d x d fp32 covariances cross NVLink (ptdeco_b200.parallel). CUDA only; no CPU path.
+"""
+from __future__ import annotations
+
+import collections.abc
+import logging
+import time
+from typing import Any, Optional
+
+import torch
+
+from .. import _native as nat
+from .. import _wrap, linalg, parallel, utils
+
+__all__ = ["decompose_in_place", "is_decomposeable_module"]
+
+EIGEN_DAMPEN_FACTOR = 0.01  # D:14
+
+logger = logging.getLogger("ptdeco.dwain.decomposition")
+
+
+class WrappedDWAINModule(_wrap.WrappedModule):
+    pass
+
+
+class WrappedDWAINLinear(_wrap.WrappedLinear, WrappedDWAINModule):
+    pass
+
+
+class WrappedDWAINConv2d1x1(_wrap.WrappedConv2d1x1, WrappedDWAINModule):
+    pass
+
+
+is_decomposeable_module = _wrap.is_decomposeable_module
+_is_num_params_reduced = _wrap.is_num_params_reduced
+
+
+def _max_rank_consumed(dim_in: int, dim_out: int, reduction_factor: float) -> int:
+    """Largest rank the descent of D:407-408 can ask for: int(full_rank * reduction_factor)."""
+    full_rank = min(dim_in, dim_out)
+    return max(1, min(full_rank, int(full_rank * reduction_factor)))
+
+
+def _update_Eyyt_in_place(acc: linalg.CovarianceAccumulator, y_reshaped: torch.Tensor,
+                          sub: Optional[torch.Tensor] = None) -> None:
+    """D:147-152: Eyyt += y^T y / N for one batch of rows."""
+    acc.update(y_reshaped, sub=sub)
+
+
+def _get_eigenvectors(acc: linalg.CovarianceAccumulator, num_vectors: Optional[int] = None,
+                      group=None) -> torch.Tensor:
+    """D:155-163 on the accumulated covariance: /steps, damping 0.01*mean(diag), eigenvectors
+    ascending (all, or the last `num_vectors`). With a process group the partial covariances are
+    summed over ranks first."""
+    parallel.allreduce_accumulator(acc, group)
+    cov = acc.finalize(use_mean=False, damp_factor=EIGEN_DAMPEN_FACTOR)
+    _, u = linalg.eigh(cov, k=num_vectors)
+    return u
+
+
+class CovarianceComputingLinearModule(torch.nn.Module):
+    """D:166-208: stands in for a target Linear during the precompute pass; its forward IS the
+    layer forward (y = x W^T on the tcgen05 GEMM engine) and folds y into the covariance."""
+
+    def __init__(self, weight: torch.nn.Parameter, bias: Optional[torch.nn.Parameter],
+                 decompose_in_float64: bool):
+        super().__init__()
+        self.weight = weight
+        self.bias = bias
+        self.in_features = weight.shape[1]
+        self.out_features = weight.shape[0]
+        self.acc = linalg.CovarianceAccumulator(self.out_features, weight.device)
+        self.use_float64 = decompose_in_float64  # accepted; see falor's use_float64 note
+
+    @property
+    def num_data_steps(self) -> int:
+        return self.acc.steps
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        rows = x.reshape(-1, self.in_features)
+        y_rows = linalg.linear_nt(rows, self.weight.detach())
+        _update_Eyyt_in_place(self.acc, y_rows)
+        y = y_rows.reshape(*x.shape[:-1], self.out_features)
+        if self.bias is not None:
+            y = y + self.bias
+        return y
+
+    def get_eigenvectors(self, num_vectors: Optional[int] = None, group=None) -> torch.Tensor:
+        """Unlike D:206-208 the result stays on the GPU in fp32 (180 GB of HBM make the reference's
+        round trip through host memory unnecessary); the rank search casts what it slices."""
+        return _get_eigenvectors(self.acc, num_vectors, group)
+
+
+def _compute_covariance_matrix_decomposition(
+    *,
+    root_module: torch.nn.Module,
+    decomposed_submodule_name: str,
+    data_iterator: collections.abc.Iterator[dict[str, torch.Tensor]],
+    weight: torch.Tensor,
+    num_data_steps: int,
+    device: torch.device,
+    decompose_in_float64: bool,
+    num_vectors: Optional[int] = None,
+) -> torch.Tensor:
+    """D:211-244: per-layer calibration (num_data_steps full forwards) -> eigenvectors."""
+    root_module.eval()
+    wrapper = root_module.get_submodule(decomposed_submodule_name)
+    assert isinstance(wrapper, WrappedDWAINModule)
+    logger.info("Using float64 for decomposition" if decompose_in_float64
+                else "Using float32 for decomposition")
+    acc = linalg.CovarianceAccumulator(weight.shape[0], device)
+    wrapper.capture_output = True
+    try:
+        for _ in range(num_data_steps):
+            inputs = utils.to_device(next(data_iterator), device)
+            _ = root_module(inputs)
+            _update_Eyyt_in_place(acc, wrapper.get_last_output_rows(), sub=wrapper.get_bias())
+    finally:
+        wrapper.capture_output = False
+        wrapper.output = None
+    return _get_eigenvectors(acc, num_vectors)
+
+
+def _compute_metrics(
+    *,
+    input_dict: dict[str, torch.Tensor],
+    root_module: torch.nn.Module,
+    decomposed_submodule: torch.nn.Module,
+    orig_weight: torch.Tensor,
+    deco_weight: torch.Tensor,
+    loss_fn: collections.abc.Callable[[dict[str, torch.Tensor], torch.Tensor], torch.Tensor],
+) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """D:247-278."""
+    assert isinstance(input_dict, dict)
+    assert isinstance(decomposed_submodule, WrappedDWAINModule)
+    root_module.eval()
+    decomposed_submodule.set_weight(deco_weight)
+    y_deco = root_module(input_dict)
+    decomposed_submodule.set_weight(orig_weight)
+    y_orig = root_module(input_dict)
+    loss_deco = loss_fn(input_dict, y_deco)
+    loss_orig = loss_fn(input_dict, y_orig)
+    nsr_final = utils.calc_per_channel_noise_to_signal_ratio(
+        y=y_orig, x=y_deco, non_channel_dim=(0, 1), mode="mean")
+    ppl_deco = torch.exp(loss_deco).mean()
+    ppl_orig = torch.exp(loss_orig).mean()
+    return nsr_final, ppl_deco, ppl_orig
+
+
+def _wrap_in_place(root_module: torch.nn.Module, decomposed_submodule_name: str) -> None:
+    """D:281-304."""
+    sub = root_module.get_submodule(decomposed_submodule_name)
+    if isinstance(sub, torch.nn.Linear):
+        wrapped: WrappedDWAINModule = WrappedDWAINLinear(sub, decomposed_submodule_name)
+    elif is_decomposeable_module(sub):
+        wrapped = WrappedDWAINConv2d1x1(sub, decomposed_submodule_name)
+    else:
+        raise ValueError(f"Cannot decompose {decomposed_submodule_name}={sub}")
+    utils.replace_submodule_in_place(root_module, decomposed_submodule_name, wrapped)
+
+
+def _unwrap_in_place(root_module: torch.nn.Module, decomposed_submodule_name: str) -> None:
+    """D:307-316."""
+    sub = root_module.get_submodule(decomposed_submodule_name)
+    assert isinstance(sub, WrappedDWAINModule)
+    utils.replace_submodule_in_place(root_module, decomposed_submodule_name, sub.get_orig_module())
+
+
+def _get_params_for_proportion(proportion: float, in_features: int, out_features: int) -> int:
+    """D:319-330 (int() truncation included)."""
+    baseline = in_features * out_features
+    original_rank = min(in_features, out_features)
+    proposed = (in_features + out_features) * proportion * original_rank
+    return int(proposed) if proposed < baseline else baseline
+
+
+def _process_module(
+    *,
+    root_module: torch.nn.Module,
+    decomposed_submodule_name: str,
+    data_iterator: collections.abc.Iterator[dict[str, torch.Tensor]],
+    loss_fn: collections.abc.Callable[[dict[str, torch.Tensor], torch.Tensor], torch.Tensor],
+    nsr_final_threshold: float,
+    num_data_steps: int,
+    num_metric_steps: int,
+    device: torch.device,
+    metric_iterator: collections.abc.Iterator[dict[str, torch.Tensor]],
+    num_params: int,
+    min_rank: int = 32,
+    trade_off_factor: float,
+    reduction_factor: float,
+    max_accepted_ppl_diff: float,
+    decompose_in_float64: bool = True,
+    u_matrix: Optional[torch.Tensor] = None,
+    trace: Optional[list] = None,
+) -> dict[str, Any]:
+    """D:333-537."""
+    indent = "    "
+    target = root_module.get_submodule(decomposed_submodule_name)
+    orig_device = target.weight.device
+    orig_dtype = target.weight.dtype
+    decomposed_type = utils.get_type_name(target)
+    _wrap_in_place(root_module, decomposed_submodule_name)
+    wrapper = root_module.get_submodule(decomposed_submodule_name)
+    assert isinstance(wrapper, WrappedDWAINModule)
+    orig_weight = wrapper.get_weight_copy()
+    nat.require_cuda(orig_weight, f"weight of {decomposed_submodule_name}")
+    dim_out, dim_in = orig_weight.shape
+    full_rank = min(dim_in, dim_out)
+    msg_prefix = f"Processing {decomposed_submodule_name}:"
+
+    if full_rank == 1:
+        _unwrap_in_place(root_module, decomposed_submodule_name)
+        logger.info(f"{msg_prefix} Module has rank 1, not decomposing")
+        return {"proportion": 1.0, "nsr_final": 0.0, "ppl_final": 0.0, "decomposed_module": None}
+
+    logger.info(f"{msg_prefix} {decomposed_type} weight_shape={tuple(orig_weight.shape)} "
+                f"{orig_weight.dtype}")
+    logger.info(f"{msg_prefix} {nsr_final_threshold=:.4f} {max_accepted_ppl_diff=:.4f}")
+
+    if u_matrix is not None:
+        logger.info(f"Using pre-computed u_matrix, {u_matrix.dtype=}")
+    else:
+        u_matrix = _compute_covariance_matrix_decomposition(
+            root_module=root_module, decomposed_submodule_name=decomposed_submodule_name,
+            data_iterator=data_iterator, weight=orig_weight, num_data_steps=num_data_steps,
+            device=device, decompose_in_float64=decompose_in_float64,
+            num_vectors=_max_rank_consumed(dim_in, dim_out, reduction_factor))
+        logger.info(f"Computed u_matrix, {u_matrix.dtype=}")
+
+    def factors(rank: int) -> tuple[torch.Tensor, torch.Tensor]:
+        """uk [out, k] and W1 = uk^T W [k, in], both in the weight dtype like D:423-428."""
+        uk = u_matrix[:, u_matrix.shape[1] - rank:].to(orig_dtype).to(device)
+        return uk, linalg.factor_w1(orig_weight, uk)
+
+    tried = False
+    i = 1
+    rank_best = full_rank
+    rank_new = full_rank
+    nsr_best, ppl_deco_best = 0.0, 0.0
+    while rank_new > min_rank:
+        rank_new = int(rank_new * reduction_factor)
+        previous_params = _get_params_for_proportion(1.0, dim_in, dim_out)
+        current_params = _get_params_for_proportion(rank_new / full_rank, dim_in, dim_out)
+        drop_in_params = previous_params - current_params
+        fraction_removed = drop_in_params / num_params
+        ppl_diff_threshold = fraction_removed * trade_off_factor
+        if drop_in_params == 0:
+            logger.info(f"{indent}{i=} {rank_new=} does not lead to params drop, skipping")
+            continue
+
+        uk, w1 = factors(rank_new)
+        deco_weight = linalg.deco_weight(uk, w1).to(orig_dtype)
+        tried = True
+
+        acc = torch.zeros(3, dtype=torch.float64, device=orig_device)
+        ppl_orig_sample = None
+        for _ in range(num_metric_steps):
+            input_dict = utils.to_device(next(metric_iterator), device)
+            nsr_sample, ppl_deco_sample, ppl_orig_sample = _compute_metrics(
+                input_dict=input_dict, root_module=root_module, decomposed_submodule=wrapper,
+                orig_weight=orig_weight, deco_weight=deco_weight, loss_fn=loss_fn)
+            ppl_diff_sample = (ppl_deco_sample - ppl_orig_sample) / ppl_orig_sample
+            acc += torch.stack([ppl_diff_sample.double(), nsr_sample.double(),
+                                ppl_deco_sample.double()])
+        acc = parallel.mean_over_ranks(acc / num_metric_steps, None)
+        ppl_diff_new, nsr_new, ppl_deco_new = acc.tolist()  # the one host sync of the trial
+
+        logger.info(f"{indent}{i=} {ppl_deco_new=:.4f} {ppl_diff_new=:.4f} "
+                    f"{ppl_diff_threshold=:.4f} {fraction_removed=:.4f} {nsr_new=:.4f}")
+        reject = f"{indent}{i=} REJECTING rank {rank_new}/{full_rank}"
+        accepted = False
+        if ppl_diff_new >= ppl_diff_threshold:
+            logger.info(f"{reject} {ppl_diff_new=:.2f} >= {ppl_diff_threshold=:.2f}")
+        elif ppl_diff_new >= max_accepted_ppl_diff:
+            logger.info(f"{reject} {ppl_diff_new=:.3f} >= {max_accepted_ppl_diff:.3f}")
+        elif nsr_new >= nsr_final_threshold:
+            logger.info(f"{reject} {nsr_new=:.4f} >= {nsr_final_threshold=:.4f}")
+        else:
+            accepted = True
+            rank_best, nsr_best, ppl_deco_best = rank_new, nsr_new, ppl_deco_new
+            logger.info(f"{indent}{i=} ACCEPTING rank {rank_best}/{full_rank}")
+        if trace is not None:
+            trace.append({"name": decomposed_submodule_name, "rank": rank_new, "nsr": nsr_new,
+                          "ppl_diff": ppl_diff_new, "ppl_deco": ppl_deco_new,
+                          "ppl_diff_threshold": ppl_diff_threshold, "accepted": accepted})
+        logger.info(f"{indent}{i=} {rank_new=}/{full_rank} {nsr_new=:.6f} {ppl_diff_new=:.6f}  "
+                    f"{rank_best=} {nsr_best=:.6f} {ppl_deco_best=:.6f}")
+        logger.info(f"{indent}---")
+        i += 1
+
+    wrapper.set_weight(orig_weight)
+    decompose_decision = False
+    proportion = 1.0
+    if tried:
+        proportion = rank_best / full_rank
+        logger.info(f"{indent}i=FINAL rank={rank_best}/{full_rank} {proportion=:.4f} "
+                    f"nsr={nsr_best:.6f} ppl={ppl_deco_best:.6f}")
+        decompose_decision = _is_num_params_reduced(proportion, dim_in, dim_out)
+        if not decompose_decision:
+            logger.info(f"{indent}{proportion=:.4f} leads to num param increase, not decomposing")
+
+    if tried and full_rank != rank_best and decompose_decision:
+        uk, w1 = factors(rank_best)  # rebuilt at rank_best (D:507-511)
+        new_module = wrapper.get_decomposed_module(u=w1, v=uk)
+        new_module.to(orig_device)
+        new_module.to(orig_dtype)
+        drop_in_params = (_get_params_for_proportion(1.0, dim_in, dim_out)
+                          - _get_params_for_proportion(proportion, dim_in, dim_out))
+    else:
+        proportion, nsr_best, ppl_deco_best, drop_in_params, new_module = 1.0, 0.0, 0.0, 0, None
+        logger.info(f"{msg_prefix} Skipping module decomposition")
+        _unwrap_in_place(root_module, decomposed_submodule_name)
+
+    return {"proportion": proportion, "nsr_final": nsr_best, "ppl_final": ppl_deco_best,
+            "drop_in_params": drop_in_params, "decomposed_module": new_module}
+
+
+def _get_decomposeable_submodule_names(module: torch.nn.Module,
+                                       blacklisted_module_names: list[str]) -> list[str]:
+    """D:549-559."""
+    res = []
+    for name, mod in module.named_modules():
+        if is_decomposeable_module(mod):
+            if name in blacklisted_module_names:
+                logger.info(f"Skipping blacklisted module {name}")
+            else:
+                res.append(name)
+    return res
+
+
+def _add_meta_to_module_config(module_config: dict[str, Any], module_deco_results: dict[str, Any]) -> None:
+    """D:562-566."""
+    module_config[utils.MODCONFIG_META_KEY] = {
+        k: v for k, v in module_deco_results.items() if k != "decomposed_module"}
+
+
+def _precompute_covariance_matrix_decompositions(
+    *,
+    module: torch.nn.Module,
+    submodule_names: list[str],
+    num_data_steps: int,
+    data_iterator: collections.abc.Iterator[dict[str, torch.Tensor]],
+    device: torch.device,
+    decompose_in_float64: bool,
+    reduction_factor: float = 1.0,
+    group=None,
+) -> dict[str, torch.Tensor]:
+    """D:580-633: one set of num_data_steps forwards updates the covariances of every listed
+    Linear at once. With a process group, rank r only runs the steps i = r (mod world) -- every
+    rank still draws all num_data_steps batches, so iterator positions stay those of the
+    reference -- partial covariances are summed over NVLink, and the eigensolves are distributed
+    round-robin with the owners broadcasting their top-k blocks."""
+    originals = {}
+    for name in submodule_names:
+        old = module.get_submodule(name)
+        if not isinstance(old, torch.nn.Linear):
+            # the reference crashes here on 1x1 convs (D:194 with a 4-D weight)
+            raise ValueError(f"covariance precompute supports Linear targets only, got {name}={old}")
+        originals[name] = old
+        logger.info(f"Replacing {name} by covariance computing wrapper")
+        utils.replace_submodule_in_place(
+            module, name, CovarianceComputingLinearModule(old.weight, old.bias, decompose_in_float64))
+
+    module.eval()
+    rank, world = parallel.rank_and_world(group)
+    with torch.no_grad():
+        for step in range(num_data_steps):
+            batch = next(data_iterator)
+            if step % world != rank:
+                continue
+            _ = module(utils.to_device(batch, device))
+    utils.free_gpu_reserved_memory()
+
+    logger.info("Computing eigenvectors ...")
+    u_dict: dict[str, torch.Tensor] = {}
+    for idx, name in enumerate(submodule_names):
+        sub = module.get_submodule(name)
+        k = _max_rank_consumed(sub.in_features, sub.out_features, reduction_factor)
+        u_dict[name] = parallel.owner_computes(
+            idx, group, lambda: sub.get_eigenvectors(k, group=None), sub.acc, (sub.out_features, k))
+    for name in submodule_names:
+        logger.info(f"Replacing {name} by original linear")
+        utils.replace_submodule_in_place(module, name, originals[name])
+    utils.free_gpu_reserved_memory()
+    return u_dict
+
+
+def _precompute_covariance_matrix_decompositions_in_splits(
+    *,
+    module: torch.nn.Module,
+    modules_to_decompose: list[str],
+    num_splits: int,
+    num_data_steps: int,
+    data_iterator: collections.abc.Iterator[dict[str, torch.Tensor]],
+    device: torch.device,
+    decompose_in_float64: bool,
+    reduction_factor: float = 1.0,
+    group=None,
+) -> dict[str, torch.Tensor]:
+    """D:636-674: chunks of len // num_splits names, plus one more partition for the remainder."""
+    chunk_size = len(modules_to_decompose) // num_splits
+    if chunk_size == 0:
+        chunk_size = 1
+        num_splits = len(modules_to_decompose)
+    num_partitions = num_splits if len(modules_to_decompose) % num_splits == 0 else num_splits + 1
+    u_dict: dict[str, torch.Tensor] = {}
+    for p in range(num_partitions):
+        sublist = modules_to_decompose[p * chunk_size:(p + 1) * chunk_size]
+        logger.info(f"Pre computing covariance matrices for {len(sublist)} modules")
+        u_dict.update(_precompute_covariance_matrix_decompositions(
+            module=module, submodule_names=sublist, num_data_steps=num_data_steps,
+            data_iterator=data_iterator, device=device, decompose_in_float64=decompose_in_float64,
+            reduction_factor=reduction_factor, group=group))
+    assert len(u_dict) == len(modules_to_decompose)
+    return u_dict
+
+
+def decompose_in_place(
+    *,
+    module: torch.nn.Module,
+    device: torch.device,
+    data_iterator: collections.abc.Iterator[dict[str, torch.Tensor]],
+    loss_fn: collections.abc.Callable[[dict[str, torch.Tensor], torch.Tensor], torch.Tensor],
+    num_data_steps: int,
+    metric_iterator: collections.abc.Iterator[dict[str, torch.Tensor]],
+    num_metric_steps: int,
+    blacklisted_module_names: Optional[list[str]] = None,
+    nsr_final_threshold: float,
+    finetune_fn: collections.abc.Callable[[torch.nn.Module, torch.device, list[str]], torch.nn.Module],
+    min_rank: int = 32,
+    trade_off_factor: float = 0.5,
+    reduction_factor: float = 0.5,
+    max_accepted_ppl_diff: float = 0.1,
+    decompose_in_float64: bool = True,
+    precomputing_covariance_num_splits: Optional[int] = None,
+    trace: Optional[list] = None,
+) -> dict[str, Any]:
+    """D:677-800. Returns the decompose_config (insertion order = reversed module order)."""
+    start_time = time.perf_counter()
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise nat.NativeError("ptdeco_b200.dwain runs on CUDA (sm_100a) only; there is no CPU path")
+    nat.lib()
+    num_params = utils.get_num_params(module)
+    current_params = num_params
+    if blacklisted_module_names is None:
+        blacklisted_module_names = []
+    names = _get_decomposeable_submodule_names(module, blacklisted_module_names)
+    n = len(names)
+    n_decomposed = 0
+    logger.info("\n".join([f"There are {n} linear modules that can be decomposed:"]
+                          + [f"  {i}. {nm}" for i, nm in enumerate(names, start=1)]))
+
+    decompose_config: dict[str, Any] = {}
+    decomposed_submodules: list[str] = []
+    group = parallel.default_group()
+
+    if precomputing_covariance_num_splits is not None and precomputing_covariance_num_splits > 0:
+        u_dict = _precompute_covariance_matrix_decompositions_in_splits(
+            module=module, modules_to_decompose=names,
+            num_splits=precomputing_covariance_num_splits, data_iterator=data_iterator,
+            num_data_steps=num_data_steps, device=device,
+            decompose_in_float64=decompose_in_float64, reduction_factor=reduction_factor,
+            group=group)
+    else:
+        logger.info("Skipping precomputing convariance matrices")
+        u_dict = {}
+    utils.free_gpu_reserved_memory()
+
+    for i, name in enumerate(reversed(names), start=1):
+        logger.info(f"PROCESSING {name} MODULE {i} OUT OF {n}")
+        with torch.no_grad():
+            logger.info(f"start reserved gpu mem={utils.get_gpu_reserved_memory_gb():.2f} GB")
+            result = _process_module(
+                root_module=module, decomposed_submodule_name=name, data_iterator=data_iterator,
+                loss_fn=loss_fn, metric_iterator=metric_iterator,
+                nsr_final_threshold=nsr_final_threshold, num_data_steps=num_data_steps,
+                num_metric_steps=num_metric_steps, device=device, num_params=num_params,
+                trade_off_factor=trade_off_factor, reduction_factor=reduction_factor,
+                max_accepted_ppl_diff=max_accepted_ppl_diff, min_rank=min_rank,
+                decompose_in_float64=decompose_in_float64,
+                u_matrix=u_dict.pop(name) if len(u_dict) > 0 else None, trace=trace)
+            logger.info(f"stop reserved gpu mem={utils.get_gpu_reserved_memory_gb():.2f} GB")
+        current_params -= result.get("drop_in_params", 0)
+        logger.info(f"CURRENT PARAMS IN M: {current_params / 1e6}")
+        new_module = result["decomposed_module"]
+        proportion = result["proportion"]
+        if new_module is not None:
+            decomposed_submodules.append(name)
+            utils.replace_submodule_in_place(module, name, new_module)
+            module = finetune_fn(module, device, decomposed_submodules)
+            utils.free_gpu_reserved_memory()
+            module_config = utils.get_module_config(new_module)
+            _add_meta_to_module_config(module_config, result)
+            decompose_config[name] = module_config
+            logger.info(f"{name} decomposed with rank {proportion=:.4f}")
+            n_decomposed += 1
+        utils.free_gpu_reserved_memory()
+
+    logger.info(f"Decomposed {n_decomposed} out of {n} modules")
+    logger.info(f"Decomposition took {time.perf_counter() - start_time:.1f} seconds")
+    return decompose_config

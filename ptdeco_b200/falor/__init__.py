@@ -1,0 +1,3 @@
+"""falor method (reference: src/ptdeco/falor/__init__.py)."""
+from .decomposition import *  # noqa: F401,F403
+from .decomposition import __all__  # noqa: F401

@@ -75,23 +75,31 @@ class CovarianceAccumulator:
         return self.C
 
 
-def eigh(cov: torch.Tensor, overwrite: bool = False) -> tuple[torch.Tensor, torch.Tensor]:
-    """Symmetric eigendecomposition (K3), ascending eigenvalues, eigenvectors in columns — the
-    layout of torch.linalg.eigh that the reference consumes (F:207, D:162)."""
+def eigh(cov: torch.Tensor, k: Optional[int] = None) -> tuple[torch.Tensor, torch.Tensor]:
+    """Symmetric eigendecomposition (K3) in the layout of torch.linalg.eigh that the reference
+    consumes (F:207, D:162): eigenvalues ascending (all d of them), eigenvectors in columns.
+    With `k` only the eigenvectors of the k LARGEST eigenvalues are back-transformed and returned
+    as U[:, d-k:] (still ascending), which is all the rank search ever slices. `cov` is not
+    modified. fp32 in, fp32 out; the tridiagonal stage runs in fp64 on the device."""
     cov = _check_2d(cov, "cov")
     d = cov.shape[0]
     if cov.shape[1] != d:
         raise ValueError("cov must be square")
-    a = cov if (overwrite and cov.dtype == torch.float32 and cov.is_contiguous()) else cov.float().clone()
+    if cov.dtype != torch.float32:
+        cov = cov.float()
+    k = d if k is None else int(k)
+    if not 1 <= k <= d:
+        raise ValueError(f"k={k} outside [1, {d}]")
     L = nat.lib()
     evals = torch.empty(d, dtype=torch.float32, device=cov.device)
-    U = torch.empty((d, d), dtype=torch.float32, device=cov.device)
-    need = L.ptdeco_eigh_workspace_bytes(d)
+    ldu = (k + 3) // 4 * 4
+    U = torch.empty((d, ldu), dtype=torch.float32, device=cov.device)
+    need = L.ptdeco_eigh_workspace_bytes(d, k)
     ws = nat.WORKSPACE.get(cov.device, need)
     nat.check(
-        L.ptdeco_eigh(a.data_ptr(), d, a.stride(0), evals.data_ptr(), U.data_ptr(), U.stride(0),
+        L.ptdeco_eigh(cov.data_ptr(), d, cov.stride(0), k, evals.data_ptr(), U.data_ptr(), ldu,
                       ws.data_ptr(), ws.numel(), nat.stream_ptr(cov.device)), "ptdeco_eigh")
-    return evals, U
+    return evals, (U if ldu == k else U[:, :k])
 
 
 def gemm(a: torch.Tensor, a_mn_major: bool, b: torch.Tensor, b_mn_major: bool, m: int, n: int, k: int,
@@ -146,3 +154,36 @@ def linear_nt(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor
     return gemm(x, False, weight, False, n_rows, weight.shape[0], in_f,
                 out_dtype=out_dtype or (x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32),
                 bias=bias)
+
+
+def lowrank_forward(x: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor,
+                    bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K7: y = (x W1^T) W2^T + b for x [N, in], W1 [k, in], W2 [out, k] -- the forward of the
+    two-factor module the decomposition builds (F:84-95, D:74-85). bf16 inputs with k <= 256 run
+    the fused kernel that keeps the [128, k] intermediate on chip (TMEM -> shared memory); other
+    shapes run two tcgen05 GEMMs with the intermediate in workspace."""
+    x = _check_2d(x, "x")
+    w1 = _check_2d(w1, "w1")
+    w2 = _check_2d(w2, "w2")
+    n, in_f = x.shape
+    k = w1.shape[0]
+    out_f = w2.shape[0]
+    if w1.shape[1] != in_f or w2.shape[1] != k:
+        raise ValueError(f"shape mismatch x{tuple(x.shape)} W1{tuple(w1.shape)} W2{tuple(w2.shape)}")
+    dt = x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32
+    x, w1, w2 = (t if t.dtype == dt else t.to(dt) for t in (x, w1, w2))
+    y = torch.empty((n, out_f), dtype=dt, device=x.device)
+    if n == 0:
+        return y
+    if bias is not None:
+        bias = bias.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    L = nat.lib()
+    code = nat.dtype_code(x)
+    need = L.ptdeco_lowrank_workspace_bytes(code, n, in_f, k, out_f)
+    ws = nat.WORKSPACE.get(x.device, need)
+    nat.check(
+        L.ptdeco_lowrank_forward(x.data_ptr(), x.stride(0), w1.data_ptr(), w1.stride(0),
+                                 w2.data_ptr(), w2.stride(0), nat.ptr(bias), y.data_ptr(),
+                                 y.stride(0), code, n, in_f, k, out_f, ws.data_ptr(), ws.numel(),
+                                 nat.stream_ptr(x.device)), "ptdeco_lowrank_forward")
+    return y

@@ -1,0 +1,128 @@
+"""Named, seeded parity cases shared by tests/golden/make_golden.py (reference run), the oracle
+tests (CPU) and the GPU parity tests (product run): same models, same streams, same keyword
+arguments, so that the three can be compared trial by trial.
+"""
+from __future__ import annotations
+
+from typing import Any, Iterator
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import models, streams
+from .streams import DATA_SEED, MODEL_SEED, IndexedStream  # noqa: F401
+
+
+# ------------------------------------------------------------------ the reference's primitive tests
+def primitive_case(kind: str, dict_input: bool = False):
+    """tests/test_deco_primitives_{falor,dwain}.py: fin 64, fout 32, h = w = 16, bs 8, weight seed
+    271828, ONE sequential data generator seeded 1314159 (the first batch is the probe input, the
+    next eight feed the covariance). Returns (net, iterator)."""
+    fin, fout, h, w, bs = 64, 32, 16, 16, 8
+    gen = torch.Generator()
+    gen.manual_seed(MODEL_SEED)
+    torch.manual_seed(0)  # the reference draws the Linear bias from the global RNG
+    if kind == "linear":
+        net = models.PrimitiveLinearNet(fin, fout, gen, dict_input=dict_input)
+        shape = (bs, h, w, fin)
+    else:
+        net = models.PrimitiveConv1x1Net(fin, fout, gen, dict_input=dict_input)
+        shape = (bs, fin, h, w)
+
+    def it() -> Iterator:
+        g = torch.Generator()
+        g.manual_seed(DATA_SEED)
+        while True:
+            x = torch.rand(*shape, generator=g)
+            yield {"inp": x} if dict_input else x
+
+    return net, it()
+
+
+def step_spectrum_batch(n: int, d: int, index: int) -> torch.Tensor:
+    return streams.step_spectrum_activations(n, d, seed=index)
+
+
+# ------------------------------------------------------------------ falor cases
+class TinyMLP(nn.Module):
+    def __init__(self, fin=48, h1=96, h2=64, classes=10, seed=MODEL_SEED):
+        super().__init__()
+        self.fc1 = nn.Linear(fin, h1)
+        self.fc2 = nn.Linear(h1, h2)
+        self.head = nn.Linear(h2, classes)
+        models._seeded_init(self, seed)
+
+    def forward(self, x):
+        return self.head(F.gelu(self.fc2(F.gelu(self.fc1(x)))))
+
+
+def _lowrank_vectors(index: int, bs: int, dim: int, latent: int, noise: float) -> torch.Tensor:
+    gb = torch.Generator()
+    gb.manual_seed(DATA_SEED - 11)
+    basis = torch.randn(latent, dim, generator=gb) / latent ** 0.5
+    g = torch.Generator()
+    g.manual_seed(DATA_SEED + index)
+    z = torch.randn(bs, latent, generator=g) * torch.logspace(0, -1.5, latent)
+    return 3.0 * z @ basis + noise * torch.randn(bs, dim, generator=g)
+
+
+FALOR_CASES = ("mlp", "convmlp", "deit_small", "deit_tiny")
+
+
+def falor_case(name: str):
+    """Returns (model, stream, kwargs for falor.decompose_in_place except module/device/iterator)."""
+    kw: dict[str, Any] = dict(blacklisted_module_names=None, proportion_threshold=0.9,
+                              use_float64=True, use_mean=False, use_damping=True)
+    if name == "mlp":
+        model = TinyMLP()
+        stream = IndexedStream(lambda i: _lowrank_vectors(i, 64, 48, 12, 0.02))
+        kw.update(nsr_final_threshold=0.055, kl_final_threshold=0.02, num_data_steps=4,
+                  num_metric_steps=2)
+    elif name == "convmlp":
+        model = models.ConvMLPNet(dims=(16, 32), depths=(1, 1), expand=4, num_classes=10)
+        stream = IndexedStream(lambda i: streams.lowrank_image_batch(0, i, 8, 3, 32, 24))
+        kw.update(nsr_final_threshold=0.055, kl_final_threshold=0.02, num_data_steps=4,
+                  num_metric_steps=2, use_mean=True)
+    elif name == "deit_small":
+        model = models.DeiTLike(img=32, patch=8, dim=48, depth=2, heads=3, num_classes=10)
+        stream = IndexedStream(lambda i: streams.lowrank_image_batch(1, i, 8, 3, 32, 24))
+        kw.update(nsr_final_threshold=0.055, kl_final_threshold=0.02, num_data_steps=4,
+                  num_metric_steps=2, blacklisted_module_names=["head"])
+    elif name == "deit_tiny":
+        # BASELINE.json configs[0]: deit_tiny_patch16_224 layout, random init, (5,3,224,224) inputs,
+        # 10 classes (the convention of the reference's tests/test_decompose_torchvision_timm.py:28-34)
+        model = models.DeiTLike(num_classes=10)
+        stream = IndexedStream(lambda i: streams.image_batch(0, i, 5))
+        kw.update(nsr_final_threshold=0.05, kl_final_threshold=0.02, num_data_steps=8,
+                  num_metric_steps=2, use_float64=False)
+    else:
+        raise KeyError(name)
+    model.eval()
+    return model, stream, kw
+
+
+# ------------------------------------------------------------------ dwain cases
+DWAIN_CASES = ("llama_tiny", "llama_tiny_splits")
+
+
+def dwain_case(name: str):
+    """Returns (model, data stream, metric stream, kwargs). The two streams are distinct objects
+    over distinct index ranges so that consumption order of each is observable."""
+    if name not in DWAIN_CASES:
+        raise KeyError(name)
+    model = models.LlamaLikeDecoder(vocab=256, hidden=64, inter=176, layers=2, heads=4, kv_heads=2,
+                                    theta=10000.0)
+    model.eval()
+    data = IndexedStream(lambda i: streams.token_batch(2, i, 2, 64, 256))
+    metric = IndexedStream(lambda i: streams.token_batch(3, i, 2, 64, 256))
+    kw: dict[str, Any] = dict(num_data_steps=4, num_metric_steps=2,
+                              blacklisted_module_names=["lm_head"], nsr_final_threshold=0.004,
+                              min_rank=8, trade_off_factor=0.5, reduction_factor=0.5,
+                              max_accepted_ppl_diff=0.1, decompose_in_float64=True,
+                              precomputing_covariance_num_splits=2 if name.endswith("splits") else None)
+    return model, data, metric, kw
+
+
+def dwain_loss_fn(name: str):
+    return models.llama_ce_loss
