@@ -65,6 +65,30 @@ int ptdeco_gemm(const void* A, int a_dtype, int a_mn_major, long long lda, const
                 const float* bias, void* C, int c_dtype, long long ldc, int accumulate,
                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- K3: symmetric eigendecomposition ------------------------------------------------------------
+ * Replaces  F:207 / D:162  _, u = torch.linalg.eigh(cov)   (and the uk = u[:, d-k:] slice of F:346,
+ * D:425): A[d][lda] fp32 symmetric (lower triangle authoritative, torch's UPLO='L'), not modified.
+ * evals[d] receives ALL eigenvalues ascending; U[d][ldu] receives in column c the eigenvector of
+ * eigenvalue number d-k+c, i.e. the k largest in ascending order (k = d gives torch's full `u`).
+ * d <= 96: one-CTA fp64 Jacobi. d > 96: blocked Householder tridiagonalisation (cooperative panel
+ * kernel + tcgen05 trailing update), fp64 multisection + twisted-factorisation eigenvectors,
+ * tcgen05 compact-WY back-transformation of the k wanted vectors. */
+size_t ptdeco_eigh_workspace_bytes(int d, int k);
+int ptdeco_eigh(const float* A, int d, long long lda, int k, float* evals, float* U, long long ldu,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K7: decomposed-layer forward -----------------------------------------------------------------
+ * Replaces the forward of the nn.Sequential(Linear(in->k, no bias), Linear(k->out, bias)) built at
+ * F:84-95 / D:74-85 (and its 1x1-conv twin on NHWC rows):
+ * Y[n][ldy] = (X[n][ldx] W1[k][ldw1]^T) W2[out][ldw2]^T + bias[out]; X, W1, W2, Y of `dtype`,
+ * bias fp32 or NULL. */
+size_t ptdeco_lowrank_workspace_bytes(int dtype, long long n, int in_features, int k,
+                                      int out_features);
+int ptdeco_lowrank_forward(const void* X, long long ldx, const void* W1, long long ldw1,
+                           const void* W2, long long ldw2, const float* bias, void* Y,
+                           long long ldy, int dtype, long long n, int in_features, int k,
+                           int out_features, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K6: rank-search metrics -------------------------------------------------------------------
  * ptdeco_nsr_metric replaces U/l:10-22 calc_per_channel_noise_to_signal_ratio for channel-last
  * inputs viewed as [rows][channels]: out[0] = mean_c( mean_r (x-y)^2 / (var_unbiased_r(y) + eps) ).

@@ -6,8 +6,10 @@
 #include <cstring>
 
 #include "../../include/ptdeco_b200.h"
+#include "eigh.cuh"
 #include "elementwise.cuh"
 #include "gemm_tc.cuh"
+#include "lowrank.cuh"
 
 namespace {
 
@@ -145,6 +147,32 @@ int ptdeco_gemm(const void* A, int a_dtype, int a_mn_major, long long lda, const
     ep.ldc = ldc;
   }
   return ptd::gemm_tc(a, b, M, N, K, -1, ep, st);
+}
+
+size_t ptdeco_eigh_workspace_bytes(int d, int k) {
+  if (d <= 0 || k < 1 || k > d) return 0;
+  return ptd::eigh_workspace_bytes(d, k);
+}
+
+int ptdeco_eigh(const float* A, int d, long long lda, int k, float* evals, float* U, long long ldu,
+                void* workspace, size_t workspace_bytes, void* stream) {
+  return ptd::eigh(A, d, lda, k, evals, U, ldu, workspace, workspace_bytes, as_stream(stream));
+}
+
+size_t ptdeco_lowrank_workspace_bytes(int dtype, long long n, int in_features, int k,
+                                      int out_features) {
+  return ptd::lowrank_workspace_bytes(dtype == PTDECO_BF16, n, in_features, k, out_features);
+}
+
+int ptdeco_lowrank_forward(const void* X, long long ldx, const void* W1, long long ldw1,
+                           const void* W2, long long ldw2, const float* bias, void* Y,
+                           long long ldy, int dtype, long long n, int in_features, int k,
+                           int out_features, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  if (dtype != PTDECO_F32 && dtype != PTDECO_BF16) return -22;
+  return ptd::lowrank_forward(X, ldx, W1, ldw1, W2, ldw2, bias, Y, ldy, dtype == PTDECO_BF16, n,
+                              in_features, k, out_features, workspace, workspace_bytes,
+                              as_stream(stream));
 }
 
 size_t ptdeco_nsr_workspace_bytes(long long channels) {

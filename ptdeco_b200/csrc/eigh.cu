@@ -1,0 +1,1100 @@
+// Symmetric eigensolver for sm_100a. See eigh.cuh for the algorithm outline.
+//
+// Replaces torch.linalg.eigh at the reference's F:207 / D:162. Only the eigenvectors of the k
+// largest eigenvalues are back-transformed (the rank search never slices more than
+// ceil(min(in,out)/2) of them).
+#include "eigh.cuh"
+
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+
+#include "gemm_tc.cuh"
+
+namespace ptd {
+
+namespace {
+
+constexpr int JACOBI_MAX = 96;
+constexpr int NB = 64;  // Householder panel width
+constexpr int PANEL_THREADS = 512;
+constexpr int PANEL_WARPS = PANEL_THREADS / 32;
+constexpr int GP_STRIDE = 2 * NB + 2;  // floats per CTA in the partial-dot exchange buffer
+
+inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& h, __nv_bfloat16& m,
+                                       __nv_bfloat16& l) {
+  h = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(h);
+  m = __float2bfloat16_rn(r1);
+  l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+}
+
+// ============================================================================ small matrices
+// Parallel cyclic Jacobi (round-robin ordering) on one CTA, everything in fp64 shared memory.
+__global__ void __launch_bounds__(512, 1)
+jacobi_kernel(const float* __restrict__ A, long long lda, int d, int k, float* __restrict__ evals,
+              float* __restrict__ U, long long ldu) {
+  extern __shared__ double smd[];
+  const int ld = d + 1;
+  const int n = d + (d & 1);  // players of the tournament (one dummy when d is odd)
+  const int half = n / 2;
+  double* a = smd;             // [d][ld]
+  double* v = a + d * ld;      // [d][ld]
+  double* cs = v + d * ld;     // [half][2]
+  int* pp = reinterpret_cast<int*>(cs + 2 * half);
+  int* qq = pp + half;
+  int* rnk = qq + half;        // [d]
+  __shared__ double red[32];
+  __shared__ double s_off, s_diag;
+  const int tid = threadIdx.x, nt = blockDim.x;
+
+  for (int idx = tid; idx < d * d; idx += nt) {
+    const int r = idx / d, c = idx % d;
+    const int hi = r > c ? r : c, lo = r > c ? c : r;
+    a[r * ld + c] = static_cast<double>(A[static_cast<long long>(hi) * lda + lo]);
+    v[r * ld + c] = (r == c) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    for (int idx = tid; idx < d * d; idx += nt) {
+      const int r = idx / d, c = idx % d;
+      const double x = a[r * ld + c];
+      if (r == c) dg += x * x; else off += x * x;
+    }
+    off = warp_sum(off);
+    dg = warp_sum(dg);
+    if ((tid & 31) == 0) red[tid >> 5] = off;
+    __syncthreads();
+    if (tid == 0) { double s = 0.0; for (int w = 0; w < (nt >> 5); ++w) s += red[w]; s_off = s; }
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = dg;
+    __syncthreads();
+    if (tid == 0) { double s = 0.0; for (int w = 0; w < (nt >> 5); ++w) s += red[w]; s_diag = s; }
+    __syncthreads();
+    if (s_off <= 1e-31 * s_diag || s_off == 0.0) break;  // uniform across the CTA
+
+    for (int round = 0; round < n - 1; ++round) {
+      if (tid < half) {
+        int p, q;
+        if (tid == 0) { p = n - 1; q = round; }
+        else { p = (round + tid) % (n - 1); q = (round - tid + (n - 1)) % (n - 1); }
+        if (p > q) { const int t = p; p = q; q = t; }
+        double c = 1.0, s = 0.0;
+        if (q < d) {
+          const double apq = a[p * ld + q];
+          if (fabs(apq) > 1e-300) {
+            const double theta = (a[q * ld + q] - a[p * ld + p]) / (2.0 * apq);
+            const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            c = 1.0 / sqrt(t * t + 1.0);
+            s = t * c;
+          }
+        }
+        pp[tid] = p; qq[tid] = q; cs[2 * tid] = c; cs[2 * tid + 1] = s;
+      }
+      __syncthreads();
+      for (int idx = tid; idx < half * d; idx += nt) {  // columns p,q of A and V
+        const int pr = idx / d, r = idx % d;
+        const double s = cs[2 * pr + 1];
+        if (s == 0.0) continue;
+        const double c = cs[2 * pr];
+        const int p = pp[pr], q = qq[pr];
+        const double arp = a[r * ld + p], arq = a[r * ld + q];
+        a[r * ld + p] = c * arp - s * arq;
+        a[r * ld + q] = s * arp + c * arq;
+        const double vrp = v[r * ld + p], vrq = v[r * ld + q];
+        v[r * ld + p] = c * vrp - s * vrq;
+        v[r * ld + q] = s * vrp + c * vrq;
+      }
+      __syncthreads();
+      for (int idx = tid; idx < half * d; idx += nt) {  // rows p,q of A
+        const int pr = idx / d, r = idx % d;
+        const double s = cs[2 * pr + 1];
+        if (s == 0.0) continue;
+        const double c = cs[2 * pr];
+        const int p = pp[pr], q = qq[pr];
+        const double apr = a[p * ld + r], aqr = a[q * ld + r];
+        a[p * ld + r] = c * apr - s * aqr;
+        a[q * ld + r] = s * apr + c * aqr;
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < d; i += nt) {
+    const double li = a[i * ld + i];
+    int cnt = 0;
+    for (int j = 0; j < d; ++j) {
+      const double lj = a[j * ld + j];
+      cnt += (lj < li) || (lj == li && j < i);
+    }
+    rnk[i] = cnt;
+    evals[cnt] = static_cast<float>(li);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < d * d; idx += nt) {
+    const int r = idx / d, i = idx % d;
+    const int c = rnk[i] - (d - k);
+    if (c >= 0) U[static_cast<long long>(r) * ldu + c] = static_cast<float>(v[r * ld + i]);
+  }
+}
+
+// ============================================================================ copy-in
+// W[r][c] = A[max(r,c)][min(r,c)] (lower triangle authoritative), zero in the pad columns.
+__global__ void copy_sym_kernel(const float* __restrict__ A, long long lda, int d,
+                                float* __restrict__ W, long long ldw) {
+  __shared__ float tile[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  if (bi >= bj) {
+    for (int yy = ty; yy < 32; yy += 8) {
+      const int i = bi * 32 + yy, j = bj * 32 + tx;
+      if (i < d && j < ldw) {
+        float x = 0.f;
+        if (j < d) {
+          const int hi = i > j ? i : j, lo = i > j ? j : i;
+          x = A[static_cast<long long>(hi) * lda + lo];
+        }
+        W[static_cast<long long>(i) * ldw + j] = x;
+      }
+    }
+  } else {
+    for (int yy = ty; yy < 32; yy += 8) {
+      const int i = bj * 32 + yy, j = bi * 32 + tx;  // source tile (bj, bi), below the diagonal
+      tile[yy][tx] = (i < d && j < d) ? A[static_cast<long long>(i) * lda + j] : 0.f;
+    }
+    __syncthreads();
+    for (int yy = ty; yy < 32; yy += 8) {
+      const int i = bi * 32 + yy, j = bj * 32 + tx;
+      if (i < d && j < ldw) W[static_cast<long long>(i) * ldw + j] = tile[tx][yy];
+    }
+  }
+}
+
+// ============================================================================ sytrd panel
+struct PanelArgs {
+  float* A;
+  long long ldA;
+  int d, j0, ncols, rows_per_cta;
+  float* Vp;      // [d][NB] indexed by global row
+  float* Wp;      // [d][NB]
+  float* colbuf;  // [d] (local row index)
+  double* npart;  // [grid]
+  float* gpart;   // [grid][GP_STRIDE]
+  float* ptop;    // [NB]
+  float* dvec;    // [d]
+  float* evec;    // [d]
+  float* taus;    // [d]
+  float* Tmat;    // [NB][NB] of this panel (pre-zeroed)
+  unsigned* bar;  // grid barrier counter (pre-zeroed)
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ++epoch;
+    const unsigned target = epoch * gridDim.x;
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned v;
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if (clock64() - t0 > 6000000000LL) __trap();  // never hang the box on a lost CTA
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// One launch = one panel of up to NB Householder columns (LAPACK latrd, lower variant).
+// Cooperative: all CTAs are co-resident; row slices of the trailing matrix are owned by CTAs.
+__global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const PanelArgs g) {
+  extern __shared__ float smf[];
+  const int m = g.d - g.j0;
+  const int L = static_cast<int>(g.ldA - g.j0);  // padded row length (multiple of 4)
+  float* vs = smf;                           // [L] current Householder vector, local index
+  float* Vt = vs + L;                        // [NB][NB+1] top block of V (rows < NB)
+  float* Wt = Vt + NB * (NB + 1);            // [NB][NB+1] top block of W
+  float* pbuf = Wt + NB * (NB + 1);          // [rows_per_cta] symv result of own rows
+  float* gWs = pbuf + g.rows_per_cta;        // [NB]  W^T v
+  float* gVs = gWs + NB;                     // [NB]  V^T v
+  float* red = gVs + NB;                     // [PANEL_WARPS][2*NB]
+  __shared__ double sred[PANEL_WARPS];
+  __shared__ double s_scal[4];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = gridDim.x, cta = blockIdx.x;
+  const int r0 = cta * g.rows_per_cta;
+  const int r1 = min(m, r0 + g.rows_per_cta);
+  unsigned epoch = 0;
+  const float* Abase = g.A + static_cast<long long>(g.j0) * g.ldA + g.j0;
+  float* Vp = g.Vp + static_cast<long long>(g.j0) * NB;
+  float* Wp = g.Wp + static_cast<long long>(g.j0) * NB;
+
+  for (int idx = tid; idx < 2 * NB * (NB + 1); idx += PANEL_THREADS) Vt[idx] = 0.f;
+  __syncthreads();
+
+  for (int i = 0; i < g.ncols; ++i) {
+    const int j = g.j0 + i;
+    // ---------------------------------------------------------------- P1: updated column i
+    double nrm = 0.0;
+    for (int r = max(r0, i) + warp; r < r1; r += PANEL_WARPS) {
+      float s = 0.f;
+      for (int c = lane; c < i; c += 32)
+        s += Vp[r * NB + c] * Wt[i * (NB + 1) + c] + Wp[r * NB + c] * Vt[i * (NB + 1) + c];
+      s = warp_sum(s);
+      if (lane == 0) {
+        const float a = Abase[static_cast<long long>(i) * g.ldA + r] - s;
+        g.colbuf[r] = a;
+        if (r >= i + 2) nrm += static_cast<double>(a) * a;
+      }
+    }
+    if (lane == 0) sred[warp] = nrm;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int w = 0; w < PANEL_WARPS; ++w) s += sred[w];
+      g.npart[cta] = s;
+    }
+    grid_barrier(g.bar, epoch);
+
+    // ---------------------------------------------------------------- P2: reflector + symv
+    if (warp == 0) {
+      double s = 0.0;
+      for (int c = lane; c < G; c += 32) s += __ldcg(g.npart + c);
+      s = warp_sum(s);
+      if (lane == 0) s_scal[0] = s;
+    }
+    __syncthreads();
+    const double xnorm2 = s_scal[0];
+    const float dj = __ldcg(g.colbuf + i);
+    if (i + 1 >= m) {  // last diagonal element of the matrix: no reflector (uniform branch)
+      if (cta == 0 && tid == 0) g.dvec[j] = dj;
+      break;
+    }
+    const float alpha = __ldcg(g.colbuf + i + 1);
+    float tau = 0.f, beta = alpha, scale = 0.f;
+    if (xnorm2 > 0.0) {
+      const double bt = -copysign(sqrt(static_cast<double>(alpha) * alpha + xnorm2),
+                                  static_cast<double>(alpha));
+      beta = static_cast<float>(bt);
+      tau = static_cast<float>((bt - alpha) / bt);
+      scale = static_cast<float>(1.0 / (static_cast<double>(alpha) - bt));
+    }
+    if (cta == 0 && tid == 0) {
+      g.dvec[j] = dj;
+      g.evec[j] = beta;
+      g.taus[j] = tau;
+    }
+    for (int c = tid; c < L; c += PANEL_THREADS) {
+      float x = 0.f;
+      if (c == i + 1) x = 1.f;
+      else if (c > i + 1 && c < m) x = __ldcg(g.colbuf + c) * scale;
+      vs[c] = x;
+    }
+    __syncthreads();
+    for (int r = r0 + tid; r < r1; r += PANEL_THREADS) Vp[r * NB + i] = vs[r];
+    for (int r = tid; r < NB; r += PANEL_THREADS) Vt[r * (NB + 1) + i] = (r < L) ? vs[r] : 0.f;
+
+    if (tau != 0.f) {
+      const int n4 = L >> 2;
+      const float4* v4 = reinterpret_cast<const float4*>(vs);
+      for (int r = max(r0, i + 1) + warp; r < r1; r += PANEL_WARPS) {
+        const float4* arow = reinterpret_cast<const float4*>(Abase + static_cast<long long>(r) * g.ldA);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int c4 = lane;
+        for (; c4 + 96 < n4; c4 += 128) {
+          const float4 a0 = __ldg(arow + c4), a1 = __ldg(arow + c4 + 32);
+          const float4 a2 = __ldg(arow + c4 + 64), a3 = __ldg(arow + c4 + 96);
+          const float4 x0 = v4[c4], x1 = v4[c4 + 32], x2 = v4[c4 + 64], x3 = v4[c4 + 96];
+          s0 += a0.x * x0.x + a0.y * x0.y + a0.z * x0.z + a0.w * x0.w;
+          s1 += a1.x * x1.x + a1.y * x1.y + a1.z * x1.z + a1.w * x1.w;
+          s2 += a2.x * x2.x + a2.y * x2.y + a2.z * x2.z + a2.w * x2.w;
+          s3 += a3.x * x3.x + a3.y * x3.y + a3.z * x3.z + a3.w * x3.w;
+        }
+        for (; c4 < n4; c4 += 32) {
+          const float4 a0 = __ldg(arow + c4);
+          const float4 x0 = v4[c4];
+          s0 += a0.x * x0.x + a0.y * x0.y + a0.z * x0.z + a0.w * x0.w;
+        }
+        const float s = warp_sum((s0 + s1) + (s2 + s3));
+        if (lane == 0) {
+          pbuf[r - r0] = s;
+          if (r < NB) g.ptop[r] = s;
+        }
+      }
+      __syncthreads();
+      float aw0 = 0.f, aw1 = 0.f, av0 = 0.f, av1 = 0.f;
+      double vp = 0.0;
+      for (int r = max(r0, i + 1) + warp; r < r1; r += PANEL_WARPS) {
+        const float vr = vs[r];
+        if (lane < i) {
+          aw0 += Wp[r * NB + lane] * vr;
+          av0 += Vp[r * NB + lane] * vr;
+        }
+        if (lane + 32 < i) {
+          aw1 += Wp[r * NB + lane + 32] * vr;
+          av1 += Vp[r * NB + lane + 32] * vr;
+        }
+        if (lane == 0) vp += static_cast<double>(vr) * pbuf[r - r0];
+      }
+      red[warp * 2 * NB + lane] = aw0;
+      red[warp * 2 * NB + 32 + lane] = aw1;
+      red[warp * 2 * NB + NB + lane] = av0;
+      red[warp * 2 * NB + NB + 32 + lane] = av1;
+      if (lane == 0) sred[warp] = vp;
+      __syncthreads();
+      if (tid < 2 * NB) {
+        float s = 0.f;
+        for (int w = 0; w < PANEL_WARPS; ++w) s += red[w * 2 * NB + tid];
+        g.gpart[cta * GP_STRIDE + tid] = s;
+      } else if (tid == 2 * NB) {
+        double s = 0.0;
+        for (int w = 0; w < PANEL_WARPS; ++w) s += sred[w];
+        g.gpart[cta * GP_STRIDE + 2 * NB] = static_cast<float>(s);
+      }
+    }
+    grid_barrier(g.bar, epoch);
+
+    // ---------------------------------------------------------------- P3: w column
+    if (tau != 0.f) {
+      if (tid <= 2 * NB) {
+        double s = 0.0;
+        for (int c = 0; c < G; ++c) s += static_cast<double>(__ldcg(g.gpart + c * GP_STRIDE + tid));
+        if (tid < NB) gWs[tid] = static_cast<float>(s);
+        else if (tid < 2 * NB) gVs[tid - NB] = static_cast<float>(s);
+        else s_scal[1] = s;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        double s = 0.0;
+        for (int c = lane; c < i; c += 32) s += static_cast<double>(gVs[c]) * gWs[c];
+        s = warp_sum(s);
+        if (lane == 0) {
+          const double dot = static_cast<double>(tau) * (s_scal[1] - 2.0 * s);
+          s_scal[2] = -0.5 * static_cast<double>(tau) * dot;
+        }
+      }
+      __syncthreads();
+      const float alpha2 = static_cast<float>(s_scal[2]);
+      for (int r = max(r0, i + 1) + warp; r < r1; r += PANEL_WARPS) {
+        float s = 0.f;
+        for (int c = lane; c < i; c += 32) s += Vp[r * NB + c] * gWs[c] + Wp[r * NB + c] * gVs[c];
+        s = warp_sum(s);
+        if (lane == 0) Wp[r * NB + i] = tau * (pbuf[r - r0] - s) + alpha2 * vs[r];
+      }
+      for (int r = r0 + tid; r < min(r1, i + 1); r += PANEL_THREADS) Wp[r * NB + i] = 0.f;
+      for (int r = warp; r < NB; r += PANEL_WARPS) {  // top block, redundantly in every CTA
+        float w = 0.f;
+        if (r > i && r < m) {
+          float s = 0.f;
+          for (int c = lane; c < i; c += 32)
+            s += Vt[r * (NB + 1) + c] * gWs[c] + Wt[r * (NB + 1) + c] * gVs[c];
+          s = warp_sum(s);
+          w = tau * (__ldcg(g.ptop + r) - s) + alpha2 * vs[r];
+        }
+        if (lane == 0) Wt[r * (NB + 1) + i] = w;
+      }
+      if (cta == 0 && tid < NB) {  // compact-WY T column: T[0:i,i] = -tau T[0:i,0:i] (V^T v)
+        if (tid < i) {
+          float s = 0.f;
+          for (int c2 = tid; c2 < i; ++c2) s += g.Tmat[tid * NB + c2] * gVs[c2];
+          g.Tmat[tid * NB + i] = -tau * s;
+        } else if (tid == i) {
+          g.Tmat[i * NB + i] = tau;
+        }
+      }
+    } else {
+      for (int r = r0 + tid; r < r1; r += PANEL_THREADS) Wp[r * NB + i] = 0.f;
+      for (int r = tid; r < NB; r += PANEL_THREADS) Wt[r * (NB + 1) + i] = 0.f;
+    }
+    __syncthreads();
+  }
+}
+
+// bf16x3 split of the finished panel: reflectors into the global store Vs (used by the
+// back-transformation) and the [V|W], [W|V] operands of the rank-2nb trailing update.
+__global__ void panel_split_kernel(const float* __restrict__ Vp, const float* __restrict__ Wp,
+                                   int j0, int m, int ncols, __nv_bfloat16* __restrict__ Vs,
+                                   long long ldv, long long vs_seg, __nv_bfloat16* __restrict__ VW,
+                                   __nv_bfloat16* __restrict__ WV, long long vw_seg) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int groups = NB / 8;
+  if (idx >= m * groups) return;
+  const int r = idx / groups, c0 = (idx % groups) * 8;
+  const long long gr = j0 + r;
+  __align__(16) __nv_bfloat16 vh[3][8], wh[3][8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = c0 + e;
+    const float v = (c < ncols) ? Vp[gr * NB + c] : 0.f;
+    const float w = (c < ncols) ? Wp[gr * NB + c] : 0.f;
+    split3(v, vh[0][e], vh[1][e], vh[2][e]);
+    split3(w, wh[0][e], wh[1][e], wh[2][e]);
+  }
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    if (c0 < ncols)
+      *reinterpret_cast<uint4*>(Vs + s * vs_seg + gr * ldv + j0 + c0) =
+          *reinterpret_cast<const uint4*>(vh[s]);
+    __nv_bfloat16* vw = VW + s * vw_seg + gr * (2 * NB);
+    __nv_bfloat16* wv = WV + s * vw_seg + gr * (2 * NB);
+    *reinterpret_cast<uint4*>(vw + c0) = *reinterpret_cast<const uint4*>(vh[s]);
+    *reinterpret_cast<uint4*>(vw + NB + c0) = *reinterpret_cast<const uint4*>(wh[s]);
+    *reinterpret_cast<uint4*>(wv + c0) = *reinterpret_cast<const uint4*>(wh[s]);
+    *reinterpret_cast<uint4*>(wv + NB + c0) = *reinterpret_cast<const uint4*>(vh[s]);
+  }
+}
+
+// ============================================================================ tridiagonal stage
+struct TriBufs {
+  double* D;     // [d]
+  double* E;     // [d] off-diagonals, E[i] couples i and i+1 (0 at splits and at d-1)
+  double* E2;    // [d]
+  int* blo;      // [d] first row of the unreduced block containing row i
+  int* bhi;      // [d] last row
+  double* lamA;  // [d] bracket of eigenvalue number (i - blo[i]) of i's block
+  double* lamB;  // [d]
+  int* sel;      // [k] row id of the eigenvalue that becomes output column c
+  double* Dp;    // [d][k]
+  double* Dm;    // [d][k]
+  double* znorm; // [k]
+  double* clam;  // [k] eigenvalue of column c
+  double* cbn;   // [k] norm of its block
+  int* clo;      // [k]
+  int* chi;      // [k]
+};
+
+__global__ void __launch_bounds__(1024, 1)
+tri_prep_kernel(const float* __restrict__ dvec, const float* __restrict__ evec, int d, TriBufs b) {
+  __shared__ double redm[32];
+  __shared__ int lastf[1024];
+  __shared__ double s_tol;
+  const int tid = threadIdx.x;
+  double mx = 0.0;
+  for (int i = tid; i < d; i += 1024) {
+    const double di = dvec[i];
+    const double el = i > 0 ? fabs(static_cast<double>(evec[i - 1])) : 0.0;
+    const double er = i < d - 1 ? fabs(static_cast<double>(evec[i])) : 0.0;
+    mx = fmax(mx, fabs(di) + el + er);
+    b.D[i] = di;
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) redm[tid >> 5] = mx;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 32; ++w) s = fmax(s, redm[w]);
+    // Off-diagonals below fp32 noise of the tridiagonalisation are treated as exact splits: the
+    // perturbation (<= 2^-27 ||T||) is smaller than the sytrd's own backward error.
+    s_tol = s * 7.450580596923828e-09;
+  }
+  __syncthreads();
+  const double tol = s_tol;
+  for (int i = tid; i < d; i += 1024) {
+    double e = (i < d - 1) ? static_cast<double>(evec[i]) : 0.0;
+    if (fabs(e) <= tol) e = 0.0;
+    b.E[i] = e;
+    b.E2[i] = e * e;
+  }
+  __syncthreads();
+  // block starts: row i starts a block iff i == 0 or E[i-1] == 0
+  const int chunk = (d + 1023) / 1024;
+  const int c0 = tid * chunk, c1 = min(d, c0 + chunk);
+  int last = -1;
+  for (int i = c0; i < c1; ++i)
+    if (i == 0 || b.E[i - 1] == 0.0) last = i;
+  lastf[tid] = last;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int t = 0; t < 1024; ++t) {
+      const int mine = lastf[t];
+      lastf[t] = run;  // block start in force when entering chunk t
+      if (mine >= 0) run = mine;
+    }
+  }
+  __syncthreads();
+  int cur = lastf[tid];
+  for (int i = c0; i < c1; ++i) {
+    if (i == 0 || b.E[i - 1] == 0.0) cur = i;
+    b.blo[i] = cur;
+  }
+  __syncthreads();
+  // block ends: row i ends a block iff i == d-1 or E[i] == 0
+  last = -1;
+  for (int i = c1 - 1; i >= c0; --i)
+    if (i == d - 1 || b.E[i] == 0.0) last = i;
+  lastf[tid] = last;
+  __syncthreads();
+  if (tid == 0) {
+    int run = d - 1;
+    for (int t = 1023; t >= 0; --t) {
+      const int mine = lastf[t];
+      lastf[t] = run;
+      if (mine >= 0) run = mine;
+    }
+  }
+  __syncthreads();
+  cur = lastf[tid];
+  for (int i = c1 - 1; i >= c0; --i) {
+    if (i == d - 1 || b.E[i] == 0.0) cur = i;
+    b.bhi[i] = cur;
+  }
+}
+
+__device__ __forceinline__ int sturm_count(const double* __restrict__ D,
+                                           const double* __restrict__ E2, int lo, int hi, double x,
+                                           double pivmin) {
+  double q = __ldg(D + lo) - x;
+  int cnt = q < 0.0;
+  for (int i = lo + 1; i <= hi; ++i) {
+    if (fabs(q) < pivmin) q = -pivmin;
+    q = (__ldg(D + i) - x) - __ldg(E2 + i - 1) / q;
+    cnt += (q < 0.0);
+  }
+  return cnt;
+}
+
+// One warp per eigenvalue: 32-way multisection on the Sturm count (5 bits per pass).
+// first = 1: start from the Gershgorin interval of the block; else continue from lamA/lamB.
+__global__ void bisect_kernel(TriBufs b, int d, int count, const int* __restrict__ sel, int first,
+                              int passes) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= count) return;
+  const int t = sel ? sel[w] : w;
+  const int lo = b.blo[t], hi = b.bhi[t];
+  const int q = t - lo;
+  if (lo == hi) {
+    if (lane == 0) { b.lamA[t] = b.D[lo]; b.lamB[t] = b.D[lo]; }
+    return;
+  }
+  double gl = DBL_MAX, gu = -DBL_MAX, e2max = 0.0;
+  for (int i = lo + lane; i <= hi; i += 32) {
+    const double el = i > lo ? fabs(b.E[i - 1]) : 0.0;
+    const double er = i < hi ? fabs(b.E[i]) : 0.0;
+    gl = fmin(gl, b.D[i] - el - er);
+    gu = fmax(gu, b.D[i] + el + er);
+    e2max = fmax(e2max, er * er);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    gl = fmin(gl, __shfl_xor_sync(0xffffffffu, gl, o));
+    gu = fmax(gu, __shfl_xor_sync(0xffffffffu, gu, o));
+    e2max = fmax(e2max, __shfl_xor_sync(0xffffffffu, e2max, o));
+  }
+  const double bnorm = fmax(fabs(gl), fabs(gu));
+  const double pivmin = DBL_MIN * fmax(1.0, e2max);
+  double a, bb;
+  if (first) {
+    const double slack = 2.1 * bnorm * DBL_EPSILON * (hi - lo + 1) + 4.2 * pivmin;
+    a = gl - slack;
+    bb = gu + slack;
+  } else {
+    a = b.lamA[t];
+    bb = b.lamB[t];
+  }
+  for (int pass = 0; pass < passes; ++pass) {
+    if (bb - a <= 2.0 * DBL_EPSILON * fmax(fabs(a), fabs(bb)) + 2.0 * pivmin) break;
+    const double wdt = (bb - a) / 33.0;
+    const double x = a + wdt * (lane + 1);
+    const int cnt = sturm_count(b.D, b.E2, lo, hi, x, pivmin);
+    const unsigned mask = __ballot_sync(0xffffffffu, cnt >= q + 1);
+    if (mask == 0u) {
+      a = a + wdt * 32.0;
+    } else {
+      const int f = __ffs(mask) - 1;
+      const double na = a + wdt * f, nb = a + wdt * (f + 1);
+      a = na;
+      bb = nb;
+    }
+  }
+  if (lane == 0) { b.lamA[t] = a; b.lamB[t] = bb; }
+}
+
+// rank of every eigenvalue in the global ascending order (ties by row id); scatter eigenvalues
+// and the row ids of the k largest.
+__global__ void rank_kernel(TriBufs b, int d, int k, float* __restrict__ evals) {
+  __shared__ double tile[256];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const double my = t < d ? 0.5 * (b.lamA[t] + b.lamB[t]) : 0.0;
+  int cnt = 0;
+  for (int base = 0; base < d; base += 256) {
+    const int s = base + threadIdx.x;
+    tile[threadIdx.x] = s < d ? 0.5 * (b.lamA[s] + b.lamB[s]) : 0.0;
+    __syncthreads();
+    const int nn = min(256, d - base);
+    for (int u = 0; u < nn; ++u) {
+      const double v = tile[u];
+      cnt += (v < my) || (v == my && (base + u) < t);
+    }
+    __syncthreads();
+  }
+  if (t < d) {
+    evals[cnt] = static_cast<float>(my);
+    if (cnt >= d - k) b.sel[cnt - (d - k)] = t;
+  }
+}
+
+__device__ __forceinline__ double guard_piv(double x, double pivmin) {
+  return fabs(x) < pivmin ? (x < 0.0 ? -pivmin : pivmin) : x;
+}
+
+// One thread per wanted eigenvector: twisted factorisation of T_block - lambda I
+// (forward L D+ L^T, backward U D- U^T, twist at argmin |gamma|), un-normalised z into Dp.
+__global__ void eigvec_kernel(TriBufs b, int d, int k) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= k) return;
+  const int t = b.sel[c];
+  const int lo = b.blo[t], hi = b.bhi[t];
+  const double lam = 0.5 * (b.lamA[t] + b.lamB[t]);
+  b.clam[c] = lam;
+  b.clo[c] = lo;
+  b.chi[c] = hi;
+  const long long K = k;
+  if (lo == hi) {
+    b.Dp[lo * K + c] = 1.0;
+    b.znorm[c] = 1.0;
+    b.cbn[c] = fabs(lam);
+    return;
+  }
+  double e2max = 0.0, bn = 0.0;
+  for (int i = lo; i <= hi; ++i) {
+    const double er = i < hi ? fabs(b.E[i]) : 0.0;
+    const double el = i > lo ? fabs(b.E[i - 1]) : 0.0;
+    e2max = fmax(e2max, er * er);
+    bn = fmax(bn, fabs(b.D[i]) + el + er);
+  }
+  b.cbn[c] = bn;
+  const double pivmin = fmax(DBL_MIN * fmax(1.0, e2max), 1e-300);
+  double dp = b.D[lo] - lam;
+  b.Dp[lo * K + c] = dp;
+  for (int i = lo; i < hi; ++i) {
+    const double e = b.E[i];
+    const double l = e / guard_piv(dp, pivmin);
+    dp = (b.D[i + 1] - lam) - l * e;
+    b.Dp[(i + 1) * K + c] = dp;
+  }
+  double dm = b.D[hi] - lam;
+  b.Dm[hi * K + c] = dm;
+  double best = fabs(dp);  // gamma at hi = Dp[hi]
+  int r = hi;
+  for (int i = hi - 1; i >= lo; --i) {
+    const double e = b.E[i];
+    const double u = e / guard_piv(dm, pivmin);
+    const double dl = b.D[i] - lam;
+    dm = dl - u * e;
+    b.Dm[i * K + c] = dm;
+    const double gam = fabs(b.Dp[i * K + c] + dm - dl);
+    if (gam < best) { best = gam; r = i; }
+  }
+  double zz = 1.0, nn = 1.0;
+  for (int i = r - 1; i >= lo; --i) {
+    zz = -(b.E[i] / guard_piv(b.Dp[i * K + c], pivmin)) * zz;
+    b.Dp[i * K + c] = zz;
+    nn += zz * zz;
+  }
+  zz = 1.0;
+  for (int i = r; i < hi; ++i) {
+    zz = -(b.E[i] / guard_piv(b.Dm[(i + 1) * K + c], pivmin)) * zz;
+    b.Dp[(i + 1) * K + c] = zz;
+    nn += zz * zz;
+  }
+  b.Dp[r * K + c] = 1.0;
+  b.znorm[c] = sqrt(nn);
+}
+
+__device__ __forceinline__ bool same_cluster(const TriBufs& b, int c1, int c2) {
+  return b.clo[c1] == b.clo[c2] && b.clo[c1] != b.chi[c1] &&
+         fabs(b.clam[c2] - b.clam[c1]) <= 1e-9 * b.cbn[c1];
+}
+
+__device__ double block_sum_256(double v, double* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < 8; ++w) s += red[w];
+  return s;
+}
+
+// Safety net for eigenvalues of one unreduced block that agree to 1e-9 ||T_b||: the independently
+// computed vectors are re-orthogonalised (modified Gram-Schmidt, twice) in fp64. One CTA per
+// cluster head; every other CTA exits at once.
+__global__ void __launch_bounds__(256) cluster_fix_kernel(TriBufs b, int k) {
+  __shared__ double red[8];
+  const int c = blockIdx.x;
+  if (c > 0 && same_cluster(b, c - 1, c)) return;
+  if (!(c + 1 < k && same_cluster(b, c, c + 1))) return;
+  const int lo = b.clo[c], hi = b.chi[c];
+  const long long K = k;
+  const int tid = threadIdx.x;
+  {
+    const double inv = 1.0 / b.znorm[c];
+    for (int i = lo + tid; i <= hi; i += 256) b.Dp[i * K + c] *= inv;
+    __syncthreads();
+    if (tid == 0) b.znorm[c] = 1.0;
+  }
+  for (int mcol = c + 1; mcol < k && same_cluster(b, mcol - 1, mcol); ++mcol) {
+    double inv = 1.0 / b.znorm[mcol];
+    for (int i = lo + tid; i <= hi; i += 256) b.Dp[i * K + mcol] *= inv;
+    __syncthreads();
+    for (int rep = 0; rep < 2; ++rep) {
+      for (int p = c; p < mcol; ++p) {
+        double dot = 0.0;
+        for (int i = lo + tid; i <= hi; i += 256) dot += b.Dp[i * K + mcol] * b.Dp[i * K + p];
+        dot = block_sum_256(dot, red);
+        for (int i = lo + tid; i <= hi; i += 256) b.Dp[i * K + mcol] -= dot * b.Dp[i * K + p];
+        __syncthreads();
+      }
+      double nn = 0.0;
+      for (int i = lo + tid; i <= hi; i += 256) nn += b.Dp[i * K + mcol] * b.Dp[i * K + mcol];
+      nn = sqrt(block_sum_256(nn, red));
+      if (nn < 1e-10 && rep == 0) {
+        // numerically identical vectors: restart from a unit vector of the block
+        const int pick = lo + (mcol - c) % (hi - lo + 1);
+        for (int i = lo + tid; i <= hi; i += 256) b.Dp[i * K + mcol] = (i == pick) ? 1.0 : 0.0;
+        __syncthreads();
+        rep = -1;  // orthogonalise the replacement twice as well
+        continue;
+      }
+      inv = nn > 0.0 ? 1.0 / nn : 0.0;
+      for (int i = lo + tid; i <= hi; i += 256) b.Dp[i * K + mcol] *= inv;
+      __syncthreads();
+    }
+    if (tid == 0) b.znorm[mcol] = 1.0;
+    __syncthreads();
+  }
+}
+
+// U[i][c] = z / ||z|| inside the block of column c, 0 outside.
+__global__ void z_to_u_kernel(TriBufs b, int d, int k, float* __restrict__ U, long long ldu) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(d) * k) return;
+  const int i = static_cast<int>(idx / k), c = static_cast<int>(idx % k);
+  float x = 0.f;
+  if (i >= b.clo[c] && i <= b.chi[c]) x = static_cast<float>(b.Dp[idx] / b.znorm[c]);
+  U[static_cast<long long>(i) * ldu + c] = x;
+}
+
+// ============================================================================ back-transform
+// Zs[seg][r][c] = split(U[row0 + r][c]) for r < m, c < kp (zero beyond k).
+__global__ void split_z_kernel(const float* __restrict__ U, long long ldu, int row0, int m, int k,
+                               int kp, __nv_bfloat16* __restrict__ Zs, long long seg) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int groups = kp / 8;
+  if (idx >= static_cast<long long>(m) * groups) return;
+  const int r = static_cast<int>(idx / groups), c0 = static_cast<int>(idx % groups) * 8;
+  __align__(16) __nv_bfloat16 o[3][8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = c0 + e;
+    const float x = c < k ? U[static_cast<long long>(row0 + r) * ldu + c] : 0.f;
+    split3(x, o[0][e], o[1][e], o[2][e]);
+  }
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+    *reinterpret_cast<uint4*>(Zs + s * seg + static_cast<long long>(r) * kp + c0) =
+        *reinterpret_cast<const uint4*>(o[s]);
+}
+
+// Xs[seg][a][n] = split( sum_{b >= a} T[a][b] X1[b][n] ), a < NB (rows >= nc give zero).
+__global__ void tmul_split_kernel(const float* __restrict__ T, const float* __restrict__ X1, int nc,
+                                  int kp, __nv_bfloat16* __restrict__ Xs, long long seg) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int a = blockIdx.y;
+  if (n >= kp) return;
+  float s = 0.f;
+  if (a < nc)
+    for (int bb = a; bb < nc; ++bb) s += T[a * NB + bb] * X1[static_cast<long long>(bb) * kp + n];
+  __nv_bfloat16 h, mm, l;
+  split3(s, h, mm, l);
+  Xs[static_cast<long long>(a) * kp + n] = h;
+  Xs[seg + static_cast<long long>(a) * kp + n] = mm;
+  Xs[2 * seg + static_cast<long long>(a) * kp + n] = l;
+}
+
+__global__ void tiny_1x1_kernel(const float* A, float* evals, float* U) {
+  evals[0] = A[0];
+  U[0] = 1.f;
+}
+
+// ---------------------------------------------------------------------------- workspace carving
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t count) {
+    off = (off + 255) & ~static_cast<size_t>(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+struct Plan {
+  float* Aw; long long ldA;
+  __nv_bfloat16* Vs; long long ldv;
+  float *Vp, *Wp, *colbuf, *gpart, *ptop, *dvec, *evec, *taus, *Tmats, *X1;
+  double* npart;
+  unsigned* bars;
+  __nv_bfloat16 *VW, *WV, *Zs, *Xs;
+  TriBufs tb;
+  int kp, npanels;
+  size_t bytes;
+};
+
+int max_grid() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+Plan make_plan(void* ws, int d, int k) {
+  Plan p;
+  Carver cv{static_cast<uint8_t*>(ws)};
+  const size_t D = d, K = k;
+  p.ldA = round_up(d, 8);
+  p.ldv = round_up(d, 8);
+  p.kp = static_cast<int>(round_up(k, 8));
+  p.npanels = (d + NB - 1) / NB;
+  p.Aw = cv.take<float>(D * p.ldA);
+  p.Vs = cv.take<__nv_bfloat16>(3 * D * p.ldv);
+  p.Vp = cv.take<float>(D * NB);
+  p.Wp = cv.take<float>(D * NB);
+  p.colbuf = cv.take<float>(D);
+  p.npart = cv.take<double>(1024);
+  p.gpart = cv.take<float>(1024 * GP_STRIDE);
+  p.ptop = cv.take<float>(NB);
+  p.dvec = cv.take<float>(D);
+  p.evec = cv.take<float>(D);
+  p.taus = cv.take<float>(D);
+  p.Tmats = cv.take<float>(static_cast<size_t>(p.npanels) * NB * NB);
+  p.bars = cv.take<unsigned>(p.npanels);
+  p.VW = cv.take<__nv_bfloat16>(3 * D * 2 * NB);
+  p.WV = cv.take<__nv_bfloat16>(3 * D * 2 * NB);
+  p.tb.D = cv.take<double>(D);
+  p.tb.E = cv.take<double>(D);
+  p.tb.E2 = cv.take<double>(D);
+  p.tb.blo = cv.take<int>(D);
+  p.tb.bhi = cv.take<int>(D);
+  p.tb.lamA = cv.take<double>(D);
+  p.tb.lamB = cv.take<double>(D);
+  p.tb.sel = cv.take<int>(K);
+  p.tb.Dp = cv.take<double>(D * K);
+  p.tb.Dm = cv.take<double>(D * K);
+  p.tb.znorm = cv.take<double>(K);
+  p.tb.clam = cv.take<double>(K);
+  p.tb.cbn = cv.take<double>(K);
+  p.tb.clo = cv.take<int>(K);
+  p.tb.chi = cv.take<int>(K);
+  p.Zs = cv.take<__nv_bfloat16>(3 * D * p.kp);
+  p.X1 = cv.take<float>(static_cast<size_t>(NB) * p.kp);
+  p.Xs = cv.take<__nv_bfloat16>(3 * static_cast<size_t>(NB) * p.kp);
+  p.bytes = cv.off + 256;
+  return p;
+}
+
+#define PTD_CHECK_LAUNCH()                                   \
+  do {                                                       \
+    if (cudaGetLastError() != cudaSuccess) return -5;        \
+  } while (0)
+
+}  // namespace
+
+size_t eigh_workspace_bytes(int d, int k) {
+  if (d <= JACOBI_MAX) return 256;
+  return make_plan(nullptr, d, k).bytes;
+}
+
+int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, long long ldu,
+         void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (A == nullptr || evals == nullptr || U == nullptr || d <= 0 || k < 1 || k > d || lda < d ||
+      ldu < k)
+    return -22;
+  if (d == 1) {
+    tiny_1x1_kernel<<<1, 1, 0, st>>>(A, evals, U);
+    PTD_CHECK_LAUNCH();
+    return 0;
+  }
+  if (d <= JACOBI_MAX) {
+    const int n = d + (d & 1);
+    const size_t smem = (2 * static_cast<size_t>(d) * (d + 1) + n) * sizeof(double) +
+                        (static_cast<size_t>(n) + d) * sizeof(int) + 64;
+    static bool attr = false;
+    if (!attr) {
+      if (cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               200 * 1024) != cudaSuccess)
+        return -12;
+      attr = true;
+    }
+    jacobi_kernel<<<1, 512, smem, st>>>(A, lda, d, k, evals, U, ldu);
+    PTD_CHECK_LAUNCH();
+    return 0;
+  }
+  if (ws == nullptr || ws_bytes < eigh_workspace_bytes(d, k)) return -12;
+  if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return -22;
+  Plan p = make_plan(ws, d, k);
+
+  // ---- copy-in (mirrors the lower triangle, zero pad columns)
+  {
+    dim3 grid(static_cast<unsigned>((p.ldA + 31) / 32), static_cast<unsigned>((d + 31) / 32));
+    copy_sym_kernel<<<grid, dim3(32, 8), 0, st>>>(A, lda, d, p.Aw, p.ldA);
+    PTD_CHECK_LAUNCH();
+  }
+  cudaMemsetAsync(p.Tmats, 0, static_cast<size_t>(p.npanels) * NB * NB * sizeof(float), st);
+  cudaMemsetAsync(p.bars, 0, static_cast<size_t>(p.npanels) * sizeof(unsigned), st);
+  cudaMemsetAsync(p.Vp, 0, static_cast<size_t>(d) * NB * sizeof(float), st);
+  cudaMemsetAsync(p.Wp, 0, static_cast<size_t>(d) * NB * sizeof(float), st);
+  cudaMemsetAsync(p.evec, 0, static_cast<size_t>(d) * sizeof(float), st);
+  cudaMemsetAsync(p.taus, 0, static_cast<size_t>(d) * sizeof(float), st);
+
+  // ---- (1) tridiagonalisation
+  static bool panel_attr = false;
+  if (!panel_attr) {
+    if (cudaFuncSetAttribute(sytrd_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             220 * 1024) != cudaSuccess)
+      return -12;
+    panel_attr = true;
+  }
+  const int sms = max_grid();
+  for (int pi = 0; pi < p.npanels; ++pi) {
+    const int j0 = pi * NB;
+    const int m = d - j0;
+    PanelArgs g;
+    g.A = p.Aw; g.ldA = p.ldA; g.d = d; g.j0 = j0; g.ncols = std::min(NB, m);
+    g.rows_per_cta = std::max(PANEL_WARPS, (m + sms - 1) / sms);
+    g.Vp = p.Vp; g.Wp = p.Wp; g.colbuf = p.colbuf; g.npart = p.npart; g.gpart = p.gpart;
+    g.ptop = p.ptop; g.dvec = p.dvec; g.evec = p.evec; g.taus = p.taus;
+    g.Tmat = p.Tmats + static_cast<size_t>(pi) * NB * NB;
+    g.bar = p.bars + pi;
+    const int grid = (m + g.rows_per_cta - 1) / g.rows_per_cta;
+    const long long L = p.ldA - j0;
+    const size_t smem = (static_cast<size_t>(L) + 2 * NB * (NB + 1) + g.rows_per_cta + 2 * NB +
+                         PANEL_WARPS * 2 * NB) * sizeof(float);
+    if (smem > 220 * 1024) return -22;  // d beyond what one SM's shared memory can stage
+    void* args[] = {&g};
+    if (cudaLaunchCooperativeKernel(reinterpret_cast<void*>(sytrd_panel_kernel), dim3(grid),
+                                    dim3(PANEL_THREADS), args, smem, st) != cudaSuccess)
+      return -5;
+    {
+      const int total = m * (NB / 8);
+      panel_split_kernel<<<(total + 255) / 256, 256, 0, st>>>(
+          p.Vp, p.Wp, j0, m, g.ncols, p.Vs, p.ldv, static_cast<long long>(d) * p.ldv, p.VW, p.WV,
+          static_cast<long long>(d) * 2 * NB);
+      PTD_CHECK_LAUNCH();
+    }
+    if (m > NB) {
+      const int mt = m - NB;
+      GemmOperand a{p.VW + static_cast<long long>(j0 + NB) * 2 * NB, 0, 2 * NB, 3,
+                    static_cast<long long>(d) * 2 * NB};
+      GemmOperand b{p.WV + static_cast<long long>(j0 + NB) * 2 * NB, 0, 2 * NB, 3,
+                    static_cast<long long>(d) * 2 * NB};
+      GemmEpilogue ep;
+      ep.alpha = -1.f;
+      ep.C = p.Aw + static_cast<long long>(j0 + NB) * p.ldA + (j0 + NB);
+      ep.ldc = p.ldA;
+      ep.accumulate = 1;
+      const int rc = gemm_tc(a, b, mt, mt, 2 * NB, -1, ep, st);
+      if (rc) return rc;
+    }
+  }
+
+  // ---- (2) tridiagonal eigenproblem in fp64
+  tri_prep_kernel<<<1, 1024, 0, st>>>(p.dvec, p.evec, d, p.tb);
+  PTD_CHECK_LAUNCH();
+  {
+    const int warps_per_block = 4;
+    // all eigenvalues to ~2^-35 of the block norm (enough for ordering and the fp32 output) ...
+    bisect_kernel<<<(d + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
+        p.tb, d, d, nullptr, 1, 7);
+    PTD_CHECK_LAUNCH();
+    rank_kernel<<<(d + 255) / 256, 256, 0, st>>>(p.tb, d, k, evals);
+    PTD_CHECK_LAUNCH();
+    // ... then the k wanted ones to full fp64 precision
+    bisect_kernel<<<(k + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
+        p.tb, d, k, p.tb.sel, 0, 12);
+    PTD_CHECK_LAUNCH();
+  }
+  eigvec_kernel<<<(k + 63) / 64, 64, 0, st>>>(p.tb, d, k);
+  PTD_CHECK_LAUNCH();
+  cluster_fix_kernel<<<k, 256, 0, st>>>(p.tb, k);
+  PTD_CHECK_LAUNCH();
+  {
+    const long long total = static_cast<long long>(d) * k;
+    z_to_u_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(p.tb, d, k, U, ldu);
+    PTD_CHECK_LAUNCH();
+  }
+
+  // ---- (3) back-transformation: U <- (I - V_p T_p V_p^T) U for p = last .. first
+  const long long zseg = static_cast<long long>(d) * p.kp;
+  const long long xseg = static_cast<long long>(NB) * p.kp;
+  for (int pi = p.npanels - 1; pi >= 0; --pi) {
+    const int j0 = pi * NB;
+    const int m = d - j0;
+    const int nc = std::min(NB, m);
+    if (m < 2) continue;  // a 1x1 trailing block has no reflector
+    {
+      const long long total = static_cast<long long>(m) * (p.kp / 8);
+      split_z_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+          U, ldu, j0, m, k, p.kp, p.Zs, zseg);
+      PTD_CHECK_LAUNCH();
+    }
+    cudaMemsetAsync(p.X1, 0, static_cast<size_t>(NB) * p.kp * sizeof(float), st);
+    const __nv_bfloat16* vblock = p.Vs + static_cast<long long>(j0) * p.ldv + j0;
+    {
+      GemmOperand a{vblock, 1, p.ldv, 3, static_cast<long long>(d) * p.ldv};
+      GemmOperand b{p.Zs, 1, p.kp, 3, zseg};
+      GemmEpilogue ep;
+      ep.C = p.X1;
+      ep.ldc = p.kp;
+      ep.accumulate = 1;
+      const int rc = gemm_tc(a, b, nc, k, m, -1, ep, st);
+      if (rc) return rc;
+    }
+    {
+      dim3 grid(static_cast<unsigned>((p.kp + 127) / 128), NB);
+      tmul_split_kernel<<<grid, 128, 0, st>>>(p.Tmats + static_cast<size_t>(pi) * NB * NB, p.X1,
+                                              nc, p.kp, p.Xs, xseg);
+      PTD_CHECK_LAUNCH();
+    }
+    {
+      GemmOperand a{vblock, 0, p.ldv, 3, static_cast<long long>(d) * p.ldv};
+      GemmOperand b{p.Xs, 1, p.kp, 3, xseg};
+      GemmEpilogue ep;
+      ep.alpha = -1.f;
+      ep.C = U + static_cast<long long>(j0) * ldu;
+      ep.ldc = ldu;
+      ep.accumulate = 1;
+      const int rc = gemm_tc(a, b, m, k, nc, -1, ep, st);
+      if (rc) return rc;
+    }
+  }
+  return 0;
+}
+
+}  // namespace ptd

@@ -1,0 +1,27 @@
+// Internal interface of the symmetric eigensolver (eigh.cu). Not part of the C-ABI.
+//
+//   d <= 96   one-CTA parallel cyclic Jacobi in fp64 shared memory (all eigenpairs, ~1e-15)
+//   d  > 96   (1) blocked Householder tridiagonalisation: a cooperative persistent panel kernel
+//                 (2 grid barriers per column: column update + reflector, then the symv against
+//                 the trailing matrix) and a tcgen05 rank-2nb trailing update A -= V W^T + W V^T
+//                 (bf16x3 split, fp32-grade);
+//             (2) tridiagonal eigenproblem in fp64: splitting, warp-parallel multisection on the
+//                 Sturm count (one warp per eigenvalue), eigenvectors by twisted factorisation
+//                 (one thread per vector), Gram-Schmidt inside numerically tight clusters;
+//             (3) back-transformation of the k wanted vectors with compact-WY block reflectors,
+//                 two tcgen05 GEMMs per panel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace ptd {
+
+size_t eigh_workspace_bytes(int d, int k);
+
+// A [d][lda] fp32 symmetric (lower triangle authoritative, like torch.linalg.eigh's UPLO='L');
+// not modified. evals[d] ascending. U [d][ldu]: column c holds the eigenvector of eigenvalue
+// number d-k+c (the k largest, ascending). Everything is enqueued on `st`; nothing syncs.
+int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, long long ldu,
+         void* ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace ptd

@@ -1,0 +1,16 @@
+// Internal interface of the decomposed-layer forward (lowrank.cu). Not part of the C-ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace ptd {
+
+size_t lowrank_workspace_bytes(int dtype_is_bf16, long long n, int in_f, int k, int out_f);
+
+// Y[n][out] = (X[n][in] W1[k][in]^T) W2[out][k]^T + bias[out]; X, W1, W2, Y all bf16 or all fp32.
+int lowrank_forward(const void* X, long long ldx, const void* W1, long long ldw1, const void* W2,
+                    long long ldw2, const float* bias, void* Y, long long ldy, int dtype_is_bf16,
+                    long long n, int in_f, int k, int out_f, void* ws, size_t ws_bytes,
+                    cudaStream_t st);
+
+}  // namespace ptd

@@ -1,0 +1,340 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, via ptdeco_b200.linalg / falor / dwain)
+against the oracle and the golden fixtures of the unmodified reference. Tolerances are the
+north_star's: covariance <= 1e-5 relative, eigenvalues <= 1e-4 (normwise), top-k principal-angle
+cosines >= 0.9999, identical ranks."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import primitives as P
+from synth import cases
+
+pytestmark = pytest.mark.gpu
+
+COV_TOL = 1e-5
+EVAL_TOL = 1e-4
+COS_TOL = 0.9999
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(np.asarray(a, np.float64) - np.asarray(b, np.float64))
+                 / np.linalg.norm(np.asarray(b, np.float64)))
+
+
+# ------------------------------------------------------------------------------------ K1 / K2
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n,d", [(1, 8), (37, 10), (1576, 192), (1000, 200), (3136, 1000), (2048, 1024)])
+def test_syrk_matches_oracle(dev, dtype, n, d):
+    from ptdeco_b200 import linalg
+    g = torch.Generator().manual_seed(n * 7919 + d)
+    acc = linalg.CovarianceAccumulator(d, dev, with_mean=True)
+    Ey = np.zeros(d, np.float64)
+    Eyyt = np.zeros((d, d), np.float64)
+    steps = 3
+    for _ in range(steps):
+        y = (torch.randn(n, d, generator=g) * torch.logspace(0, -2, d)).to(dtype)
+        acc.update(y.to(dev))
+        yd = y.double().numpy()
+        Eyyt += yd.T @ yd / n
+        Ey += yd.mean(0)
+    assert acc.steps == steps
+    cov = acc.finalize(use_mean=False, damp_factor=0.0).cpu().numpy()
+    assert _rel(cov, Eyyt / steps) < COV_TOL
+    assert np.array_equal(cov, cov.T)
+    assert np.abs(acc.colsum.cpu().numpy() / steps - Ey / steps).max() < 1e-5 * (np.abs(Ey).max() / steps + 1e-3)
+
+
+def test_syrk_bias_subtraction_and_strided_rows(dev):
+    from ptdeco_b200 import linalg
+    g = torch.Generator().manual_seed(5)
+    n, d = 500, 96
+    y = torch.randn(n, d + 8, generator=g)
+    b = torch.randn(d, generator=g)
+    acc = linalg.CovarianceAccumulator(d, dev)
+    acc.update(y.to(dev)[:, :d], sub=b.to(dev))  # row pitch d+8
+    ref = ((y[:, :d] - b).double().T @ (y[:, :d] - b).double() / n).numpy()
+    assert _rel(acc.finalize(False, 0.0).cpu().numpy(), ref) < COV_TOL
+
+
+@pytest.mark.parametrize("use_mean,use_damping", [(False, True), (True, True), (True, False), (False, False)])
+def test_finalize_matches_falor_covariance(dev, use_mean, use_damping):
+    """F:192-205 including the damping quirk (a no-op when use_mean=True)."""
+    from ptdeco_b200 import linalg
+    d, n, steps = 64, 300, 4
+    g = torch.Generator().manual_seed(11)
+    w = np.eye(d, dtype=np.float32)
+    Ey, Eyyt = np.zeros(d, np.float32), np.zeros((d, d), np.float32)
+    acc = linalg.CovarianceAccumulator(d, dev, with_mean=True)
+    for _ in range(steps):
+        y = torch.randn(n, d, generator=g) + 0.5
+        acc.update(y.to(dev))
+        P.accumulate_Ey_and_Eyyt(Ey, Eyyt, w, y.numpy())
+    ref = P.falor_covariance(Ey, Eyyt, steps, use_mean, use_damping)
+    damp = P.EIGEN_DAMPEN_FACTOR if (use_damping and not use_mean) else 0.0
+    cov = acc.finalize(use_mean=use_mean, damp_factor=damp).cpu().numpy()
+    assert _rel(cov, ref) < COV_TOL
+
+
+def test_syrk_empty_and_bad_arguments(dev):
+    from ptdeco_b200 import _native as nat
+    from ptdeco_b200 import linalg
+    acc = linalg.CovarianceAccumulator(16, dev)
+    with pytest.raises(ValueError):
+        acc.update(torch.zeros(0, 16, device=dev))
+    with pytest.raises(ValueError):
+        acc.update(torch.zeros(4, 17, device=dev))
+    with pytest.raises(nat.NativeError):
+        acc.update(torch.zeros(4, 16))  # CPU tensor: no CPU path
+    with pytest.raises(nat.NativeError):
+        linalg.CovarianceAccumulator(16, torch.device("cpu"))
+
+
+# ------------------------------------------------------------------------------------ K3
+def _check_eigh(cov64, ev, u, k, cos_ks=()):
+    d = cov64.shape[0]
+    ref_ev, ref_u = np.linalg.eigh(cov64)
+    assert np.abs(ev - ref_ev).max() / np.abs(ref_ev).max() < EVAL_TOL
+    assert np.abs(u.T @ u - np.eye(k)).max() < 2e-5
+    resid = np.abs(cov64 @ u - u * ref_ev[d - k:]).max() / np.abs(ref_ev).max()
+    assert resid < 2e-5, resid
+    for kk in cos_ks:
+        assert P.min_principal_cosine(ref_u[:, d - kk:], u[:, k - kk:]) >= COS_TOL
+
+
+def test_eigh_golden_d192(dev, golden_dir):
+    from ptdeco_b200 import linalg
+    g = np.load(os.path.join(golden_dir, "cov_eig_d192.npz"))
+    ev, u = linalg.eigh(torch.from_numpy(g["damped"]).to(dev))
+    ev, u = ev.cpu().numpy().astype(np.float64), u.cpu().numpy().astype(np.float64)
+    assert np.abs(ev - g["evals"]).max() / g["evals"].max() < EVAL_TOL
+    for k in (24, 48, 96):
+        assert P.min_principal_cosine(P.top_k(g["u"], k), P.top_k(u, k)) >= COS_TOL
+    _check_eigh(g["damped"].astype(np.float64), ev, u, 192)
+
+
+@pytest.mark.parametrize("d,k", [(1, 1), (2, 2), (3, 2), (10, 10), (32, 32), (33, 7), (96, 96), (97, 97),
+                                 (128, 128), (130, 65), (200, 50), (576, 288), (768, 384), (1000, 125)])
+def test_eigh_step_spectrum(dev, d, k):
+    from ptdeco_b200 import linalg
+    y = cases.step_spectrum_batch(4 * d + 8, d, 3).double()
+    cov = (y.T @ y / y.shape[0])
+    cov = cov + 0.01 * cov.diagonal().mean() * torch.eye(d, dtype=torch.float64)
+    c32 = cov.float()
+    ev, u = linalg.eigh(c32.to(dev), k=k)
+    assert tuple(u.shape) == (d, k) and tuple(ev.shape) == (d,)
+    cos_ks = [kk for kk in (d // 8, d // 4, d // 2) if 1 <= kk <= k and d >= 32]
+    _check_eigh(c32.double().numpy(), ev.cpu().numpy().astype(np.float64),
+                u.cpu().numpy().astype(np.float64), k, cos_ks)
+
+
+def test_eigh_rank_deficient_with_damping(dev):
+    """Covariance of rank d/4 plus damping: a (d - d/4)-fold near-degenerate cluster."""
+    from ptdeco_b200 import linalg
+    d, r = 320, 80
+    g = torch.Generator().manual_seed(2)
+    y = (torch.randn(4 * d, r, generator=g) @ torch.randn(r, d, generator=g)).float()
+    acc = linalg.CovarianceAccumulator(d, dev)
+    acc.update(y.to(dev))
+    cov = acc.finalize(False, 0.01).clone()
+    ev, u = linalg.eigh(cov)
+    c64 = cov.double().cpu().numpy()
+    _check_eigh(c64, ev.cpu().numpy().astype(np.float64), u.cpu().numpy().astype(np.float64), d, (r // 2, r))
+    assert not np.shares_memory(c64, c64.T) and torch.equal(cov, cov.T)  # input untouched, symmetric
+
+
+def test_eigh_input_not_modified_and_uplo(dev):
+    from ptdeco_b200 import linalg
+    d = 150
+    g = torch.Generator().manual_seed(4)
+    a = torch.randn(d, d, generator=g)
+    sym = (a + a.T) / 2
+    garbage_upper = torch.tril(sym) + torch.triu(torch.randn(d, d, generator=g), 1)  # only lower counts
+    x = garbage_upper.to(dev)
+    keep = x.clone()
+    ev, _ = linalg.eigh(x)
+    assert torch.equal(x, keep)
+    ref = np.linalg.eigvalsh(sym.double().numpy())
+    assert np.abs(ev.cpu().numpy() - ref).max() / np.abs(ref).max() < EVAL_TOL
+
+
+# ------------------------------------------------------------------------------------ K4 / K5 / K7
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("out_f,in_f,k", [(32, 64, 32), (96, 48, 13), (192, 768, 96), (576, 192, 100)])
+def test_factors_match_oracle(dev, dtype, out_f, in_f, k):
+    from ptdeco_b200 import linalg
+    g = torch.Generator().manual_seed(out_f + in_f + k)
+    w = (torch.randn(out_f, in_f, generator=g) / in_f ** 0.5).to(dtype)
+    q, _ = torch.linalg.qr(torch.randn(out_f, out_f, generator=g))
+    uk = q[:, out_f - k:].contiguous().to(dtype)
+    w1 = linalg.factor_w1(w.to(dev), uk.to(dev))
+    deco = linalg.deco_weight(uk.to(dev), w1)
+    U, V, deco_ref = P.factors(w.double().numpy(), uk.double().numpy())
+    tol = 2e-6 if dtype == torch.float32 else 1e-2
+    assert np.abs(w1.double().cpu().numpy() - U.T).max() <= tol * np.abs(U).max()
+    # K5 consumes the (possibly bf16-rounded) W1 the kernel produced
+    deco_ref2 = uk.double().numpy() @ w1.double().cpu().numpy()
+    assert np.abs(deco.double().cpu().numpy() - deco_ref2).max() <= tol * np.abs(deco_ref).max()
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-6), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("n,in_f,k,out_f", [(1, 64, 8, 32), (16, 192, 48, 160), (300, 200, 50, 168),
+                                            (1024, 768, 96, 3072), (2048, 1024, 256, 1024)])
+def test_lowrank_forward(dev, dtype, tol, n, in_f, k, out_f):
+    from ptdeco_b200 import linalg
+    g = torch.Generator().manual_seed(n + k)
+    x = torch.randn(n, in_f, generator=g).to(dtype)
+    w1 = (torch.randn(k, in_f, generator=g) / in_f ** 0.5).to(dtype)
+    w2 = (torch.randn(out_f, k, generator=g) / k ** 0.5).to(dtype)
+    b = torch.randn(out_f, generator=g)
+    y = linalg.lowrank_forward(x.to(dev), w1.to(dev), w2.to(dev), b.to(dev))
+    ref = (x.double() @ w1.double().T) @ w2.double().T + b.double()
+    assert y.dtype == dtype and tuple(y.shape) == (n, out_f)
+    assert (y.double().cpu() - ref).abs().max() <= tol * ref.abs().max()
+
+
+# ------------------------------------------------------------------------------------ K6
+def test_metrics_match_reference(dev, golden_dir):
+    from ptdeco_b200 import utils
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    fx, fy = torch.from_numpy(g["falor_logits_x"]).to(dev), torch.from_numpy(g["falor_logits_y"]).to(dev)
+    dx, dy = torch.from_numpy(g["dwain_logits_x"]).to(dev), torch.from_numpy(g["dwain_logits_y"]).to(dev)
+    assert utils.calc_per_channel_noise_to_signal_ratio(x=fx, y=fy, non_channel_dim=(0,)).item() == \
+        pytest.approx(float(g["falor_logits_nsr"]), rel=1e-5)
+    assert utils.calc_per_channel_noise_to_signal_ratio(x=dx, y=dy, non_channel_dim=(0, 1)).item() == \
+        pytest.approx(float(g["dwain_logits_nsr"]), rel=1e-5)
+    assert utils.calc_kl_loss(fx, fy).item() == pytest.approx(float(g["falor_logits_kl"]), rel=1e-5)
+    np.testing.assert_allclose(utils.calc_kl_divergence(fx, fy).cpu().numpy(), g["falor_logits_kl_rows"],
+                               rtol=2e-4, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------ primitives
+@pytest.mark.parametrize("method", ["falor", "dwain"])
+@pytest.mark.parametrize("kind,bound", [("linear", 1e-6), ("conv", 9e-4)])
+def test_reference_primitive_tests(dev, golden_dir, method, kind, bound):
+    """Mirror of tests/test_deco_primitives_{falor,dwain}.py (full-rank reconstruction), with the
+    reference's own GPU bounds, plus covariance / eigenvector parity against the captured golden."""
+    import ptdeco_b200.dwain.decomposition as D
+    import ptdeco_b200.falor.decomposition as F
+    from ptdeco_b200 import linalg, utils
+    gold = np.load(os.path.join(golden_dir, f"prim_{method}_{kind}.npz"))
+    net, stream = cases.primitive_case(kind, dict_input=(method == "dwain"))
+    net.to(dev)
+    mod = F if method == "falor" else D
+    x = utils.to_device(next(stream), dev)
+    with torch.no_grad():
+        y0 = net(x)
+    mod._wrap_in_place(net, "mod")
+    w = net.mod.get_weight_copy()
+    with torch.no_grad():
+        if method == "falor":
+            u = F._compute_decompositon_of_covariance_matrix(
+                root_module=net, decomposed_submodule_name="mod", data_iterator=stream, weight=w,
+                num_data_steps=8, device=dev, use_float64=True, use_mean=False, use_damping=True)
+        else:
+            u = D._compute_covariance_matrix_decomposition(
+                root_module=net, decomposed_submodule_name="mod", data_iterator=stream, weight=w,
+                num_data_steps=8, device=dev, decompose_in_float64=True)
+        assert tuple(u.shape) == (32, 32)
+        for k in (4, 8, 16):
+            assert P.min_principal_cosine(P.top_k(gold["u"].astype(np.float64), k),
+                                          P.top_k(u.double().cpu().numpy(), k)) >= COS_TOL
+        uk = u[:, u.shape[1] - 32:].to(torch.float)
+        w1 = linalg.factor_w1(w, uk)
+        new = net.get_submodule("mod").get_decomposed_module(u=w1, v=uk)
+        new.to(dev)
+    mod._unwrap_in_place(net, "mod")
+    utils.replace_submodule_in_place(net, "mod", new)
+    with torch.no_grad():
+        y1 = net(x)
+    assert (y0 - y1).abs().max().item() < bound
+
+
+# ------------------------------------------------------------------------------------ drivers
+def _ranks(cfg):
+    return {n: c["modules"]["0"].get("out_features", c["modules"]["0"].get("out_channels"))
+            for n, c in cfg.items()}
+
+
+@pytest.mark.parametrize("name", ["mlp", "convmlp", "deit_small"])
+def test_falor_decompose_in_place_matches_reference(dev, golden_dir, name):
+    import ptdeco_b200.falor as falor
+    from ptdeco_b200 import utils
+    gold = json.load(open(os.path.join(golden_dir, f"falor_{name}.json")))
+    model, stream, kw = cases.falor_case(name)
+    model.to(dev)
+    trace = []
+    cfg = falor.decompose_in_place(module=model, device=dev, data_iterator=stream, trace=trace, **kw)
+    assert stream.position == gold["stream_position"]  # iterator consumption order (fact 10)
+    assert [(t["name"], t["rank"]) for t in trace] == [(t["name"], t["rank"]) for t in gold["trace"]]
+    for t, g in zip(trace, gold["trace"]):
+        assert t["nsr"] == pytest.approx(g["nsr"], rel=5e-3, abs=1e-6)
+        assert t["kl"] == pytest.approx(g["kl"], rel=1e-2, abs=1e-6)
+    assert list(cfg.keys()) == list(gold["decompose_config"].keys())
+    assert _ranks(cfg) == _ranks(gold["decompose_config"])
+    for n in cfg:
+        a = json.loads(json.dumps(cfg[n]))
+        b = gold["decompose_config"][n]
+        ma, mb = a.pop("__meta__"), b.pop("__meta__")
+        assert a == b
+        assert ma["proportion"] == mb["proportion"]
+        assert ma["nsr_final"] == pytest.approx(mb["nsr_final"], rel=5e-3, abs=1e-6)
+    # the config round-trips into a fresh model and the state dict loads strictly (U/m:114-130)
+    fresh, _, _ = cases.falor_case(name)
+    utils.apply_decompose_config_in_place(fresh, json.loads(json.dumps(cfg)))
+    fresh.load_state_dict(model.state_dict(), strict=True)
+    fresh.to(dev).eval()
+    xb = next(stream).to(dev)
+    with torch.no_grad():
+        torch.testing.assert_close(fresh(xb), model(xb))
+
+
+@pytest.mark.parametrize("name", list(cases.DWAIN_CASES))
+def test_dwain_decompose_in_place_matches_reference(dev, golden_dir, name):
+    import ptdeco_b200.dwain as dwain
+    gold = json.load(open(os.path.join(golden_dir, f"dwain_{name}.json")))
+    model, stream, mstream, kw = cases.dwain_case(name)
+    model.to(dev)
+    trace = []
+    cfg = dwain.decompose_in_place(module=model, device=dev, data_iterator=stream,
+                                   metric_iterator=mstream, loss_fn=cases.dwain_loss_fn(name),
+                                   finetune_fn=lambda m, d, names: m, trace=trace, **kw)
+    assert stream.position == gold["stream_position"]
+    assert mstream.position == gold["metric_stream_position"]
+    assert [(t["name"], t["rank"]) for t in trace] == [(t["name"], t["rank"]) for t in gold["trace"]]
+    for t, g in zip(trace, gold["trace"]):
+        assert t["nsr"] == pytest.approx(g["nsr"], rel=1e-2, abs=1e-6)
+    assert list(cfg.keys()) == list(gold["decompose_config"].keys())  # reversed module order
+    assert _ranks(cfg) == _ranks(gold["decompose_config"])
+    for n in cfg:
+        assert cfg[n]["__meta__"]["drop_in_params"] == gold["decompose_config"][n]["__meta__"]["drop_in_params"]
+
+
+# ------------------------------------------------------------------------------------ full size
+def test_full_size_properties_d4096(dev):
+    """BASELINE-size checks through size-independent properties: trace(C) = mean ||y||^2, symmetry,
+    linearity in the number of steps; eigh: orthonormal top-k and small residual."""
+    from ptdeco_b200 import linalg
+    d, n, k = 4096, 8192, 512
+    y = cases.step_spectrum_batch(n, d, 0).to(torch.bfloat16).to(dev)
+    acc = linalg.CovarianceAccumulator(d, dev)
+    acc.update(y)
+    acc.update(y)
+    cov = acc.finalize(False, 0.0)
+    tr = cov.diagonal().double().sum().item()
+    expect = (y.double() ** 2).sum().item() / n
+    assert abs(tr - expect) / expect < 1e-5
+    assert torch.equal(cov, cov.T)
+    ev, u = linalg.eigh(cov, k=k)
+    ud = u.double()
+    assert (ud.T @ ud - torch.eye(k, dtype=torch.float64, device=dev)).abs().max().item() < 5e-5
+    assert abs(ev.double().sum().item() - tr) / tr < 1e-4
+    resid = (cov.double() @ ud - ud * ev[d - k:].double()).abs().max().item() / ev.max().item()
+    assert resid < 5e-5

@@ -1,0 +1,230 @@
+"""CPU tests of the host logic: config schema, wrappers, rank arithmetic, the C-ABI surface, the
+no-CPU-fallback rule, and the world_size-2 gloo path of ptdeco_b200.parallel."""
+import ctypes
+import json
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_capi_exports_every_declared_symbol():
+    from ptdeco_b200 import _native as nat
+    header = open(os.path.join(ROOT, "include", "ptdeco_b200.h")).read()
+    declared = set(re.findall(r"\b(ptdeco_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(nat.SIGNATURES), declared ^ set(nat.SIGNATURES)
+    lib = ctypes.CDLL(nat.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    L = nat.lib()
+    assert L.ptdeco_version() >= 100
+    assert L.ptdeco_strerror(-22).decode().startswith("invalid argument")
+    # pure size queries need no GPU
+    assert L.ptdeco_syrk_workspace_bytes(nat.BF16, 2048, 4096) == 2 * 2048 * 4096
+    assert L.ptdeco_syrk_workspace_bytes(nat.F32, 100, 10) >= 3 * 2 * 100 * 16
+    assert L.ptdeco_eigh_workspace_bytes(64, 64) > 0
+    assert L.ptdeco_eigh_workspace_bytes(4096, 2048) > 4096 * 4096 * 4
+    assert L.ptdeco_eigh_workspace_bytes(10, 11) == 0
+
+
+def test_no_cpu_fallback():
+    from ptdeco_b200 import _native as nat
+    from ptdeco_b200 import linalg, utils
+    import ptdeco_b200.falor as falor
+    with pytest.raises(nat.NativeError):
+        linalg.CovarianceAccumulator(8, torch.device("cpu"))
+    with pytest.raises(nat.NativeError):
+        linalg.eigh(torch.eye(4))
+    with pytest.raises(nat.NativeError):
+        utils.calc_kl_loss(torch.zeros(2, 3), torch.zeros(2, 3))
+    with pytest.raises(nat.NativeError):
+        falor.decompose_in_place(module=torch.nn.Linear(4, 4), device=torch.device("cpu"),
+                                 data_iterator=iter([]), proportion_threshold=0.9,
+                                 nsr_final_threshold=0.1, kl_final_threshold=0.1, num_data_steps=1,
+                                 num_metric_steps=1, use_float64=False, use_mean=False, use_damping=True)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "ptdeco_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert not re.search(r"^\s*(from|import)\s+synth\b", src, re.M), f
+
+
+def test_public_api_names():
+    import ptdeco_b200
+    import ptdeco_b200.falor
+    assert hasattr(ptdeco_b200, "dwain") and hasattr(ptdeco_b200, "utils")
+    for name in ("decompose_in_place", "is_decomposeable_module"):
+        assert hasattr(ptdeco_b200.falor, name) and hasattr(ptdeco_b200.dwain, name)
+    import ptdeco_b200.dwain.decomposition as D
+    import ptdeco_b200.falor.decomposition as F
+    for name in ("_wrap_in_place", "_unwrap_in_place", "_compute_decompositon_of_covariance_matrix",
+                 "WrappedFALORLinear", "WrappedFALORConv2d1x1", "_process_module", "_compute_metrics"):
+        assert hasattr(F, name), name
+    for name in ("_wrap_in_place", "_unwrap_in_place", "_compute_covariance_matrix_decomposition",
+                 "CovarianceComputingLinearModule", "_get_params_for_proportion", "_is_num_params_reduced",
+                 "_precompute_covariance_matrix_decompositions_in_splits", "WrappedDWAINLinear"):
+        assert hasattr(D, name), name
+    for name in ("apply_decompose_config_in_place", "get_module_config", "build_module_from_config",
+                 "MODCONFIG_META_KEY", "replace_submodule_in_place", "calc_per_channel_noise_to_signal_ratio",
+                 "calc_kl_divergence", "calc_kl_loss", "to_device", "get_num_params", "free_gpu_reserved_memory"):
+        assert hasattr(ptdeco_b200.utils, name), name
+    import inspect
+    sig = inspect.signature(ptdeco_b200.dwain.decompose_in_place)
+    assert sig.parameters["min_rank"].default == 32 and sig.parameters["reduction_factor"].default == 0.5
+    assert sig.parameters["decompose_in_float64"].default is True
+    assert all(p.kind is inspect.Parameter.KEYWORD_ONLY for p in sig.parameters.values())
+
+
+def test_is_decomposeable_and_wrapping():
+    import ptdeco_b200.falor.decomposition as F
+    assert F.is_decomposeable_module(torch.nn.Linear(3, 4))
+    assert F.is_decomposeable_module(torch.nn.Conv2d(3, 4, 1))
+    assert F.is_decomposeable_module(torch.nn.Conv2d(3, 4, 1, stride=2))  # accepted, like the reference
+    assert not F.is_decomposeable_module(torch.nn.Conv2d(4, 4, 1, groups=2))
+    assert not F.is_decomposeable_module(torch.nn.Conv2d(3, 4, 3))
+    assert F.is_decomposeable_module(torch.nn.modules.linear.NonDynamicallyQuantizableLinear(3, 3))
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 1), torch.nn.ReLU(), torch.nn.Conv2d(8, 4, 3))
+    F._wrap_in_place(net, "0")
+    assert isinstance(net[0], F.WrappedFALORConv2d1x1)
+    x = torch.randn(2, 3, 5, 5)
+    y = net[0](x)
+    assert tuple(net[0].get_last_input().shape) == (50, 3)
+    assert torch.equal(net[0].get_last_input(), x.permute(0, 2, 3, 1).reshape(-1, 3))
+    assert tuple(net[0].get_weight_copy().shape) == (8, 3)
+    net[0].capture_output = True
+    y = net[0](x)
+    assert torch.equal(net[0].get_last_output_rows(), y.permute(0, 2, 3, 1).reshape(-1, 8))
+    with torch.no_grad():
+        two = net[0].get_decomposed_module(u=torch.randn(2, 3), v=torch.randn(8, 2))
+    assert [tuple(p.shape) for p in two.parameters()] == [(2, 3, 1, 1), (8, 2, 1, 1), (8,)]
+    assert torch.equal(two[1].bias, net[0].get_orig_module().bias) and two[0].bias is None
+    F._unwrap_in_place(net, "0")
+    assert isinstance(net[0], torch.nn.Conv2d)
+    with pytest.raises(ValueError):
+        F._wrap_in_place(net, "2")
+    with pytest.raises(AttributeError):
+        F._wrap_in_place(net, "nope")
+
+
+def test_rank_arithmetic_matches_reference_formulas():
+    import ptdeco_b200.dwain.decomposition as D
+    assert D._get_params_for_proportion(1.0, 4096, 14336) == 4096 * 14336
+    assert D._get_params_for_proportion(0.5, 4096, 4096) == int((8192) * 0.5 * 4096)
+    assert D._get_params_for_proportion(100 / 192, 192, 576) == int((192 + 576) * (100 / 192) * 192)
+    assert D._is_num_params_reduced(0.25, 64, 64) and not D._is_num_params_reduced(0.5, 64, 64)
+    assert D._max_rank_consumed(4096, 14336, 0.5) == 2048
+    assert D._max_rank_consumed(3, 3, 0.5) == 1
+
+
+def test_modconfig_roundtrip_and_schema():
+    from ptdeco_b200 import utils
+    seq = torch.nn.Sequential(torch.nn.Linear(6, 3, bias=False), torch.nn.Linear(3, 5))
+    cfg = utils.get_module_config(seq)
+    assert cfg == {"type": "Sequential", "modules": {
+        "0": {"type": "Linear", "in_features": 6, "out_features": 3, "bias": False},
+        "1": {"type": "Linear", "in_features": 3, "out_features": 5, "bias": True}}}
+    conv = torch.nn.Sequential(torch.nn.Conv2d(4, 2, 1, bias=False), torch.nn.Conv2d(2, 7, 1))
+    ccfg = json.loads(json.dumps(utils.get_module_config(conv)))  # tuples -> lists, like the artifact
+    assert list(ccfg["modules"]["0"].keys()) == ["type", "in_channels", "out_channels", "kernel_size", "bias",
+                                                 "groups", "padding", "padding_mode", "stride", "dilation"]
+    ccfg["__meta__"] = {"proportion": 0.5}
+    rebuilt = utils.build_module_from_config(ccfg)
+    assert isinstance(rebuilt[1], torch.nn.Conv2d) and rebuilt[1].out_channels == 7
+    model = torch.nn.ModuleDict({"a": torch.nn.Linear(6, 5), "b": torch.nn.Conv2d(4, 7, 1)})
+    utils.apply_decompose_config_in_place(model, {"a": cfg, "b": ccfg})
+    assert isinstance(model["a"], torch.nn.Sequential) and isinstance(model["b"], torch.nn.Sequential)
+    model["a"].load_state_dict(seq.state_dict(), strict=True)
+    named = torch.nn.Sequential()
+    named.add_module("first", torch.nn.Linear(2, 2))
+    assert list(utils.build_module_from_config(utils.get_module_config(named))._modules) == ["first"]
+    with pytest.raises(ValueError):
+        utils.build_module_from_config({"type": "GRU"})
+    with pytest.raises(ValueError):
+        utils.get_module_config(torch.nn.ReLU())
+    with pytest.raises(ValueError):
+        utils.to_device([1, 2], torch.device("cpu"))
+    tied = torch.nn.Linear(4, 4)
+    holder = torch.nn.ModuleList([tied, tied])
+    assert utils.get_num_params(holder) == 20
+
+
+def test_shard_plan():
+    from ptdeco_b200 import parallel
+    assert parallel.steps_of_rank(10, 1, 4) == [1, 5, 9]
+    assert sorted(sum((parallel.steps_of_rank(7, r, 3) for r in range(3)), [])) == list(range(7))
+    assert [parallel.owner_of(i, 8) for i in (0, 7, 8, 225)] == [0, 7, 0, 1]
+    assert parallel.rank_and_world(None) == (0, 1)
+
+
+class _FakeAcc:
+    """Stands in for linalg.CovarianceAccumulator on CPU: the partial sums come from the oracle."""
+
+    def __init__(self, d):
+        self.C = torch.zeros(d, d)
+        self.colsum = None
+        self.steps = 0
+
+
+def _gloo_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from oracle import primitives as P
+    from ptdeco_b200 import parallel
+    from synth import cases
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    group = parallel.default_group()
+    assert parallel.rank_and_world(group) == (rank, world)
+    d, n, steps, k = 24, 64, 5, 6
+    results = {}
+    for layer in range(3):
+        acc = _FakeAcc(d)
+        for i in parallel.steps_of_rank(steps, rank, world):
+            y = cases.step_spectrum_batch(n, d, 10 * layer + i).numpy()
+            part = np.zeros((d, d), np.float32)
+            P.update_Eyyt_in_place(part, y)
+            acc.C += torch.from_numpy(part)
+            acc.steps += 1
+
+        def compute():
+            cov = (acc.C / acc.steps).numpy()
+            return torch.from_numpy(P.top_k(P.dwain_get_eigenvectors(cov), k).astype(np.float32).copy())
+
+        u = parallel.owner_computes(layer, group, compute, acc, (d, k))
+        assert acc.steps == steps
+        results[layer] = u
+    t = parallel.mean_over_ranks(torch.tensor([float(rank)], dtype=torch.float64), group)
+    assert t.item() == pytest.approx((world - 1) / 2)
+    assert parallel.max_over_ranks(float(rank), torch.device("cpu")) == world - 1
+    torch.save(results, os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharded_covariance(tmp_path):
+    """world_size 2 on CPU: sharded steps + reduce-to-owner + owner eigensolve + broadcast gives
+    every rank the same subspace as the single-process computation."""
+    from oracle import primitives as P
+    from synth import cases
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0 = torch.load(os.path.join(tmp_path, "rank0.pt"))
+    r1 = torch.load(os.path.join(tmp_path, "rank1.pt"))
+    d, n, steps, k = 24, 64, 5, 6
+    for layer in range(3):
+        assert torch.equal(r0[layer], r1[layer])
+        full = np.zeros((d, d), np.float32)
+        for i in range(steps):
+            P.update_Eyyt_in_place(full, cases.step_spectrum_batch(n, d, 10 * layer + i).numpy())
+        u = P.top_k(P.dwain_get_eigenvectors(full / steps), k)
+        assert P.min_principal_cosine(u, r0[layer].numpy()) > 0.9999
