@@ -1,0 +1,363 @@
+"""Benchmark of the calibration hot path (BASELINE.json: "calib tokens/s", configs[2]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-e2e] [--no-extra]
+
+Workload (config.workload): dwain calibration of a Llama-3-8B-shape decoder -- per step one
+2048-token bf16 sequence per GPU is folded into the fp32 output covariances of all 224 target
+Linears (32 x {q 4096, k 1024, v 1024, o 4096, gate 14336, up 14336, down 4096}); tokens are
+sharded over GPUs (weak scaling), the only exchange is the final d x d reduction, timed separately.
+
+  value   tokens/s with the layer outputs already resident in HBM: 224 tcgen05 SYRK launches/step
+  e2e     tokens/s through the public API path (ptdeco_b200.dwain covariance-computing modules
+          installed in a random-init Llama-3-8B-shape model): pinned host token ids -> H2D ->
+          full model forward (layer forwards on the tcgen05 GEMM engine, SYRK per target) -> D2H
+          of a per-step checksum
+  roofline    tensor-bound: algorithmic N*d*(d+1) FLOP / CUDA-event time vs MEASURED_PEAKS.json
+  cpu_baseline / --impl reference   the reference's _update_Eyyt_in_place arithmetic (oracle port,
+          numpy fp32 on all host cores) on a bounded sample: the 7 targets of ONE decoder layer,
+          scaled by 1/32 to the whole model
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LAYER_DIMS = [("q_proj", 4096), ("k_proj", 1024), ("v_proj", 1024), ("o_proj", 4096),
+              ("gate_proj", 14336), ("up_proj", 14336), ("down_proj", 4096)]
+N_LAYERS = 32
+SEQ = 2048
+METRIC = "calib tokens/s"
+UNIT = "tokens/s"
+
+
+def alg_flops_per_token() -> float:
+    return float(N_LAYERS * sum(d * (d + 1) for _, d in LAYER_DIMS))
+
+
+def load_peaks() -> tuple[dict, str]:
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows: list[list[str]] = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self) -> dict:
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4),
+                              ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_sample(threads: int) -> tuple[float, str]:
+    """One bounded sample of the reference arithmetic (D:147-152, oracle port) on the host:
+    fp32 y^T y / N for the 7 targets of one decoder layer, N = 2048. Returns (tokens/s scaled to the
+    32-layer model, description)."""
+    import torch
+
+    from oracle import torch_cpu as R
+
+    torch.set_num_threads(threads)
+    gen = torch.Generator().manual_seed(1314159)
+    t = 0.0
+    for _, d in LAYER_DIMS:
+        y = torch.randn(SEQ, d, generator=gen)
+        acc = torch.zeros(d, d)
+        t0 = time.perf_counter()
+        R.update_Eyyt_in_place(acc, y)
+        t += time.perf_counter() - t0
+    return SEQ / (N_LAYERS * t), ("oracle port of _update_Eyyt_in_place (torch CPU fp32 einsum, all host threads) on "
+                                  "the 7 targets of 1 of 32 decoder layers, 2048 tokens; tokens/s scaled by 1/32")
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_sample(cores)
+    vals = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, sample = cpu_sample(cores)
+        vals.append(v)
+    dt = time.perf_counter() - t0
+    value = sum(vals) / len(vals)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {"workload": "BASELINE configs[2]: dwain calibration, Llama-3-8B-shape decoder (random init, bf16), "
+                        "2048-token synthetic sequences, all 224 target Linears",
+            "tokens_per_step_per_gpu": SEQ, "global_tokens_per_step": SEQ * n_gpus,
+            "parallelism": f"dp{n_gpus} (tokens sharded, d x d fp32 reduction at the end)",
+            "l2": "inputs (176 MB) + accumulators (59 GB) exceed the 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ptdeco_b200")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--layers", type=int, default=N_LAYERS, help="debug: fewer decoder layers")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from ptdeco_b200 import _native as nat
+    from ptdeco_b200 import linalg, parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nat.lib()
+    n_layers = args.layers
+    peaks, peak_src = load_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- value: SYRK over resident layer outputs -----------------------------------
+    g = torch.Generator(device=dev).manual_seed(1314159 + rank)
+    acts = {name: torch.randn(SEQ, d, generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+            for name, d in LAYER_DIMS}
+    accs = [[linalg.CovarianceAccumulator(d, dev) for _, d in LAYER_DIMS] for _ in range(n_layers)]
+    launches_per_step = n_layers * len(LAYER_DIMS)
+
+    def syrk_step():
+        for layer in accs:
+            for (name, _), acc in zip(LAYER_DIMS, layer):
+                acc.update(acts[name])
+
+    for _ in range(args.warmup):
+        syrk_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            syrk_step()
+        e1.record()
+        barrier()
+    ms = parallel.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+    tokens_per_step = SEQ * world
+    value = tokens_per_step / (ms * 1e-3)
+    flops_step = (n_layers / N_LAYERS) * alg_flops_per_token() * SEQ  # per GPU
+    achieved = flops_step / (ms * 1e-3) / 1e12
+    peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+
+    # exchange: one reduction of every covariance to its owner (once per calibration, not per step)
+    exchange_ms = None
+    if world > 1:
+        barrier()
+        e0.record()
+        for li, layer in enumerate(accs):
+            for ti, acc in enumerate(layer):
+                parallel.reduce_accumulator_to(acc, parallel.owner_of(li * len(LAYER_DIMS) + ti, world),
+                                               parallel.default_group())
+        e1.record()
+        barrier()
+        exchange_ms = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
+    del accs
+    torch.cuda.empty_cache()
+
+    # ---------------- extra: eigh @ d=4096 next to the host CPU ---------------------------------
+    extra = {}
+    if not args.no_extra and rank == 0:
+        try:
+            d = 4096
+            y = torch.randn(4 * d, d, generator=g, device=dev) * torch.logspace(0, -2, d, device=dev)
+            acc = linalg.CovarianceAccumulator(d, dev)
+            acc.update(y)
+            cov = acc.finalize(False, 0.01).clone()
+            linalg.eigh(cov)
+            torch.cuda.synchronize()
+            e0.record()
+            linalg.eigh(cov)
+            e1.record()
+            torch.cuda.synchronize()
+            extra["eigh_ms_d4096_full"] = e0.elapsed_time(e1)
+            e0.record()
+            linalg.eigh(cov, k=2048)
+            e1.record()
+            torch.cuda.synchronize()
+            extra["eigh_ms_d4096_top2048"] = e0.elapsed_time(e1)
+            if world == 1:
+                c = cov.cpu()
+                torch.set_num_threads(os.cpu_count() or 1)
+                t0 = time.perf_counter()
+                torch.linalg.eigh(c)
+                extra["eigh_ms_d4096_host_cpu_fp32"] = 1e3 * (time.perf_counter() - t0)
+                extra["host_cores"] = os.cpu_count()
+            del cov, acc, y
+        except Exception as exc:  # the headline number must survive an extra failing
+            extra["eigh_error"] = repr(exc)[:200]
+    torch.cuda.empty_cache()
+
+    # ---------------- e2e: public API path with host token ids ----------------------------------
+    e2e = None
+    forward_only_ms = None
+    if not args.no_e2e:
+        import ptdeco_b200.dwain.decomposition as D
+        from synth import models
+
+        with torch.device(dev):
+            model = models.LlamaLikeDecoder(layers=n_layers, init=False).to(torch.bfloat16)
+        models.fast_init_(model, 271828)
+        model.eval()
+        names = D._get_decomposeable_submodule_names(model, ["lm_head"])
+        gen = torch.Generator().manual_seed(1314159 + rank)
+        host_tokens = [torch.randint(0, 128256, (1, SEQ), generator=gen).pin_memory()
+                       for _ in range(args.warmup + args.steps)]
+        check = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+        def fwd(ids_host):
+            ids = ids_host.to(dev, non_blocking=True)
+            with torch.no_grad():
+                out = model({"input_ids": ids})
+            return out
+
+        for i in range(args.warmup):  # plain forward (the user's model alone), for reference
+            fwd(host_tokens[i])
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            fwd(host_tokens[args.warmup + i])
+        e1.record()
+        barrier()
+        forward_only_ms = parallel.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+
+        originals = D._install_covariance_modules(model, names, True)
+        last = model.get_submodule(names[-1])
+
+        def e2e_step(ids_host):
+            fwd(ids_host)
+            check.copy_(last.acc.C[0, :1], non_blocking=True)  # D2H read of the step's result
+            torch.cuda.current_stream().synchronize()
+
+        for i in range(args.warmup):
+            e2e_step(host_tokens[i])
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(args.steps):
+            e2e_step(host_tokens[args.warmup + i])
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        e2e_ms = parallel.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+        e2e = {"value": tokens_per_step / (e2e_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": SEQ * 8, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
+               "model_forward_only_ms": forward_only_ms,
+               "path": "ptdeco_b200.dwain covariance-computing modules in a Llama-3-8B-shape model"}
+        D._restore_modules(model, originals)
+        del model, originals
+        torch.cuda.empty_cache()
+
+    # ---------------- CPU baseline (rank 0, N = 1) ----------------------------------------------
+    cpu = None
+    if world == 1:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cpu_sample(cores)
+        v, sample = cpu_sample(cores)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
+            "clocks": clk.summary(),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "kernel": "gemm_tc_kernel<MN,MN,256> (SYRK, lower triangle)",
+                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})",
+                         "algorithmic_flop_per_token": alg_flops_per_token()},
+            "gpu_launches": launches_per_step * args.steps,
+            "e2e": e2e, "cpu_baseline": cpu, "extra": extra,
+        }
+        if exchange_ms is not None:
+            line["exchange_ms_all_covariances"] = exchange_ms
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

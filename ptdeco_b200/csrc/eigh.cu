@@ -237,8 +237,10 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
   float* gWs = pbuf + g.rows_per_cta;        // [NB]  W^T v
   float* gVs = gWs + NB;                     // [NB]  V^T v
   float* red = gVs + NB;                     // [PANEL_WARPS][2*NB]
+  float* pseg = red + PANEL_WARPS * 2 * NB;  // [rows_per_cta][segments] symv partials
   __shared__ double sred[PANEL_WARPS];
   __shared__ double s_scal[4];
+  __shared__ double sum3[3 * (2 * NB + 1)];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x, cta = blockIdx.x;
@@ -315,31 +317,48 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
     for (int r = tid; r < NB; r += PANEL_THREADS) Vt[r * (NB + 1) + i] = (r < L) ? vs[r] : 0.f;
 
     if (tau != 0.f) {
+      // symv over the CTA's row block, split into (row, 1024-float segment) items so that every
+      // lane keeps 8 independent 16-byte loads in flight even when the block has few rows
       const int n4 = L >> 2;
       const float4* v4 = reinterpret_cast<const float4*>(vs);
-      for (int r = max(r0, i + 1) + warp; r < r1; r += PANEL_WARPS) {
-        const float4* arow = reinterpret_cast<const float4*>(Abase + static_cast<long long>(r) * g.ldA);
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        int c4 = lane;
-        for (; c4 + 96 < n4; c4 += 128) {
-          const float4 a0 = __ldg(arow + c4), a1 = __ldg(arow + c4 + 32);
-          const float4 a2 = __ldg(arow + c4 + 64), a3 = __ldg(arow + c4 + 96);
-          const float4 x0 = v4[c4], x1 = v4[c4 + 32], x2 = v4[c4 + 64], x3 = v4[c4 + 96];
-          s0 += a0.x * x0.x + a0.y * x0.y + a0.z * x0.z + a0.w * x0.w;
-          s1 += a1.x * x1.x + a1.y * x1.y + a1.z * x1.z + a1.w * x1.w;
-          s2 += a2.x * x2.x + a2.y * x2.y + a2.z * x2.z + a2.w * x2.w;
-          s3 += a3.x * x3.x + a3.y * x3.y + a3.z * x3.z + a3.w * x3.w;
+      const int rbeg = max(r0, i + 1);
+      const int R = max(0, r1 - rbeg);
+      const int seg0 = (i + 1) >> 10;  // segments entirely left of column i+1 multiply zeros
+      const int nseg = ((n4 + 255) >> 8) - seg0;
+      for (int item = warp; item < R * nseg; item += PANEL_WARPS) {
+        const int rr = item / nseg, sg = item - rr * nseg + seg0;
+        const float4* arow =
+            reinterpret_cast<const float4*>(Abase + static_cast<long long>(rbeg + rr) * g.ldA);
+        const int cbase = (sg << 8) + lane;
+        float4 a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int c4 = cbase + 32 * u;
+          a[u] = (c4 < n4) ? __ldg(arow + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        for (; c4 < n4; c4 += 32) {
-          const float4 a0 = __ldg(arow + c4);
-          const float4 x0 = v4[c4];
-          s0 += a0.x * x0.x + a0.y * x0.y + a0.z * x0.z + a0.w * x0.w;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) {
+          const int c4 = cbase + 32 * u;
+          if (c4 < n4) {
+            const float4 x = v4[c4];
+            s0 += a[u].x * x.x + a[u].y * x.y + a[u].z * x.z + a[u].w * x.w;
+          }
+          if (c4 + 32 < n4) {
+            const float4 x = v4[c4 + 32];
+            s1 += a[u + 1].x * x.x + a[u + 1].y * x.y + a[u + 1].z * x.z + a[u + 1].w * x.w;
+          }
         }
-        const float s = warp_sum((s0 + s1) + (s2 + s3));
-        if (lane == 0) {
-          pbuf[r - r0] = s;
-          if (r < NB) g.ptop[r] = s;
-        }
+        const float s = warp_sum(s0 + s1);
+        if (lane == 0) pseg[rr * nseg + (sg - seg0)] = s;
+      }
+      __syncthreads();
+      for (int rr = tid; rr < R; rr += PANEL_THREADS) {
+        float s = 0.f;
+        for (int sg = 0; sg < nseg; ++sg) s += pseg[rr * nseg + sg];
+        const int r = rbeg + rr;
+        pbuf[r - r0] = s;
+        if (r < NB) g.ptop[r] = s;
       }
       __syncthreads();
       float aw0 = 0.f, aw1 = 0.f, av0 = 0.f, av1 = 0.f;
@@ -376,9 +395,15 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
 
     // ---------------------------------------------------------------- P3: w column
     if (tau != 0.f) {
-      if (tid <= 2 * NB) {
+      if (tid < 3 * (2 * NB + 1)) {  // 3 thread groups each sum a third of the CTAs' partials
+        const int part = tid / (2 * NB + 1), idx = tid - part * (2 * NB + 1);
         double s = 0.0;
-        for (int c = 0; c < G; ++c) s += static_cast<double>(__ldcg(g.gpart + c * GP_STRIDE + tid));
+        for (int c = part; c < G; c += 3) s += static_cast<double>(__ldcg(g.gpart + c * GP_STRIDE + idx));
+        sum3[part * (2 * NB + 1) + idx] = s;
+      }
+      __syncthreads();
+      if (tid <= 2 * NB) {
+        const double s = sum3[tid] + sum3[(2 * NB + 1) + tid] + sum3[2 * (2 * NB + 1) + tid];
         if (tid < NB) gWs[tid] = static_cast<float>(s);
         else if (tid < 2 * NB) gVs[tid - NB] = static_cast<float>(s);
         else s_scal[1] = s;
@@ -574,29 +599,34 @@ __device__ __forceinline__ int sturm_count(const double* __restrict__ D,
   return cnt;
 }
 
-// One warp per eigenvalue: 32-way multisection on the Sturm count (5 bits per pass).
+// LPE lanes per eigenvalue: (LPE+1)-way multisection on the Sturm count, log2(LPE+1) bits per pass.
+// 8 lanes cost 2.5x the arithmetic of plain bisection (32 lanes: 6.4x) and still give the FP64 pipe
+// 8 d independent recurrences to overlap.
 // first = 1: start from the Gershgorin interval of the block; else continue from lamA/lamB.
+constexpr int LPE = 8;
 __global__ void bisect_kernel(TriBufs b, int d, int count, const int* __restrict__ sel, int first,
                               int passes) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (w >= count) return;
-  const int t = sel ? sel[w] : w;
+  const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = gthread / LPE;
+  const int sub = threadIdx.x & (LPE - 1);                  // lane within the eigenvalue's group
+  const int gshift = (threadIdx.x & 31) & ~(LPE - 1);       // first lane of the group in the warp
+  const unsigned gmask = ((1u << LPE) - 1u) << gshift;
+  const bool active = w < count;
+  const int t = active ? (sel ? sel[w] : w) : 0;
   const int lo = b.blo[t], hi = b.bhi[t];
   const int q = t - lo;
   if (lo == hi) {
-    if (lane == 0) { b.lamA[t] = b.D[lo]; b.lamB[t] = b.D[lo]; }
-    return;
+    if (active && sub == 0) { b.lamA[t] = b.D[lo]; b.lamB[t] = b.D[lo]; }
   }
   double gl = DBL_MAX, gu = -DBL_MAX, e2max = 0.0;
-  for (int i = lo + lane; i <= hi; i += 32) {
+  for (int i = lo + sub; i <= hi; i += LPE) {
     const double el = i > lo ? fabs(b.E[i - 1]) : 0.0;
     const double er = i < hi ? fabs(b.E[i]) : 0.0;
     gl = fmin(gl, b.D[i] - el - er);
     gu = fmax(gu, b.D[i] + el + er);
     e2max = fmax(e2max, er * er);
   }
-  for (int o = 16; o > 0; o >>= 1) {
+  for (int o = LPE / 2; o > 0; o >>= 1) {
     gl = fmin(gl, __shfl_xor_sync(0xffffffffu, gl, o));
     gu = fmax(gu, __shfl_xor_sync(0xffffffffu, gu, o));
     e2max = fmax(e2max, __shfl_xor_sync(0xffffffffu, e2max, o));
@@ -612,22 +642,26 @@ __global__ void bisect_kernel(TriBufs b, int d, int count, const int* __restrict
     a = b.lamA[t];
     bb = b.lamB[t];
   }
+  const bool work = active && lo != hi;
   for (int pass = 0; pass < passes; ++pass) {
-    if (bb - a <= 2.0 * DBL_EPSILON * fmax(fabs(a), fabs(bb)) + 2.0 * pivmin) break;
-    const double wdt = (bb - a) / 33.0;
-    const double x = a + wdt * (lane + 1);
-    const int cnt = sturm_count(b.D, b.E2, lo, hi, x, pivmin);
-    const unsigned mask = __ballot_sync(0xffffffffu, cnt >= q + 1);
-    if (mask == 0u) {
-      a = a + wdt * 32.0;
-    } else {
-      const int f = __ffs(mask) - 1;
-      const double na = a + wdt * f, nb = a + wdt * (f + 1);
-      a = na;
-      bb = nb;
+    // every lane of the warp runs every pass (the ballot is warp-wide); converged groups idle
+    const bool done = !work || (bb - a <= 2.0 * DBL_EPSILON * fmax(fabs(a), fabs(bb)) + 2.0 * pivmin);
+    const double wdt = (bb - a) / (LPE + 1);
+    const double x = a + wdt * (sub + 1);
+    const int cnt = done ? 0 : sturm_count(b.D, b.E2, lo, hi, x, pivmin);
+    const unsigned mask = (__ballot_sync(0xffffffffu, !done && cnt >= q + 1) & gmask) >> gshift;
+    if (!done) {
+      if (mask == 0u) {
+        a = a + wdt * LPE;
+      } else {
+        const int f = __ffs(mask) - 1;
+        const double na = a + wdt * f, nb = a + wdt * (f + 1);
+        a = na;
+        bb = nb;
+      }
     }
   }
-  if (lane == 0) { b.lamA[t] = a; b.lamB[t] = bb; }
+  if (work && sub == 0) { b.lamA[t] = a; b.lamB[t] = bb; }
 }
 
 // rank of every eigenvalue in the global ascending order (ties by row id); scatter eigenvalues
@@ -693,30 +727,59 @@ __global__ void eigvec_kernel(TriBufs b, int d, int k) {
     dp = (b.D[i + 1] - lam) - l * e;
     b.Dp[(i + 1) * K + c] = dp;
   }
+  // The remaining passes read D+ / D- back from global memory; the loads do not depend on the
+  // recurrence, so they are issued eight at a time ahead of the dependent chain.
   double dm = b.D[hi] - lam;
   b.Dm[hi * K + c] = dm;
   double best = fabs(dp);  // gamma at hi = Dp[hi]
   int r = hi;
-  for (int i = hi - 1; i >= lo; --i) {
-    const double e = b.E[i];
-    const double u = e / guard_piv(dm, pivmin);
-    const double dl = b.D[i] - lam;
-    dm = dl - u * e;
-    b.Dm[i * K + c] = dm;
-    const double gam = fabs(b.Dp[i * K + c] + dm - dl);
-    if (gam < best) { best = gam; r = i; }
+  for (int i0 = hi - 1; i0 >= lo; i0 -= 8) {
+    double dpv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) dpv[u] = (i0 - u >= lo) ? b.Dp[(i0 - u) * K + c] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 - u;
+      if (i >= lo) {
+        const double e = b.E[i];
+        const double uu = e / guard_piv(dm, pivmin);
+        const double dl = b.D[i] - lam;
+        dm = dl - uu * e;
+        b.Dm[i * K + c] = dm;
+        const double gam = fabs(dpv[u] + dm - dl);
+        if (gam < best) { best = gam; r = i; }
+      }
+    }
   }
   double zz = 1.0, nn = 1.0;
-  for (int i = r - 1; i >= lo; --i) {
-    zz = -(b.E[i] / guard_piv(b.Dp[i * K + c], pivmin)) * zz;
-    b.Dp[i * K + c] = zz;
-    nn += zz * zz;
+  for (int i0 = r - 1; i0 >= lo; i0 -= 8) {
+    double dpv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) dpv[u] = (i0 - u >= lo) ? b.Dp[(i0 - u) * K + c] : 1.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 - u;
+      if (i >= lo) {
+        zz = -(b.E[i] / guard_piv(dpv[u], pivmin)) * zz;
+        b.Dp[i * K + c] = zz;
+        nn += zz * zz;
+      }
+    }
   }
   zz = 1.0;
-  for (int i = r; i < hi; ++i) {
-    zz = -(b.E[i] / guard_piv(b.Dm[(i + 1) * K + c], pivmin)) * zz;
-    b.Dp[(i + 1) * K + c] = zz;
-    nn += zz * zz;
+  for (int i0 = r; i0 < hi; i0 += 8) {
+    double dmv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) dmv[u] = (i0 + u < hi) ? b.Dm[(i0 + u + 1) * K + c] : 1.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u;
+      if (i < hi) {
+        zz = -(b.E[i] / guard_piv(dmv[u], pivmin)) * zz;
+        b.Dp[(i + 1) * K + c] = zz;
+        nn += zz * zz;
+      }
+    }
   }
   b.Dp[r * K + c] = 1.0;
   b.znorm[c] = sqrt(nn);
@@ -994,8 +1057,9 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
     g.bar = p.bars + pi;
     const int grid = (m + g.rows_per_cta - 1) / g.rows_per_cta;
     const long long L = p.ldA - j0;
+    const size_t nseg_max = static_cast<size_t>((L / 4 + 255) / 256);
     const size_t smem = (static_cast<size_t>(L) + 2 * NB * (NB + 1) + g.rows_per_cta + 2 * NB +
-                         PANEL_WARPS * 2 * NB) * sizeof(float);
+                         PANEL_WARPS * 2 * NB + g.rows_per_cta * nseg_max) * sizeof(float);
     if (smem > 220 * 1024) return -22;  // d beyond what one SM's shared memory can stage
     void* args[] = {&g};
     if (cudaLaunchCooperativeKernel(reinterpret_cast<void*>(sytrd_panel_kernel), dim3(grid),
@@ -1028,19 +1092,17 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
   tri_prep_kernel<<<1, 1024, 0, st>>>(p.dvec, p.evec, d, p.tb);
   PTD_CHECK_LAUNCH();
   {
-    const int warps_per_block = 4;
-    // all eigenvalues to ~2^-35 of the block norm (enough for ordering and the fp32 output) ...
-    bisect_kernel<<<(d + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
-        p.tb, d, d, nullptr, 1, 7);
+    const int tpb = 128, per_block = tpb / LPE;
+    // all eigenvalues to ~2^-31 of the block norm (enough for ordering and the fp32 output) ...
+    bisect_kernel<<<(d + per_block - 1) / per_block, tpb, 0, st>>>(p.tb, d, d, nullptr, 1, 10);
     PTD_CHECK_LAUNCH();
     rank_kernel<<<(d + 255) / 256, 256, 0, st>>>(p.tb, d, k, evals);
     PTD_CHECK_LAUNCH();
     // ... then the k wanted ones to full fp64 precision
-    bisect_kernel<<<(k + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
-        p.tb, d, k, p.tb.sel, 0, 12);
+    bisect_kernel<<<(k + per_block - 1) / per_block, tpb, 0, st>>>(p.tb, d, k, p.tb.sel, 0, 9);
     PTD_CHECK_LAUNCH();
   }
-  eigvec_kernel<<<(k + 63) / 64, 64, 0, st>>>(p.tb, d, k);
+  eigvec_kernel<<<(k + 31) / 32, 32, 0, st>>>(p.tb, d, k);
   PTD_CHECK_LAUNCH();
   cluster_fix_kernel<<<k, 256, 0, st>>>(p.tb, k);
   PTD_CHECK_LAUNCH();

@@ -352,6 +352,30 @@ def _add_meta_to_module_config(module_config: dict[str, Any], module_deco_result
         k: v for k, v in module_deco_results.items() if k != "decomposed_module"}
 
 
+def _install_covariance_modules(module: torch.nn.Module, submodule_names: list[str],
+                                decompose_in_float64: bool) -> dict[str, torch.nn.Module]:
+    """D:592-603: swap every listed Linear for a CovarianceComputingLinearModule that shares its
+    weight and bias. Returns the originals for _restore_modules."""
+    originals: dict[str, torch.nn.Module] = {}
+    for name in submodule_names:
+        old = module.get_submodule(name)
+        if not isinstance(old, torch.nn.Linear):
+            # the reference crashes here on 1x1 convs (D:194 with a 4-D weight)
+            raise ValueError(f"covariance precompute supports Linear targets only, got {name}={old}")
+        originals[name] = old
+        logger.info(f"Replacing {name} by covariance computing wrapper")
+        utils.replace_submodule_in_place(
+            module, name, CovarianceComputingLinearModule(old.weight, old.bias, decompose_in_float64))
+    return originals
+
+
+def _restore_modules(module: torch.nn.Module, originals: dict[str, torch.nn.Module]) -> None:
+    """D:624-630."""
+    for name, old in originals.items():
+        logger.info(f"Replacing {name} by original linear")
+        utils.replace_submodule_in_place(module, name, old)
+
+
 def _precompute_covariance_matrix_decompositions(
     *,
     module: torch.nn.Module,
@@ -368,16 +392,7 @@ def _precompute_covariance_matrix_decompositions(
     rank still draws all num_data_steps batches, so iterator positions stay those of the
     reference -- partial covariances are summed over NVLink, and the eigensolves are distributed
     round-robin with the owners broadcasting their top-k blocks."""
-    originals = {}
-    for name in submodule_names:
-        old = module.get_submodule(name)
-        if not isinstance(old, torch.nn.Linear):
-            # the reference crashes here on 1x1 convs (D:194 with a 4-D weight)
-            raise ValueError(f"covariance precompute supports Linear targets only, got {name}={old}")
-        originals[name] = old
-        logger.info(f"Replacing {name} by covariance computing wrapper")
-        utils.replace_submodule_in_place(
-            module, name, CovarianceComputingLinearModule(old.weight, old.bias, decompose_in_float64))
+    originals = _install_covariance_modules(module, submodule_names, decompose_in_float64)
 
     module.eval()
     rank, world = parallel.rank_and_world(group)
@@ -396,9 +411,7 @@ def _precompute_covariance_matrix_decompositions(
         k = _max_rank_consumed(sub.in_features, sub.out_features, reduction_factor)
         u_dict[name] = parallel.owner_computes(
             idx, group, lambda: sub.get_eigenvectors(k, group=None), sub.acc, (sub.out_features, k))
-    for name in submodule_names:
-        logger.info(f"Replacing {name} by original linear")
-        utils.replace_submodule_in_place(module, name, originals[name])
+    _restore_modules(module, originals)
     utils.free_gpu_reserved_memory()
     return u_dict
 

@@ -180,8 +180,9 @@ def _process_module(
     logger.info(f"{msg_prefix} {decomposed_type} weight_shape={tuple(orig_weight.shape)}")
     logger.info(f"{msg_prefix} {nsr_final_threshold=:.6f} {kl_final_threshold=:.6f}")
 
-    # the first (and largest) candidate rank is full_rank - full_rank // 2 (F:340-346)
-    k_max = full_rank - full_rank // 2
+    # The bisection asks for rank_best - rank_width; while every trial is rejected rank_best stays
+    # full_rank and the width halves, so any rank up to full_rank - 1 can be requested (F:340-375).
+    k_max = max(1, full_rank - 1)
     u = _compute_decompositon_of_covariance_matrix(
         root_module=root_module, decomposed_submodule_name=decomposed_submodule_name,
         data_iterator=data_iterator, weight=orig_weight, num_data_steps=num_data_steps,

@@ -173,7 +173,55 @@ def run_dwain(cfg):
     return out
 
 
-RUNNERS = {"eigh": run_eigh, "lowrank": run_lowrank, "falor": run_falor, "dwain": run_dwain}
+def run_gemmacc(cfg):
+    """fp32-split GEMM accuracy / SYRK speed as a function of the TMEM accumulation chunk."""
+    import torch
+    from ptdeco_b200 import _native as nat
+    from ptdeco_b200 import linalg
+    L = nat.lib()
+    dev = torch.device("cuda:0")
+    L.ptdeco_debug_set(6, cfg["chunk"])
+    g = torch.Generator().manual_seed(1)
+    M, N, K = cfg.get("M", 512), cfg.get("N", 512), cfg["K"]
+    a = torch.randn(M, K, generator=g).to(dev)
+    b = torch.randn(N, K, generator=g).to(dev)
+    c = linalg.gemm(a, False, b, False, M, N, K)
+    ref = a.double() @ b.double().T
+    out = {"rel_err_max": ((c.double() - ref).abs().max() / ref.abs().max()).item(),
+           "rel_fro": ((c.double() - ref).norm() / ref.norm()).item(),
+           "bias": ((c.double() - ref).mean() / ref.abs().mean()).item()}
+    ab, bb = a.to(torch.bfloat16), b.to(torch.bfloat16)
+    c = linalg.gemm(ab, False, bb, False, M, N, K)
+    ref = ab.double() @ bb.double().T
+    out["bf16_rel_fro"] = ((c.double() - ref).norm() / ref.norm()).item()
+    n, d = 8192, 4096
+    y = torch.randn(n, d, generator=g).to(torch.bfloat16).to(dev)
+    acc = linalg.CovarianceAccumulator(d, dev)
+    for _ in range(3):
+        acc.update(y)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        acc.update(y)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    out["syrk_d4096_ms"] = ms
+    out["syrk_tflops_alg"] = n * d * (d + 1) / ms / 1e9
+    y32 = y.float()
+    acc = linalg.CovarianceAccumulator(d, dev)
+    for _ in range(2):
+        acc.update(y32)
+    e0.record()
+    for _ in range(5):
+        acc.update(y32)
+    e1.record()
+    torch.cuda.synchronize()
+    out["syrk_f32_d4096_ms"] = e0.elapsed_time(e1) / 5
+    return out
+
+
+RUNNERS = {"gemmacc": run_gemmacc, "eigh": run_eigh, "lowrank": run_lowrank, "falor": run_falor, "dwain": run_dwain}
 
 
 def sub(kind, cfg, timeout=300):
@@ -203,6 +251,9 @@ def main():
             json.dump(results, f, indent=1)
 
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    if "gemmacc" in what:
+        for chunk in (16, 8, 4, 2, 1):
+            rec(f"gemmacc_chunk{chunk}_K4096", "gemmacc", dict(chunk=chunk, K=4096))
     if "eigh" in what:
         rec("eigh_d2", "eigh", dict(d=2))
         rec("eigh_d10", "eigh", dict(d=10, kind="decay"))
