@@ -86,7 +86,9 @@ class CovarianceComputingLinearModule(torch.nn.Module):
         self.bias = bias
         self.in_features = weight.shape[1]
         self.out_features = weight.shape[0]
-        self.acc = linalg.CovarianceAccumulator(self.out_features, weight.device)
+        self.acc = linalg.CovarianceAccumulator(
+            self.out_features, weight.device,
+            defer_rows=linalg.default_defer_rows(self.out_features, weight.element_size()))
         self.use_float64 = decompose_in_float64  # accepted; see falor's use_float64 note
 
     @property
@@ -125,7 +127,8 @@ def _compute_covariance_matrix_decomposition(
     assert isinstance(wrapper, WrappedDWAINModule)
     logger.info("Using float64 for decomposition" if decompose_in_float64
                 else "Using float32 for decomposition")
-    acc = linalg.CovarianceAccumulator(weight.shape[0], device)
+    acc = linalg.CovarianceAccumulator(
+        weight.shape[0], device, defer_rows=linalg.default_defer_rows(weight.shape[0], weight.element_size()))
     wrapper.capture_output = True
     try:
         for _ in range(num_data_steps):

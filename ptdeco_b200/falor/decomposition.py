@@ -85,7 +85,8 @@ def _compute_decompositon_of_covariance_matrix(
     wrapper = root_module.get_submodule(decomposed_submodule_name)
     assert isinstance(wrapper, WrappedFALORModule)
     n_out = weight.shape[0]
-    acc = linalg.CovarianceAccumulator(n_out, device, with_mean=use_mean)
+    acc = linalg.CovarianceAccumulator(n_out, device, with_mean=use_mean,
+                                       defer_rows=linalg.default_defer_rows(n_out, weight.element_size()))
     wrapper.capture_output = True
     try:
         for _ in range(num_data_steps):

@@ -5,6 +5,7 @@ without host synchronisation. There is no CPU path.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -21,6 +22,15 @@ def _check_2d(t: torch.Tensor, name: str) -> torch.Tensor:
     return t
 
 
+def default_defer_rows(d: int, esize: int = 2) -> int:
+    """Rows to stage before a SYRK call: up to 8192 tokens, at most 256 MB of staging per layer
+    (PTDECO_B200_DEFER_ROWS overrides; 0 disables deferral)."""
+    env = os.environ.get("PTDECO_B200_DEFER_ROWS")
+    if env is not None:
+        return int(env)
+    return int(min(8192, (256 << 20) // max(1, d * esize)))
+
+
 class CovarianceAccumulator:
     """fp32 d x d accumulator of E[y y^T] (and E[y]) fed by the SYRK kernel (K1/K1b/K2).
 
@@ -28,9 +38,16 @@ class CovarianceAccumulator:
     D:147-152, D:166-208). `accumulate_in_float64` of the reference maps to the same fp32
     accumulator: each per-batch product is formed with fp32-grade arithmetic (exact bf16 products or
     bf16x3 split, fp32 adds with bounded tensor-core chunks), which measures within 1e-6 of the
-    reference's fp64 accumulator (parity section)."""
+    reference's fp64 accumulator (parity section).
 
-    def __init__(self, d: int, device: torch.device, with_mean: bool = False):
+    Deferred updates: the accumulator read-modify-write costs 8 d^2 bytes per SYRK call whatever
+    the number of tokens, so short batches (N = 2048) leave the kernel epilogue-bound. With
+    `defer_rows > 0` batches of equal N are first copied into a staging buffer and folded in with
+    ONE call once `defer_rows` rows are pending (sum_steps y^T y / N is a SYRK over the
+    concatenated rows); `flush()` / `finalize()` drain it. Results are identical up to fp32
+    summation order."""
+
+    def __init__(self, d: int, device: torch.device, with_mean: bool = False, defer_rows: int = 0):
         self.d = int(d)
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -38,6 +55,23 @@ class CovarianceAccumulator:
         self.C = torch.zeros((self.d, self.d), dtype=torch.float32, device=self.device)
         self.colsum = torch.zeros(self.d, dtype=torch.float32, device=self.device) if with_mean else None
         self.steps = 0
+        self.defer_rows = int(defer_rows)
+        self._stage: Optional[torch.Tensor] = None
+        self._pending_rows = 0
+        self._pending_n = 0
+        self.launches = 0
+
+    def _syrk(self, y: torch.Tensor, sub: Optional[torch.Tensor], alpha: float) -> None:
+        L = nat.lib()
+        n = y.shape[0]
+        need = L.ptdeco_syrk_workspace_bytes(nat.dtype_code(y), n, self.d)
+        ws = nat.WORKSPACE.get(y.device, need)
+        nat.check(
+            L.ptdeco_syrk_accumulate(y.data_ptr(), nat.dtype_code(y), n, self.d, y.stride(0),
+                                     nat.ptr(sub), self.C.data_ptr(), self.C.stride(0),
+                                     nat.ptr(self.colsum), alpha, ws.data_ptr(), ws.numel(),
+                                     nat.stream_ptr(y.device)), "ptdeco_syrk_accumulate")
+        self.launches += 1
 
     def update(self, y: torch.Tensor, sub: Optional[torch.Tensor] = None) -> None:
         """C += (y - sub)^T (y - sub) / N ; colsum += mean_rows(y - sub). y: [N, d] fp32 or bf16."""
@@ -51,15 +85,30 @@ class CovarianceAccumulator:
             raise ValueError("empty activation batch")
         if sub is not None:
             sub = sub.detach().to(device=y.device, dtype=torch.float32).contiguous()
-        L = nat.lib()
-        need = L.ptdeco_syrk_workspace_bytes(nat.dtype_code(y), n, self.d)
-        ws = nat.WORKSPACE.get(y.device, need)
-        nat.check(
-            L.ptdeco_syrk_accumulate(y.data_ptr(), nat.dtype_code(y), n, self.d, y.stride(0),
-                                     nat.ptr(sub), self.C.data_ptr(), self.C.stride(0),
-                                     nat.ptr(self.colsum), 1.0 / n, ws.data_ptr(), ws.numel(),
-                                     nat.stream_ptr(y.device)), "ptdeco_syrk_accumulate")
         self.steps += 1
+        if self.defer_rows <= n or sub is not None:
+            self.flush()
+            self._syrk(y, sub, 1.0 / n)
+            return
+        if self._stage is not None and (self._pending_n != n or self._stage.dtype != y.dtype):
+            self.flush()
+        if self._stage is None or self._stage.dtype != y.dtype or self._stage.shape[0] < n:
+            cap = max(1, self.defer_rows // n) * n
+            self._stage = torch.empty((cap, self.d), dtype=y.dtype, device=y.device)
+        self._stage[self._pending_rows:self._pending_rows + n].copy_(y)
+        self._pending_rows += n
+        self._pending_n = n
+        if self._pending_rows + n > self._stage.shape[0]:
+            self.flush()
+
+    def flush(self) -> None:
+        if self._pending_rows:
+            self._syrk(self._stage[:self._pending_rows], None, 1.0 / self._pending_n)
+            self._pending_rows = 0
+
+    def release_staging(self) -> None:
+        self.flush()
+        self._stage = None
 
     def finalize(self, use_mean: bool, damp_factor: float) -> torch.Tensor:
         """In place: /steps, optional centring, mirror to the upper triangle, damping. Returns C."""
@@ -67,6 +116,7 @@ class CovarianceAccumulator:
             raise ValueError("no batches accumulated")
         if use_mean and self.colsum is None:
             raise ValueError("accumulator was created without mean tracking")
+        self.release_staging()
         nat.check(
             nat.lib().ptdeco_cov_finalize(self.C.data_ptr(), self.C.stride(0), self.d,
                                           nat.ptr(self.colsum), self.steps, int(bool(use_mean)),

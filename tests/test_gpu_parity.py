@@ -86,6 +86,31 @@ def test_finalize_matches_falor_covariance(dev, use_mean, use_damping):
     assert _rel(cov, ref) < COV_TOL
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_deferred_updates_match_immediate(dev, dtype):
+    """Staging several equal-N batches and folding them in with one SYRK call gives the covariance
+    of per-batch calls (sum_steps y^T y / N is a SYRK over the concatenated rows)."""
+    from ptdeco_b200 import linalg
+    d, n = 200, 96
+    g = torch.Generator().manual_seed(9)
+    ys = [torch.randn(n, d, generator=g).to(dtype).to(dev) for _ in range(7)]
+    ys.append(torch.randn(n + 8, d, generator=g).to(dtype).to(dev))  # a different N forces a flush
+    now = linalg.CovarianceAccumulator(d, dev, with_mean=True)
+    later = linalg.CovarianceAccumulator(d, dev, with_mean=True, defer_rows=3 * n)
+    for y in ys:
+        now.update(y)
+        later.update(y)
+    assert later.launches < now.launches and later.steps == now.steps == 8
+    a = now.finalize(True, 0.01).cpu().numpy()
+    b = later.finalize(True, 0.01).cpu().numpy()
+    assert _rel(b, a) < 2e-6
+    ref = sum((y.double().T @ y.double() / y.shape[0]) for y in ys) / 8
+    mean = sum(y.double().mean(0) for y in ys) / 8
+    ref = (ref - torch.outer(mean, mean)).cpu().numpy()
+    ref = ref + 0.01 * np.mean(np.diag(ref)) * np.eye(d)
+    assert _rel(b, ref) < COV_TOL
+
+
 def test_syrk_empty_and_bad_arguments(dev):
     from ptdeco_b200 import _native as nat
     from ptdeco_b200 import linalg
