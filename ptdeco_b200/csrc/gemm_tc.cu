@@ -79,15 +79,37 @@ __device__ __forceinline__ void decode_tile(const KArgs& g, int t, int& m0, int&
     m0 = i * TILE_M;
     n0 = (t - i * (i + 1) / 2) * TILE_N;
   } else {
-    // 256-wide column blocks: row blocks 2q and 2q+1 hold q+1 tiles each; cumulative q(q+1)
-    int q = static_cast<int>((sqrtf(4.f * static_cast<float>(t) + 1.f) - 1.f) * 0.5f);
-    while (q * (q + 1) > t) --q;
-    while ((q + 1) * (q + 2) <= t) ++q;
-    int rem = t - q * (q + 1);
-    int i = 2 * q, j = rem;
-    if (rem >= q + 1) {
-      i = 2 * q + 1;
-      j = rem - (q + 1);
+    // 256-wide column blocks: row block i (128 rows) owns column blocks j <= i/2. Tiles are
+    // enumerated by super-rows of SUPER row blocks, column-major inside a super-row, so that
+    // the ~148 tiles in flight share ~16 A slabs and ~9 B slabs (~70 MB, L2-resident) instead
+    // of sweeping the whole operand once per row block (measured 4x the algorithmic DRAM reads).
+    constexpr int SUPER = 16;
+    const int tiles_m = (g.M + TILE_M - 1) / TILE_M;
+    int i = 0, j = 0;
+    for (int lo = 0; lo < tiles_m; lo += SUPER) {
+      const int hi = min(tiles_m, lo + SUPER);
+      const int nrows = hi - lo;
+      const int full_cols = lo / 2;  // column blocks every row block of the super-row owns
+      const int cnt_full = full_cols * nrows;
+      if (t < cnt_full) {
+        j = t / nrows;
+        i = lo + t - j * nrows;
+        break;
+      }
+      t -= cnt_full;
+      bool found = false;
+      for (int jj = full_cols; 2 * jj < hi; ++jj) {  // the staircase at the diagonal
+        const int first = max(lo, 2 * jj);
+        const int c = hi - first;
+        if (t < c) {
+          j = jj;
+          i = first + t;
+          found = true;
+          break;
+        }
+        t -= c;
+      }
+      if (found) break;
     }
     m0 = i * TILE_M;
     n0 = j * TILE_N;
@@ -416,6 +438,13 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const KArgs& g, int gri
 }
 
 }  // namespace
+
+int make_tma_2d_bf16(CUtensorMap* map, const void* ptr, long long inner, long long rows,
+                     long long ld, int box_rows) {
+  GemmOperand op{static_cast<const __nv_bfloat16*>(ptr), 0, ld, 1, 0};
+  return make_map(map, op, inner, rows, box_rows);
+}
+int device_sm_count() { return num_sms(); }
 
 void gemm_tc_debug_set(int key, long long value) {
   if (key >= 0 && key < 16) g_dbg[key] = value;

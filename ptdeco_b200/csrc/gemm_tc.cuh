@@ -11,6 +11,7 @@
 //   eigh trailing updates / back-transform: mixes of the above
 // fp32-grade products use the "bf16x3" split (x = h + m + l, six h/m/l segment pairs).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -45,6 +46,12 @@ struct GemmEpilogue {
 // Returns 0 on success, negative errno-style on bad arguments / launch failure.
 int gemm_tc(const GemmOperand& A, const GemmOperand& B, int M, int N, int K, int full_pairs,
             const GemmEpilogue& ep, cudaStream_t stream);
+
+// 2-D bf16 tensor map {inner, rows} with row pitch ld (elements), box {64, box_rows}, 128B swizzle,
+// zero fill out of bounds. Shared with the fused low-rank kernel. 0 on success.
+int make_tma_2d_bf16(CUtensorMap* map, const void* ptr, long long inner, long long rows,
+                     long long ld, int box_rows);
+int device_sm_count();
 
 // Debug overrides used by the descriptor sweep in tests/tools (0 = default).
 void gemm_tc_debug_set(int key, long long value);

@@ -1,16 +1,28 @@
 // Decomposed-layer forward y = W2 (W1 x) + b (reference: the nn.Sequential built at F:84-95 /
 // D:74-85, K7 of SURVEY.md).
 //
-// Unfused path (any dtype / rank): two passes of the tcgen05 GEMM engine with the [n, k]
-// intermediate H staged in workspace (bf16 for bf16 models, bf16x3 split for fp32 models).
+// Fused path (bf16, k <= 256, TMA-friendly pointers): ONE kernel per 128-token tile computes
+// H = X W1^T into TMEM (tcgen05), drains it once to a 128B-swizzled bf16 tile in shared memory
+// and feeds that tile straight back to the tensor core as the A operand of Y = H W2^T; the rank-k
+// intermediate never leaves the SM. Warp-specialised: warp 0 TMA producer (one 3-stage ring
+// carries first X/W1 k-blocks, then W2 tiles), warp 1 issues tcgen05.mma, warps 2-9 drain TMEM
+// (H -> smem, Y -> +bias -> bf16 -> global) with double-buffered Y accumulators. When there are
+// fewer token tiles than SMs the `out` dimension is split over CTAs of the same token tile
+// (a cost model trades the recomputed first GEMM against idle SMs).
+//
+// Unfused path (fp32 models, k > 256): two passes of the tcgen05 GEMM engine with the [n, k]
+// intermediate H staged in workspace (bf16, or bf16x3 split for fp32 models).
 #include "lowrank.cuh"
 
 #include <cuda_bf16.h>
 
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 
 #include "elementwise.cuh"
 #include "gemm_tc.cuh"
+#include "ptx.cuh"
 
 namespace ptd {
 
@@ -53,6 +65,330 @@ int stage(const void* src, int is_bf16, long long rows, int cols, long long ld, 
   op->seg_stride = rows * ldp;
   return 0;
 }
+// ------------------------------------------------------------------------------ fused kernel
+constexpr int F_TILE_M = 128;
+constexpr int F_BK = 64;
+constexpr int F_TILE_N = 256;
+constexpr int F_STAGES = 3;
+constexpr int F_XBYTES = F_TILE_M * F_BK * 2;    // X k-block: 128 rows x 128 B
+constexpr int F_WBYTES = 256 * F_BK * 2;         // W1 k-block (<= 256 rows) or W2 tile (256 rows)
+constexpr int F_STAGE = F_XBYTES + F_WBYTES;     // 48 KB
+constexpr int F_HBLOCK = F_TILE_M * 128;         // one 64-wide k-block of H: 16 KB
+constexpr int F_EPI_WARPS = 8;
+constexpr int F_THREADS = 64 + 32 * F_EPI_WARPS;
+constexpr int F_SMEM = F_STAGES * F_STAGE + 4 * F_HBLOCK + 1024 + 256;
+
+struct FusedArgs {
+  int n, in_f, k, out_f, kp;
+  int groups, tiles_per_group, out_tiles;
+  __nv_bfloat16* Y;
+  long long ldy;
+  const float* bias;
+  int tma_store;  // 1: Y tiles leave through shared memory + cp.async.bulk.tensor stores
+};
+
+__global__ void __launch_bounds__(F_THREADS, 1)
+lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                     const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmY,
+                     const FusedArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* hbuf = smem + F_STAGES * F_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(hbuf + 4 * F_HBLOCK);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + F_STAGES;
+  uint64_t* h_full = bars + 2 * F_STAGES;
+  uint64_t* h_ready = h_full + 1;
+  uint64_t* y_full = h_ready + 1;
+  uint64_t* y_empty = y_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rt = blockIdx.x / g.groups, og = blockIdx.x % g.groups;
+  const int m0 = rt * F_TILE_M;
+  const int t0 = og * g.tiles_per_group;
+  const int t1 = min(g.out_tiles, t0 + g.tiles_per_group);
+  const int kb1 = (g.in_f + F_BK - 1) / F_BK;
+  const int kb2 = g.kp / F_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    for (int s = 0; s < F_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(h_full, 1);
+    mbar_init(h_ready, F_EPI_WARPS);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&y_full[a], 1);
+      mbar_init(&y_empty[a], F_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t h_tmem = tmem_base + 256;  // H accumulates in the upper half; Y tile 0 uses the lower
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < kb1; ++kb) {  // GEMM 1 operands
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sA = smem + stage * F_STAGE;
+        mbar_expect_tx(&full[stage], F_XBYTES + g.kp * 128);
+        tma_load_3d(sA, &tmX, &full[stage], kb * F_BK, m0, 0);
+        tma_load_3d(sA + F_XBYTES, &tmW1, &full[stage], kb * F_BK, 0, 0);
+        if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+      }
+      for (int t = t0; t < t1; ++t) {     // GEMM 2: W2 tiles
+        for (int kb = 0; kb < kb2; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sB = smem + stage * F_STAGE + F_XBYTES;
+          mbar_expect_tx(&full[stage], F_WBYTES);
+          tma_load_3d(sB, &tmW2, &full[stage], kb * F_BK, t * F_TILE_N, 0);
+          if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc1 = umma_idesc_bf16(F_TILE_M, g.kp, 0, 0);
+      const uint32_t idesc2 = umma_idesc_bf16(F_TILE_M, F_TILE_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < kb1; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + stage * F_STAGE);
+        const uint32_t sB = sA + F_XBYTES;
+#pragma unroll
+        for (int ks = 0; ks < F_BK / 16; ++ks)
+          umma_bf16(h_tmem, umma_smem_desc_sw128(sA + ks * 32, 16, 1024),
+                    umma_smem_desc_sw128(sB + ks * 32, 16, 1024), idesc1, (kb > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(&empty[stage]);
+        if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(h_full);
+      mbar_wait(h_ready, 0);  // H is in shared memory as a swizzled bf16 K-major tile
+      tc_fence_after();
+      const uint32_t sH = smem_u32(hbuf);
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(&y_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * F_TILE_N;
+        for (int kb = 0; kb < kb2; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sB = smem_u32(smem + stage * F_STAGE + F_XBYTES);
+          const uint32_t sA = sH + kb * F_HBLOCK;
+#pragma unroll
+          for (int ks = 0; ks < F_BK / 16; ++ks)
+            umma_bf16(d_tmem, umma_smem_desc_sw128(sA + ks * 32, 16, 1024),
+                      umma_smem_desc_sw128(sB + ks * 32, 16, 1024), idesc2, (kb > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&y_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;                 // TMEM lane quarter of this warp
+    const int half = (warp - 2) >> 2;       // column half
+    const int row = q * 32 + lane;
+    const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
+    // ---- H: TMEM -> bf16 -> swizzled shared memory (the layout TMA would have produced)
+    mbar_wait(h_full, 0);
+    tc_fence_after();
+    const int hcols = g.kp / 2;
+    for (int c = 0; c < hcols / 32; ++c) {
+      const int col0 = half * hcols + c * 32;
+      uint32_t r[32];
+      tmem_ld_32x32(h_tmem + col0 + lane_bits, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = __float2bfloat16_rn(__uint_as_float(r[8 * j + e]));
+        const int col = col0 + 8 * j;
+        const int chunk = (col & 63) >> 3;
+        uint8_t* dst = hbuf + (col >> 6) * F_HBLOCK + row * 128 + ((chunk ^ (row & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(h_ready);
+    // ---- Y tiles
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int m = m0 + row;
+    const bool yvec = ((g.ldy & 7) == 0) && ((reinterpret_cast<uintptr_t>(g.Y) & 15) == 0);
+    // Output staging: the X slots of the operand ring are idle during GEMM 2 (the producer only
+    // refills the W halves), so each epilogue warp owns a 4 KB slice (32 rows x 128 B, swizzled).
+    uint8_t* stg = smem + ((warp - 2) >> 2) * F_STAGE + ((warp - 2) & 3) * 4096;
+    for (int t = t0; t < t1; ++t) {
+      mbar_wait(&y_full[acc], acc_phase);
+      tc_fence_after();
+      const int nbase = t * F_TILE_N + half * 128;
+      if (g.tma_store) {
+#pragma unroll 1
+        for (int rnd = 0; rnd < 2; ++rnd) {
+          uint32_t ra[32], rb[32];
+          const uint32_t taddr = tmem_base + acc * F_TILE_N + half * 128 + rnd * 64 + lane_bits;
+          tmem_ld_32x32(taddr, ra);
+          tmem_ld_32x32(taddr + 32, rb);
+          tmem_ld_wait();
+          if (lane == 0) bulk_wait_read_all();  // the previous store has drained this slice
+          __syncwarp();
+          const int n0 = nbase + rnd * 64;
+          const bool full64 = (n0 + 64 <= g.out_f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float x = __uint_as_float(j < 4 ? ra[8 * j + e] : rb[8 * (j - 4) + e]);
+              if (g.bias != nullptr && (full64 || n0 + 8 * j + e < g.out_f)) x += __ldg(g.bias + n0 + 8 * j + e);
+              o[e] = __float2bfloat16_rn(x);
+            }
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                *reinterpret_cast<const uint4*>(o);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && n0 < g.out_f && m0 + q * 32 < g.n) {
+            tma_store_3d(&tmY, stg, n0, m0 + q * 32, 0);
+            bulk_commit();
+          }
+        }
+      } else {
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + acc * F_TILE_N + half * 128 + c * 32 + lane_bits, r);
+        tmem_ld_wait();
+        const int n0 = nbase + c * 32;
+        if (m < g.n && n0 < g.out_f) {
+          __nv_bfloat16* yrow = g.Y + static_cast<long long>(m) * g.ldy + n0;
+          if (yvec && n0 + 32 <= g.out_f) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float x = __uint_as_float(r[8 * j + e]);
+                if (g.bias != nullptr) x += __ldg(g.bias + n0 + 8 * j + e);
+                o[e] = __float2bfloat16_rn(x);
+              }
+              *reinterpret_cast<uint4*>(yrow + 8 * j) = *reinterpret_cast<const uint4*>(o);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              if (n0 + e < g.out_f) {
+                float x = __uint_as_float(r[e]);
+                if (g.bias != nullptr) x += __ldg(g.bias + n0 + e);
+                yrow[e] = __float2bfloat16_rn(x);
+              }
+            }
+          }
+        }
+      }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&y_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (g.tma_store && lane == 0) bulk_wait_read_all();  // staging must outlive the last store
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+bool fused_eligible(const void* X, long long ldx, const void* W1, long long ldw1, const void* W2,
+                    long long ldw2, int is_bf16, int k) {
+  return is_bf16 && k <= 256 && aligned16(X) && aligned16(W1) && aligned16(W2) && (ldx % 8) == 0 &&
+         (ldw1 % 8) == 0 && (ldw2 % 8) == 0;
+}
+
+int launch_fused(const void* X, long long ldx, const void* W1, long long ldw1, const void* W2,
+                 long long ldw2, const float* bias, void* Y, long long ldy, long long n, int in_f,
+                 int k, int out_f, cudaStream_t st) {
+  FusedArgs g;
+  g.n = static_cast<int>(n);
+  g.in_f = in_f;
+  g.k = k;
+  g.out_f = out_f;
+  g.kp = static_cast<int>(round_up(k, 64));
+  g.out_tiles = (out_f + F_TILE_N - 1) / F_TILE_N;
+  g.Y = static_cast<__nv_bfloat16*>(Y);
+  g.ldy = ldy;
+  g.bias = bias;
+  const int row_tiles = static_cast<int>((n + F_TILE_M - 1) / F_TILE_M);
+  const int sms = device_sm_count();
+  const int kb1 = (in_f + F_BK - 1) / F_BK, kb2 = g.kp / F_BK;
+  // split `out` over CTAs of one token tile when token tiles alone cannot fill the GPU
+  double best = 1e300;
+  g.groups = 1;
+  g.tiles_per_group = g.out_tiles;
+  for (int G = 1; G <= g.out_tiles; ++G) {
+    const int tpg = (g.out_tiles + G - 1) / G;
+    const int geff = (g.out_tiles + tpg - 1) / tpg;
+    const long long units = static_cast<long long>(row_tiles) * geff;
+    const long long waves = (units + sms - 1) / sms;
+    const double cost = static_cast<double>(waves) *
+                        (static_cast<double>(kb1) * g.kp + static_cast<double>(tpg) * kb2 * F_TILE_N);
+    if (cost < best * 0.999) {
+      best = cost;
+      g.groups = geff;
+      g.tiles_per_group = tpg;
+    }
+  }
+  CUtensorMap tx, tw1, tw2, ty;
+  int rc;
+  g.tma_store = (aligned16(Y) && (ldy % 8) == 0 && std::getenv("PTDECO_B200_NO_TMA_STORE") == nullptr) ? 1 : 0;
+  if (g.tma_store) {
+    if ((rc = make_tma_2d_bf16(&ty, Y, out_f, n, ldy, 32))) return rc;
+  } else {
+    memset(&ty, 0, sizeof(ty));
+  }
+  if ((rc = make_tma_2d_bf16(&tx, X, in_f, n, ldx, F_TILE_M))) return rc;
+  if ((rc = make_tma_2d_bf16(&tw1, W1, in_f, k, ldw1, g.kp))) return rc;
+  if ((rc = make_tma_2d_bf16(&tw2, W2, k, out_f, ldw2, F_TILE_N))) return rc;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(lowrank_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             F_SMEM) != cudaSuccess)
+      return -12;
+    attr = true;
+  }
+  const long long grid = static_cast<long long>(row_tiles) * g.groups;
+  if (grid > 0x7fffffffLL) return -22;
+  lowrank_fused_kernel<<<static_cast<unsigned>(grid), F_THREADS, F_SMEM, st>>>(tx, tw1, tw2, ty, g);
+  return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
+
 }  // namespace
 
 size_t lowrank_workspace_bytes(int is_bf16, long long n, int in_f, int k, int out_f) {
@@ -73,6 +409,8 @@ int lowrank_forward(const void* X, long long ldx, const void* W1, long long ldw1
   if (X == nullptr || W1 == nullptr || W2 == nullptr || Y == nullptr) return -22;
   if (n <= 0 || in_f <= 0 || k <= 0 || out_f <= 0 || n > 0x7fffffffLL) return -22;
   if (ldx < in_f || ldw1 < in_f || ldw2 < k || ldy < out_f) return -22;
+  if (fused_eligible(X, ldx, W1, ldw1, W2, ldw2, is_bf16, k) && std::getenv("PTDECO_B200_NO_FUSED") == nullptr)
+    return launch_fused(X, ldx, W1, ldw1, W2, ldw2, bias, Y, ldy, n, in_f, k, out_f, st);
   if (ws == nullptr || ws_bytes < lowrank_workspace_bytes(is_bf16, n, in_f, k, out_f)) return -12;
   uint8_t* base = static_cast<uint8_t*>(ws);
   base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(base) + 255) & ~uintptr_t(255));

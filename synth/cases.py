@@ -67,7 +67,7 @@ def _lowrank_vectors(index: int, bs: int, dim: int, latent: int, noise: float) -
     return 3.0 * z @ basis + noise * torch.randn(bs, dim, generator=g)
 
 
-FALOR_CASES = ("mlp", "convmlp", "deit_small", "deit_tiny")
+FALOR_CASES = ("mlp", "convmlp", "deit_small", "deit_tiny", "convnext_tiny")
 
 
 def falor_case(name: str):
@@ -96,6 +96,21 @@ def falor_case(name: str):
         stream = IndexedStream(lambda i: streams.image_batch(0, i, 5))
         kw.update(nsr_final_threshold=0.05, kl_final_threshold=0.02, num_data_steps=8,
                   num_metric_steps=2, use_float64=False)
+    elif name == "convnext_tiny":
+        # BASELINE.json configs[1]: torchvision convnext_tiny (random init, 37 Linear targets; it has
+        # no 1x1 convs), synthetic ImageNet-shape batches; layer_scale set to 1 so that the block
+        # MLPs matter at random init (with the default 1e-6 every rank collapses to 2)
+        import torchvision
+
+        torch.manual_seed(MODEL_SEED)
+        model = torchvision.models.convnext_tiny(weights=None)
+        with torch.no_grad():
+            for n_, p_ in model.named_parameters():
+                if n_.endswith("layer_scale"):
+                    p_.fill_(1.0)
+        stream = IndexedStream(lambda i: streams.image_batch(4, i, 4))
+        kw.update(nsr_final_threshold=0.055, kl_final_threshold=0.02, num_data_steps=2,
+                  num_metric_steps=1)
     else:
         raise KeyError(name)
     model.eval()

@@ -1,0 +1,85 @@
+"""Multi-GPU parity of the sharded calibration path (run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29533 tools/dist_check.py
+
+Every rank builds the same seeded tiny Llama; the covariance precompute runs sharded over the
+ranks (steps i = rank mod world, NCCL reduce to the owner, owner eigensolve, broadcast) and is
+compared with the unsharded computation done redundantly on every rank: same subspaces (principal
+angle cosines >= 0.9999 at the ranks the search consumes) and bit-identical results across ranks.
+Then dwain.decompose_in_place with precompute splits must return the golden ranks on every rank.
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+import torch.distributed as dist
+
+import ptdeco_b200.dwain as dwain
+import ptdeco_b200.dwain.decomposition as D
+from ptdeco_b200 import parallel
+from synth import cases
+
+
+def main():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    group = parallel.default_group()
+    out = {"world": world}
+
+    model, stream, _, kw = cases.dwain_case("llama_tiny")
+    model.to(dev)
+    names = D._get_decomposeable_submodule_names(model, ["lm_head"])
+    sharded = D._precompute_covariance_matrix_decompositions(
+        module=model, submodule_names=names, num_data_steps=8, data_iterator=stream, device=dev,
+        decompose_in_float64=True, reduction_factor=0.5, group=group)
+    model2, stream2, _, _ = cases.dwain_case("llama_tiny")
+    model2.to(dev)
+    single = D._precompute_covariance_matrix_decompositions(
+        module=model2, submodule_names=names, num_data_steps=8, data_iterator=stream2, device=dev,
+        decompose_in_float64=True, reduction_factor=0.5, group=None)
+    assert stream.position == stream2.position == 8
+    worst = 1.0
+    for n in names:
+        a, b = sharded[n].double(), single[n].double()
+        k = a.shape[1]
+        for kk in {k, max(1, k // 2)}:
+            s = torch.linalg.svdvals(a[:, k - kk:].T @ b[:, k - kk:])
+            worst = min(worst, s.min().item())
+        if world > 1:
+            ref = sharded[n].clone()
+            dist.broadcast(ref, src=0)
+            assert torch.equal(ref, sharded[n]), f"rank {rank} holds a different U for {n}"
+    out["min_cosine_sharded_vs_single"] = worst
+    assert worst >= 0.9999, worst
+
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "dwain_llama_tiny_splits.json")))
+    model3, s3, m3, kw3 = cases.dwain_case("llama_tiny_splits")
+    model3.to(dev)
+    cfg = dwain.decompose_in_place(module=model3, device=dev, data_iterator=s3, metric_iterator=m3,
+                                   loss_fn=cases.dwain_loss_fn("llama_tiny_splits"),
+                                   finetune_fn=lambda m, d, nn: m, **kw3)
+    ranks = {n: c["modules"]["0"]["out_features"] for n, c in cfg.items()}
+    granks = {n: c["modules"]["0"]["out_features"] for n, c in gold["decompose_config"].items()}
+    out["ranks_equal_golden"] = ranks == granks
+    out["positions"] = [s3.position, m3.position, gold["stream_position"], gold["metric_stream_position"]]
+    assert ranks == granks, (ranks, granks)
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        print("DIST_CHECK " + json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

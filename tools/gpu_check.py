@@ -120,6 +120,8 @@ def run_lowrank(cfg):
 
 def run_falor(cfg):
     import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     import ptdeco_b200.falor as falor
     from synth import cases
     gold = json.load(open(os.path.join(ROOT, "tests", "golden", f"falor_{cfg['name']}.json")))
@@ -138,6 +140,15 @@ def run_falor(cfg):
             mism.append({"mine": [t["name"], t["rank"]], "gold": [g["name"], g["rank"]]})
             break
     out["first_mismatch"] = mism
+    diffs = []
+    for idx, (t, g) in enumerate(zip(trace, gold["trace"])):
+        if (t["name"], t["rank"]) != (g["name"], g["rank"]):
+            break
+        diffs.append((abs(t["nsr"] - g["nsr"]) / max(g["nsr"], 1e-9), idx, t["name"], t["rank"], t["nsr"], g["nsr"]))
+    diffs.sort(reverse=True)
+    out["worst_trials"] = [list(d[1:]) for d in diffs[:8]]
+    out["n_matching_prefix"] = len(diffs)
+    out["rel_diff_quantiles"] = [sorted(d[0] for d in diffs)[int(q * (len(diffs) - 1))] for q in (0.5, 0.9, 0.99)] if diffs else []
     out["max_rel_nsr_diff"] = max((abs(t["nsr"] - g["nsr"]) / max(g["nsr"], 1e-9) for t, g in zip(trace, gold["trace"])
                                    if (t["name"], t["rank"]) == (g["name"], g["rank"])), default=None)
     ranks = {n: c["modules"]["0"].get("out_features", c["modules"]["0"].get("out_channels")) for n, c in dc.items()}
@@ -279,11 +290,17 @@ def main():
         rec("lowrank_bf16_4096_k256_n8192", "lowrank", dict(n=8192, **{"in": 4096, "k": 256, "out": 4096}, time=True))
         rec("lowrank_bf16_4096_k1024_n8192", "lowrank", dict(n=8192, **{"in": 4096, "k": 1024, "out": 4096}, time=True))
         rec("lowrank_bf16_4096_k256_n128", "lowrank", dict(n=128, **{"in": 4096, "k": 256, "out": 4096}, time=True))
+        rec("lowrank_bf16_ragged", "lowrank", dict(n=333, **{"in": 200, "k": 72, "out": 520}))
+        rec("lowrank_bf16_4096_k128_n32768", "lowrank", dict(n=32768, **{"in": 4096, "k": 128, "out": 4096}, time=True))
+        rec("lowrank_bf16_4096_k64_n32768", "lowrank", dict(n=32768, **{"in": 4096, "k": 64, "out": 4096}, time=True))
+        rec("lowrank_bf16_14336x4096_k256_n8192", "lowrank", dict(n=8192, **{"in": 4096, "k": 256, "out": 14336}, time=True))
+        rec("lowrank_bf16_4096_k128_n16", "lowrank", dict(n=16, **{"in": 4096, "k": 128, "out": 4096}, time=True))
     if "falor" in what:
         for n in ("mlp", "convmlp", "deit_small"):
             rec(f"falor_{n}", "falor", dict(name=n))
     if "falorbig" in what:
         rec("falor_deit_tiny", "falor", dict(name="deit_tiny"), timeout=1200)
+        rec("falor_convnext_tiny", "falor", dict(name="convnext_tiny"), timeout=1200)
     if "dwain" in what:
         for n in ("llama_tiny", "llama_tiny_splits"):
             rec(f"dwain_{n}", "dwain", dict(name=n))
