@@ -278,6 +278,38 @@ def main() -> None:
             del cov, acc, y
         except Exception as exc:  # the headline number must survive an extra failing
             extra["eigh_error"] = repr(exc)[:200]
+        try:  # decomposed-layer forward (K7) at a prefill shape, next to torch's nn.Sequential
+            n, fin, k, fout = 32768, 4096, 128, 4096
+            x = torch.randn(n, fin, generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+            w1 = (torch.randn(k, fin, generator=g, device=dev) / fin ** 0.5).to(torch.bfloat16)
+            w2 = (torch.randn(fout, k, generator=g, device=dev) / k ** 0.5).to(torch.bfloat16)
+            for _ in range(3):
+                linalg.lowrank_forward(x, w1, w2, None)
+            e0.record()
+            for _ in range(10):
+                linalg.lowrank_forward(x, w1, w2, None)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_lr = e0.elapsed_time(e1) / 10
+            alg_bytes = 2.0 * n * (fin + fout) + 2.0 * k * (fin + fout)
+            seq = torch.nn.Sequential(torch.nn.Linear(fin, k, bias=False),
+                                      torch.nn.Linear(k, fout, bias=False)).to(dev).to(torch.bfloat16)
+            with torch.no_grad():
+                for _ in range(3):
+                    seq(x)
+                e0.record()
+                for _ in range(10):
+                    seq(x)
+                e1.record()
+            torch.cuda.synchronize()
+            extra["lowrank_forward"] = {
+                "shape": f"N={n} in={fin} k={k} out={fout} bf16", "ms": ms_lr,
+                "achieved_gbs": alg_bytes / ms_lr / 1e6, "peak_gbs": float(peaks.get("hbm_gbs", 6650.0)),
+                "frac_hbm": alg_bytes / ms_lr / 1e6 / float(peaks.get("hbm_gbs", 6650.0)),
+                "torch_sequential_ms": e0.elapsed_time(e1) / 10}
+            del x, w1, w2, seq
+        except Exception as exc:
+            extra["lowrank_error"] = repr(exc)[:200]
     torch.cuda.empty_cache()
 
     # ---------------- e2e: public API path with host token ids ----------------------------------

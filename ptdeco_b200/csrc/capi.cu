@@ -195,7 +195,13 @@ int ptdeco_kl_metric(const void* student, const void* teacher, int dtype, long l
                         as_stream(stream));
 }
 
-void ptdeco_debug_set(int key, long long value) { ptd::gemm_tc_debug_set(key, value); }
-long long ptdeco_debug_get(int key) { return ptd::gemm_tc_last_launch_info(key); }
+void ptdeco_debug_set(int key, long long value) {
+  if (key == 100) ptd::eigh_debug_profile(static_cast<int>(value));
+  else ptd::gemm_tc_debug_set(key, value);
+}
+long long ptdeco_debug_get(int key) {
+  if (key >= 100 && key < 108) return ptd::eigh_debug_phase_cycles(key - 100);
+  return ptd::gemm_tc_last_launch_info(key);
+}
 
 }  // extern "C"

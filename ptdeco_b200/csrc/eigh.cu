@@ -196,15 +196,19 @@ struct PanelArgs {
   float* Vp;      // [d][NB] indexed by global row
   float* Wp;      // [d][NB]
   float* colbuf;  // [d] (local row index)
-  double* npart;  // [grid]
-  float* gpart;   // [grid][GP_STRIDE]
+  double* nacc;   // [NB] per-column sum of squares, accumulated with atomics (pre-zeroed)
+  float* gacc;    // [NB][GP_STRIDE] per-column W^T v | V^T v | v^T A v, atomics (pre-zeroed)
   float* ptop;    // [NB]
   float* dvec;    // [d]
   float* evec;    // [d]
   float* taus;    // [d]
   float* Tmat;    // [NB][NB] of this panel (pre-zeroed)
   unsigned* bar;  // grid barrier counter (pre-zeroed)
+  int prof;       // 1: CTA 0 accumulates per-phase cycle counts into g_phase_cycles
 };
+
+// P1 | barrier A | reflector + v | symv + dots | barrier B | P3   (cycles of CTA 0, summed over columns)
+__device__ unsigned long long g_phase_cycles[8];
 
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& epoch) {
   __syncthreads();
@@ -237,10 +241,11 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
   float* gWs = pbuf + g.rows_per_cta;        // [NB]  W^T v
   float* gVs = gWs + NB;                     // [NB]  V^T v
   float* red = gVs + NB;                     // [PANEL_WARPS][2*NB]
-  float* pseg = red + PANEL_WARPS * 2 * NB;  // [rows_per_cta][segments] symv partials
+  float* pts = red + PANEL_WARPS * 2 * NB;   // [NB] symv results of the top rows (all CTAs)
+  float* Ts = pts + NB;                      // [NB][NB+1] compact-WY T (CTA 0 only)
+  float* pseg = Ts + NB * (NB + 1);          // [rows_per_cta][segments] symv partials
   __shared__ double sred[PANEL_WARPS];
   __shared__ double s_scal[4];
-  __shared__ double sum3[3 * (2 * NB + 1)];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x, cta = blockIdx.x;
@@ -252,8 +257,17 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
   float* Wp = g.Wp + static_cast<long long>(g.j0) * NB;
 
   for (int idx = tid; idx < 2 * NB * (NB + 1); idx += PANEL_THREADS) Vt[idx] = 0.f;
+  for (int idx = tid; idx < NB * (NB + 1); idx += PANEL_THREADS) Ts[idx] = 0.f;
   __syncthreads();
 
+  const bool prof = g.prof && cta == 0 && tid == 0;
+  long long tp = prof ? clock64() : 0;
+#define PTD_PHASE(k)                                             \
+  if (prof) {                                                    \
+    const long long tn = clock64();                              \
+    atomicAdd(&g_phase_cycles[k], (unsigned long long)(tn - tp)); \
+    tp = tn;                                                     \
+  }
   for (int i = 0; i < g.ncols; ++i) {
     const int j = g.j0 + i;
     // ---------------------------------------------------------------- P1: updated column i
@@ -274,19 +288,22 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
     if (tid == 0) {
       double s = 0.0;
       for (int w = 0; w < PANEL_WARPS; ++w) s += sred[w];
-      g.npart[cta] = s;
+      if (s != 0.0) atomicAdd(g.nacc + i, s);
     }
+    PTD_PHASE(0)
     grid_barrier(g.bar, epoch);
+    PTD_PHASE(1)
 
     // ---------------------------------------------------------------- P2: reflector + symv
-    if (warp == 0) {
-      double s = 0.0;
-      for (int c = lane; c < G; c += 32) s += __ldcg(g.npart + c);
-      s = warp_sum(s);
-      if (lane == 0) s_scal[0] = s;
+    // The column and its norm were produced by other CTAs: read through L2 (ld.cg). The column
+    // loads are issued before the norm is consumed so both latencies overlap.
+    float raw[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = tid + u * PANEL_THREADS;
+      raw[u] = (c > i + 1 && c < m) ? __ldcg(g.colbuf + c) : 0.f;
     }
-    __syncthreads();
-    const double xnorm2 = s_scal[0];
+    const double xnorm2 = __ldcg(g.nacc + i);
     const float dj = __ldcg(g.colbuf + i);
     if (i + 1 >= m) {  // last diagonal element of the matrix: no reflector (uniform branch)
       if (cta == 0 && tid == 0) g.dvec[j] = dj;
@@ -306,7 +323,12 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
       g.evec[j] = beta;
       g.taus[j] = tau;
     }
-    for (int c = tid; c < L; c += PANEL_THREADS) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = tid + u * PANEL_THREADS;
+      if (c < L) vs[c] = (c == i + 1) ? 1.f : raw[u] * scale;
+    }
+    for (int c = tid + 8 * PANEL_THREADS; c < L; c += PANEL_THREADS) {
       float x = 0.f;
       if (c == i + 1) x = 1.f;
       else if (c > i + 1 && c < m) x = __ldcg(g.colbuf + c) * scale;
@@ -315,6 +337,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
     __syncthreads();
     for (int r = r0 + tid; r < r1; r += PANEL_THREADS) Vp[r * NB + i] = vs[r];
     for (int r = tid; r < NB; r += PANEL_THREADS) Vt[r * (NB + 1) + i] = (r < L) ? vs[r] : 0.f;
+    PTD_PHASE(2)
 
     if (tau != 0.f) {
       // symv over the CTA's row block, split into (row, 1024-float segment) items so that every
@@ -382,31 +405,31 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
       if (lane == 0) sred[warp] = vp;
       __syncthreads();
       if (tid < 2 * NB) {
-        float s = 0.f;
-        for (int w = 0; w < PANEL_WARPS; ++w) s += red[w * 2 * NB + tid];
-        g.gpart[cta * GP_STRIDE + tid] = s;
-      } else if (tid == 2 * NB) {
+        if ((tid & (NB - 1)) < i && R > 0) {
+          float s = 0.f;
+          for (int w = 0; w < PANEL_WARPS; ++w) s += red[w * 2 * NB + tid];
+          atomicAdd(g.gacc + i * GP_STRIDE + tid, s);
+        }
+      } else if (tid == 2 * NB && R > 0) {
         double s = 0.0;
         for (int w = 0; w < PANEL_WARPS; ++w) s += sred[w];
-        g.gpart[cta * GP_STRIDE + 2 * NB] = static_cast<float>(s);
+        atomicAdd(g.gacc + i * GP_STRIDE + 2 * NB, static_cast<float>(s));
       }
     }
+    PTD_PHASE(3)
     grid_barrier(g.bar, epoch);
+    PTD_PHASE(4)
 
     // ---------------------------------------------------------------- P3: w column
     if (tau != 0.f) {
-      if (tid < 3 * (2 * NB + 1)) {  // 3 thread groups each sum a third of the CTAs' partials
-        const int part = tid / (2 * NB + 1), idx = tid - part * (2 * NB + 1);
-        double s = 0.0;
-        for (int c = part; c < G; c += 3) s += static_cast<double>(__ldcg(g.gpart + c * GP_STRIDE + idx));
-        sum3[part * (2 * NB + 1) + idx] = s;
-      }
-      __syncthreads();
       if (tid <= 2 * NB) {
-        const double s = sum3[tid] + sum3[(2 * NB + 1) + tid] + sum3[2 * (2 * NB + 1) + tid];
-        if (tid < NB) gWs[tid] = static_cast<float>(s);
-        else if (tid < 2 * NB) gVs[tid - NB] = static_cast<float>(s);
-        else s_scal[1] = s;
+        const float s = __ldcg(g.gacc + i * GP_STRIDE + tid);
+        if (tid < NB) gWs[tid] = s;
+        else if (tid < 2 * NB) gVs[tid - NB] = s;
+        else s_scal[1] = static_cast<double>(s);
+      } else if (tid >= 256 && tid < 256 + NB) {  // one parallel fetch of the top rows' symv results
+        const int r = tid - 256;
+        pts[r] = (r > i && r < m) ? __ldcg(g.ptop + r) : 0.f;
       }
       __syncthreads();
       if (warp == 0) {
@@ -434,17 +457,17 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
           for (int c = lane; c < i; c += 32)
             s += Vt[r * (NB + 1) + c] * gWs[c] + Wt[r * (NB + 1) + c] * gVs[c];
           s = warp_sum(s);
-          w = tau * (__ldcg(g.ptop + r) - s) + alpha2 * vs[r];
+          w = tau * (pts[r] - s) + alpha2 * vs[r];
         }
         if (lane == 0) Wt[r * (NB + 1) + i] = w;
       }
       if (cta == 0 && tid < NB) {  // compact-WY T column: T[0:i,i] = -tau T[0:i,0:i] (V^T v)
         if (tid < i) {
           float s = 0.f;
-          for (int c2 = tid; c2 < i; ++c2) s += g.Tmat[tid * NB + c2] * gVs[c2];
-          g.Tmat[tid * NB + i] = -tau * s;
+          for (int c2 = tid; c2 < i; ++c2) s += Ts[tid * (NB + 1) + c2] * gVs[c2];
+          Ts[tid * (NB + 1) + i] = -tau * s;
         } else if (tid == i) {
-          g.Tmat[i * NB + i] = tau;
+          Ts[i * (NB + 1) + i] = tau;
         }
       }
     } else {
@@ -452,6 +475,13 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
       for (int r = tid; r < NB; r += PANEL_THREADS) Wt[r * (NB + 1) + i] = 0.f;
     }
     __syncthreads();
+    PTD_PHASE(5)
+  }
+#undef PTD_PHASE
+  if (cta == 0) {
+    __syncthreads();
+    for (int idx = tid; idx < NB * NB; idx += PANEL_THREADS)
+      g.Tmat[idx] = Ts[(idx / NB) * (NB + 1) + (idx % NB)];
   }
 }
 
@@ -917,8 +947,8 @@ struct Carver {
 struct Plan {
   float* Aw; long long ldA;
   __nv_bfloat16* Vs; long long ldv;
-  float *Vp, *Wp, *colbuf, *gpart, *ptop, *dvec, *evec, *taus, *Tmats, *X1;
-  double* npart;
+  float *Vp, *Wp, *colbuf, *gacc, *ptop, *dvec, *evec, *taus, *Tmats, *X1;
+  double* nacc;
   unsigned* bars;
   __nv_bfloat16 *VW, *WV, *Zs, *Xs;
   TriBufs tb;
@@ -950,8 +980,9 @@ Plan make_plan(void* ws, int d, int k) {
   p.Vp = cv.take<float>(D * NB);
   p.Wp = cv.take<float>(D * NB);
   p.colbuf = cv.take<float>(D);
-  p.npart = cv.take<double>(1024);
-  p.gpart = cv.take<float>(1024 * GP_STRIDE);
+  // per-panel accumulators for the cross-CTA reductions, zeroed once for all panels
+  p.nacc = cv.take<double>(static_cast<size_t>(p.npanels) * NB);
+  p.gacc = cv.take<float>(static_cast<size_t>(p.npanels) * NB * GP_STRIDE);
   p.ptop = cv.take<float>(NB);
   p.dvec = cv.take<float>(D);
   p.evec = cv.take<float>(D);
@@ -988,6 +1019,18 @@ Plan make_plan(void* ws, int d, int k) {
   } while (0)
 
 }  // namespace
+
+static int g_panel_prof = 0;
+void eigh_debug_profile(int enable) {
+  g_panel_prof = enable;
+  unsigned long long z[8] = {0};
+  cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
+}
+long long eigh_debug_phase_cycles(int k) {
+  unsigned long long v[8];
+  cudaMemcpyFromSymbol(v, g_phase_cycles, sizeof(v));
+  return (k >= 0 && k < 8) ? static_cast<long long>(v[k]) : 0;
+}
 
 size_t eigh_workspace_bytes(int d, int k) {
   if (d <= JACOBI_MAX) return 256;
@@ -1031,6 +1074,8 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
   }
   cudaMemsetAsync(p.Tmats, 0, static_cast<size_t>(p.npanels) * NB * NB * sizeof(float), st);
   cudaMemsetAsync(p.bars, 0, static_cast<size_t>(p.npanels) * sizeof(unsigned), st);
+  cudaMemsetAsync(p.nacc, 0, static_cast<size_t>(p.npanels) * NB * sizeof(double), st);
+  cudaMemsetAsync(p.gacc, 0, static_cast<size_t>(p.npanels) * NB * GP_STRIDE * sizeof(float), st);
   cudaMemsetAsync(p.Vp, 0, static_cast<size_t>(d) * NB * sizeof(float), st);
   cudaMemsetAsync(p.Wp, 0, static_cast<size_t>(d) * NB * sizeof(float), st);
   cudaMemsetAsync(p.evec, 0, static_cast<size_t>(d) * sizeof(float), st);
@@ -1051,14 +1096,17 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
     PanelArgs g;
     g.A = p.Aw; g.ldA = p.ldA; g.d = d; g.j0 = j0; g.ncols = std::min(NB, m);
     g.rows_per_cta = std::max(PANEL_WARPS, (m + sms - 1) / sms);
-    g.Vp = p.Vp; g.Wp = p.Wp; g.colbuf = p.colbuf; g.npart = p.npart; g.gpart = p.gpart;
+    g.Vp = p.Vp; g.Wp = p.Wp; g.colbuf = p.colbuf;
+    g.nacc = p.nacc + static_cast<size_t>(pi) * NB;
+    g.gacc = p.gacc + static_cast<size_t>(pi) * NB * GP_STRIDE;
     g.ptop = p.ptop; g.dvec = p.dvec; g.evec = p.evec; g.taus = p.taus;
     g.Tmat = p.Tmats + static_cast<size_t>(pi) * NB * NB;
     g.bar = p.bars + pi;
+    g.prof = g_panel_prof;
     const int grid = (m + g.rows_per_cta - 1) / g.rows_per_cta;
     const long long L = p.ldA - j0;
     const size_t nseg_max = static_cast<size_t>((L / 4 + 255) / 256);
-    const size_t smem = (static_cast<size_t>(L) + 2 * NB * (NB + 1) + g.rows_per_cta + 2 * NB +
+    const size_t smem = (static_cast<size_t>(L) + 3 * NB * (NB + 1) + g.rows_per_cta + 3 * NB +
                          PANEL_WARPS * 2 * NB + g.rows_per_cta * nseg_max) * sizeof(float);
     if (smem > 220 * 1024) return -22;  // d beyond what one SM's shared memory can stage
     void* args[] = {&g};

@@ -24,4 +24,8 @@ size_t eigh_workspace_bytes(int d, int k);
 int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, long long ldu,
          void* ws, size_t ws_bytes, cudaStream_t st);
 
+// Debug: per-phase cycle counters of the panel kernel (CTA 0), see eigh.cu.
+void eigh_debug_profile(int enable);
+long long eigh_debug_phase_cycles(int k);
+
 }  // namespace ptd

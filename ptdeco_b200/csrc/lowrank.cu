@@ -69,14 +69,18 @@ int stage(const void* src, int is_bf16, long long rows, int cols, long long ld, 
 constexpr int F_TILE_M = 128;
 constexpr int F_BK = 64;
 constexpr int F_TILE_N = 256;
-constexpr int F_STAGES = 3;
+constexpr int F_MAX_STAGES = 5;
 constexpr int F_XBYTES = F_TILE_M * F_BK * 2;    // X k-block: 128 rows x 128 B
-constexpr int F_WBYTES = 256 * F_BK * 2;         // W1 k-block (<= 256 rows) or W2 tile (256 rows)
-constexpr int F_STAGE = F_XBYTES + F_WBYTES;     // 48 KB
+constexpr int F_WBYTES = 256 * F_BK * 2;         // W2 tile: 256 rows x 128 B
 constexpr int F_HBLOCK = F_TILE_M * 128;         // one 64-wide k-block of H: 16 KB
 constexpr int F_EPI_WARPS = 8;
 constexpr int F_THREADS = 64 + 32 * F_EPI_WARPS;
-constexpr int F_SMEM = F_STAGES * F_STAGE + 4 * F_HBLOCK + 1024 + 256;
+constexpr int F_STG_BYTES = F_EPI_WARPS * 2 * 4096;  // output staging, 2 x 4 KB per epilogue warp
+// Shared-memory plans (the ring must keep ~2 us of TMA latency covered, so it is as deep as fits):
+//   kp <= 128: 4 slots of [X 16 KB | W1 16 KB]; a 32 KB W2 tile fills a whole slot; H 32 KB;
+//              separate double-buffered 64 KB output staging                  -> 225 KB
+//   kp  > 128: 3 slots of [X 16 KB | W 32 KB]; W2 tiles land in the W part; H 64 KB; the idle X
+//              parts of slots 0 and 1 are the output staging                  -> 208 KB
 
 struct FusedArgs {
   int n, in_f, k, out_f, kp;
@@ -85,6 +89,7 @@ struct FusedArgs {
   long long ldy;
   const float* bias;
   int tma_store;  // 1: Y tiles leave through shared memory + cp.async.bulk.tensor stores
+  int stages, slot_bytes, w2_off, stg_separate;
 };
 
 __global__ void __launch_bounds__(F_THREADS, 1)
@@ -94,11 +99,13 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
+  const int F_STAGES = g.stages, F_STAGE = g.slot_bytes;
   uint8_t* hbuf = smem + F_STAGES * F_STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(hbuf + 4 * F_HBLOCK);
+  uint8_t* stg_base = hbuf + (g.kp / F_BK) * F_HBLOCK;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + (g.stg_separate ? F_STG_BYTES : 0));
   uint64_t* full = bars;
-  uint64_t* empty = bars + F_STAGES;
-  uint64_t* h_full = bars + 2 * F_STAGES;
+  uint64_t* empty = bars + F_MAX_STAGES;
+  uint64_t* h_full = bars + 2 * F_MAX_STAGES;
   uint64_t* h_ready = h_full + 1;
   uint64_t* y_full = h_ready + 1;
   uint64_t* y_empty = y_full + 2;
@@ -153,7 +160,7 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       for (int t = t0; t < t1; ++t) {     // GEMM 2: W2 tiles
         for (int kb = 0; kb < kb2; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sB = smem + stage * F_STAGE + F_XBYTES;
+          uint8_t* sB = smem + stage * F_STAGE + g.w2_off;
           mbar_expect_tx(&full[stage], F_WBYTES);
           tma_load_3d(sB, &tmW2, &full[stage], kb * F_BK, t * F_TILE_N, 0);
           if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
@@ -191,7 +198,7 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         for (int kb = 0; kb < kb2; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sB = smem_u32(smem + stage * F_STAGE + F_XBYTES);
+          const uint32_t sB = smem_u32(smem + stage * F_STAGE + g.w2_off);
           const uint32_t sA = sH + kb * F_HBLOCK;
 #pragma unroll
           for (int ks = 0; ks < F_BK / 16; ++ks)
@@ -240,7 +247,9 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const bool yvec = ((g.ldy & 7) == 0) && ((reinterpret_cast<uintptr_t>(g.Y) & 15) == 0);
     // Output staging: the X slots of the operand ring are idle during GEMM 2 (the producer only
     // refills the W halves), so each epilogue warp owns a 4 KB slice (32 rows x 128 B, swizzled).
-    uint8_t* stg = smem + ((warp - 2) >> 2) * F_STAGE + ((warp - 2) & 3) * 4096;
+    uint8_t* stg0 = g.stg_separate ? stg_base + (warp - 2) * 8192
+                                   : smem + ((warp - 2) >> 2) * F_STAGE + ((warp - 2) & 3) * 4096;
+    int stg_flip = 0;
     for (int t = t0; t < t1; ++t) {
       mbar_wait(&y_full[acc], acc_phase);
       tc_fence_after();
@@ -253,7 +262,11 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           tmem_ld_32x32(taddr, ra);
           tmem_ld_32x32(taddr + 32, rb);
           tmem_ld_wait();
-          if (lane == 0) bulk_wait_read_all();  // the previous store has drained this slice
+          uint8_t* stg = stg0 + (g.stg_separate ? stg_flip * 4096 : 0);
+          stg_flip ^= 1;
+          if (lane == 0) {  // the store that last used this slice has finished reading it
+            if (g.stg_separate) bulk_wait_read_1(); else bulk_wait_read_all();
+          }
           __syncwarp();
           const int n0 = nbase + rnd * 64;
           const bool full64 = (n0 + 64 <= g.out_f);
@@ -376,10 +389,21 @@ int launch_fused(const void* X, long long ldx, const void* W1, long long ldw1, c
   if ((rc = make_tma_2d_bf16(&tx, X, in_f, n, ldx, F_TILE_M))) return rc;
   if ((rc = make_tma_2d_bf16(&tw1, W1, in_f, k, ldw1, g.kp))) return rc;
   if ((rc = make_tma_2d_bf16(&tw2, W2, k, out_f, ldw2, F_TILE_N))) return rc;
+  if (g.kp <= 128) {
+    g.stages = 4; g.slot_bytes = 32768; g.w2_off = 0; g.stg_separate = 1;
+  } else {
+    g.stages = 3; g.slot_bytes = 49152; g.w2_off = F_XBYTES; g.stg_separate = 0;
+  }
+  if (const char* e = std::getenv("PTDECO_B200_FUSED_STAGES")) {  // experiment knob
+    const int v = atoi(e);
+    if (v >= 2 && v <= g.stages) g.stages = v;
+  }
+  const int F_SMEM = g.stages * g.slot_bytes + (g.kp / F_BK) * F_HBLOCK +
+                     (g.stg_separate ? F_STG_BYTES : 0) + 1024 + 256;
   static bool attr = false;
   if (!attr) {
     if (cudaFuncSetAttribute(lowrank_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             F_SMEM) != cudaSuccess)
+                             227 * 1024) != cudaSuccess)
       return -12;
     attr = true;
   }

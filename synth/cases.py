@@ -94,8 +94,11 @@ def falor_case(name: str):
         # 10 classes (the convention of the reference's tests/test_decompose_torchvision_timm.py:28-34)
         model = models.DeiTLike(num_classes=10)
         stream = IndexedStream(lambda i: streams.image_batch(0, i, 5))
+        # use_float64=True (the reference examples' setting): with fp32 LAPACK the reference's own
+        # eigenvectors are noise-determined in the flat tail of these random-init spectra (its fp32
+        # and fp64 runs disagree by 20 % in NSR on blocks.0.attn.proj), which makes parity ill-posed.
         kw.update(nsr_final_threshold=0.05, kl_final_threshold=0.02, num_data_steps=8,
-                  num_metric_steps=2, use_float64=False)
+                  num_metric_steps=2, use_float64=True)
     elif name == "convnext_tiny":
         # BASELINE.json configs[1]: torchvision convnext_tiny (random init, 37 Linear targets; it has
         # no 1x1 convs), synthetic ImageNet-shape batches; layer_scale set to 1 so that the block
@@ -108,8 +111,10 @@ def falor_case(name: str):
             for n_, p_ in model.named_parameters():
                 if n_.endswith("layer_scale"):
                     p_.fill_(1.0)
-        stream = IndexedStream(lambda i: streams.image_batch(4, i, 4))
-        kw.update(nsr_final_threshold=0.055, kl_final_threshold=0.02, num_data_steps=2,
+        # 16 calibration batches of 8 images: the last stage sees 8*49*16 = 6272 rows >= d = 3072, so
+        # no tested rank falls inside the rank-deficient (arbitrary-basis) part of a covariance
+        stream = IndexedStream(lambda i: streams.image_batch(4, i, 8))
+        kw.update(nsr_final_threshold=0.055, kl_final_threshold=0.02, num_data_steps=16,
                   num_metric_steps=1)
     else:
         raise KeyError(name)

@@ -228,6 +228,24 @@ def test_lowrank_forward(dev, dtype, tol, n, in_f, k, out_f):
     assert (y.double().cpu() - ref).abs().max() <= tol * ref.abs().max()
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+def test_lowrank_sequential_matches_torch_sequential(dev, dtype, tol):
+    from ptdeco_b200 import modules
+    g = torch.Generator().manual_seed(21)
+    lin = torch.nn.Sequential(torch.nn.Linear(96, 24, bias=False), torch.nn.Linear(24, 80)).to(dev).to(dtype)
+    conv = torch.nn.Sequential(torch.nn.Conv2d(32, 8, 1, bias=False), torch.nn.Conv2d(8, 40, 1)).to(dev).to(dtype)
+    holder = torch.nn.ModuleDict({"lin": lin, "conv": conv})
+    xl = torch.randn(3, 17, 96, generator=g).to(dtype).to(dev)
+    xc = torch.randn(2, 32, 9, 7, generator=g).to(dtype).to(dev)
+    with torch.no_grad():
+        ref_l, ref_c = lin(xl).float(), conv(xc).float()
+        assert modules.fuse_decomposed_modules_in_place(holder) == 2
+        out_l, out_c = holder["lin"](xl), holder["conv"](xc)
+    assert out_l.shape == ref_l.shape and out_c.shape == ref_c.shape and out_l.dtype == dtype
+    assert (out_l.float() - ref_l).abs().max() <= tol * ref_l.abs().max()
+    assert (out_c.float() - ref_c).abs().max() <= tol * ref_c.abs().max()
+
+
 # ------------------------------------------------------------------------------------ K6
 def test_metrics_match_reference(dev, golden_dir):
     from ptdeco_b200 import utils

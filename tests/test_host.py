@@ -228,3 +228,24 @@ def test_two_rank_gloo_sharded_covariance(tmp_path):
             P.update_Eyyt_in_place(full, cases.step_spectrum_batch(n, d, 10 * layer + i).numpy())
         u = P.top_k(P.dwain_get_eigenvectors(full / steps), k)
         assert P.min_principal_cosine(u, r0[layer].numpy()) > 0.9999
+
+
+def test_lowrank_sequential_is_a_sequential():
+    """The fused module keeps the artifact contract: config type, state-dict keys, CPU behaviour."""
+    from ptdeco_b200 import modules, utils
+    model = torch.nn.ModuleDict({
+        "a": torch.nn.Sequential(torch.nn.Linear(6, 3, bias=False), torch.nn.Linear(3, 5)),
+        "b": torch.nn.Sequential(torch.nn.Conv2d(4, 2, 1, bias=False), torch.nn.Conv2d(2, 7, 1)),
+        "c": torch.nn.Sequential(torch.nn.Linear(6, 3), torch.nn.ReLU()),
+        "d": torch.nn.Sequential(torch.nn.Linear(6, 3), torch.nn.Linear(3, 5)),  # first has a bias
+    })
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    cfg_before = utils.get_module_config(model["a"])
+    x = torch.randn(2, 6)
+    y_before = model["a"](x)
+    assert modules.fuse_decomposed_modules_in_place(model) == 2
+    assert isinstance(model["a"], modules.LowRankSequential) and isinstance(model["b"], modules.LowRankSequential)
+    assert type(model["c"]) is torch.nn.Sequential and type(model["d"]) is torch.nn.Sequential
+    assert utils.get_module_config(model["a"]) == cfg_before
+    assert list(model.state_dict().keys()) == list(before.keys())
+    torch.testing.assert_close(model["a"](x), y_before)  # CPU input: the reference's own path

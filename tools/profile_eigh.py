@@ -21,3 +21,15 @@ for _ in range(reps):
 e1.record()
 torch.cuda.synchronize()
 print(f"eigh d={d} k={k}: {e0.elapsed_time(e1) / reps:.3f} ms")
+if os.environ.get("PANEL_PROF"):
+    from ptdeco_b200 import _native as nat
+    L = nat.lib()
+    L.ptdeco_debug_set(100, 1)
+    linalg.eigh(cov, k=k)
+    torch.cuda.synchronize()
+    cyc = [L.ptdeco_debug_get(100 + i) for i in range(6)]
+    L.ptdeco_debug_set(100, 0)
+    names = ["P1 column update", "barrier A", "reflector + v fill", "symv + partial dots", "barrier B", "P3 w column"]
+    tot = sum(cyc)
+    for n_, c in zip(names, cyc):
+        print(f"  panel phase {n_:22s} {c / 1e6:9.2f} Mcycles  {100.0 * c / max(tot, 1):5.1f} %  {c / d / 1.0:8.0f} cycles/column")
