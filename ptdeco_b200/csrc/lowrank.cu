@@ -250,11 +250,24 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     uint8_t* stg0 = g.stg_separate ? stg_base + (warp - 2) * 8192
                                    : smem + ((warp - 2) >> 2) * F_STAGE + ((warp - 2) & 3) * 4096;
     int stg_flip = 0;
+    const bool bias_vec = (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0;
     for (int t = t0; t < t1; ++t) {
       mbar_wait(&y_full[acc], acc_phase);
       tc_fence_after();
       const int nbase = t * F_TILE_N + half * 128;
       if (g.tma_store) {
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.bias != nullptr) {
+          const int c = nbase + 4 * lane;
+          if (c + 3 < g.out_f && bias_vec) {
+            b4 = __ldg(reinterpret_cast<const float4*>(g.bias + c));
+          } else {
+            if (c < g.out_f) b4.x = __ldg(g.bias + c);
+            if (c + 1 < g.out_f) b4.y = __ldg(g.bias + c + 1);
+            if (c + 2 < g.out_f) b4.z = __ldg(g.bias + c + 2);
+            if (c + 3 < g.out_f) b4.w = __ldg(g.bias + c + 3);
+          }
+        }
 #pragma unroll 1
         for (int rnd = 0; rnd < 2; ++rnd) {
           uint32_t ra[32], rb[32];
@@ -269,14 +282,19 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           }
           __syncwarp();
           const int n0 = nbase + rnd * 64;
-          const bool full64 = (n0 + 64 <= g.out_f);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             __align__(16) __nv_bfloat16 o[8];
+            // lane l holds the bias of columns 4l..4l+3 of this warp's 128 (one 16-byte load per
+            // tile); shuffles hand each chunk its eight values instead of eight global loads
+            const int l0 = rnd * 16 + 2 * j;
+            const float bb[8] = {__shfl_sync(0xffffffffu, b4.x, l0),     __shfl_sync(0xffffffffu, b4.y, l0),
+                                 __shfl_sync(0xffffffffu, b4.z, l0),     __shfl_sync(0xffffffffu, b4.w, l0),
+                                 __shfl_sync(0xffffffffu, b4.x, l0 + 1), __shfl_sync(0xffffffffu, b4.y, l0 + 1),
+                                 __shfl_sync(0xffffffffu, b4.z, l0 + 1), __shfl_sync(0xffffffffu, b4.w, l0 + 1)};
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              float x = __uint_as_float(j < 4 ? ra[8 * j + e] : rb[8 * (j - 4) + e]);
-              if (g.bias != nullptr && (full64 || n0 + 8 * j + e < g.out_f)) x += __ldg(g.bias + n0 + 8 * j + e);
+              const float x = __uint_as_float(j < 4 ? ra[8 * j + e] : rb[8 * (j - 4) + e]) + bb[e];
               o[e] = __float2bfloat16_rn(x);
             }
             *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =

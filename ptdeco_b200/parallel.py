@@ -38,10 +38,18 @@ def owner_of(layer_index: int, world: int) -> int:
     return layer_index % world
 
 
+def _flush(acc) -> None:
+    """Staged (deferred) batches must be folded into C before C crosses ranks."""
+    flush = getattr(acc, "flush", None)
+    if flush is not None:
+        flush()
+
+
 def allreduce_accumulator(acc, group) -> None:
     """Sum the partial covariance (and column sums, step counts) over ranks, in place."""
     if group is None:
         return
+    _flush(acc)
     steps = torch.tensor([acc.steps], dtype=torch.int64, device=acc.C.device)
     dist.all_reduce(acc.C, op=dist.ReduceOp.SUM, group=group)
     if getattr(acc, "colsum", None) is not None:
@@ -55,6 +63,7 @@ def reduce_accumulator_to(acc, owner: int, group) -> None:
     count is summed everywhere so every rank agrees on it."""
     if group is None:
         return
+    _flush(acc)
     steps = torch.tensor([acc.steps], dtype=torch.int64, device=acc.C.device)
     dst = dist.get_global_rank(group, owner)
     dist.reduce(acc.C, dst=dst, op=dist.ReduceOp.SUM, group=group)

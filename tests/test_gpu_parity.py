@@ -342,6 +342,28 @@ def test_falor_decompose_in_place_matches_reference(dev, golden_dir, name):
         torch.testing.assert_close(fresh(xb), model(xb))
 
 
+@pytest.mark.parametrize("name", ["deit_tiny", "convnext_tiny"])
+def test_falor_baseline_configs_match_reference(dev, golden_dir, name):
+    """BASELINE.json configs[0] (DeiT-tiny layout, (5,3,224,224) inputs) and configs[1]
+    (torchvision convnext_tiny): the whole trial sequence (339 / 285 rank trials) and the chosen
+    ranks must be the unmodified reference's."""
+    import ptdeco_b200.falor as falor
+    gold = json.load(open(os.path.join(golden_dir, f"falor_{name}.json")))
+    model, stream, kw = cases.falor_case(name)
+    model.to(dev)
+    trace = []
+    cfg = falor.decompose_in_place(module=model, device=dev, data_iterator=stream, trace=trace, **kw)
+    assert stream.position == gold["stream_position"]
+    assert [(t["name"], t["rank"]) for t in trace] == [(t["name"], t["rank"]) for t in gold["trace"]]
+    assert list(cfg.keys()) == list(gold["decompose_config"].keys())
+    assert _ranks(cfg) == _ranks(gold["decompose_config"])
+    for n in cfg:
+        assert cfg[n]["__meta__"]["proportion"] == gold["decompose_config"][n]["__meta__"]["proportion"]
+    # metrics: tight wherever the tested rank lies inside the well-determined part of the spectrum
+    rel = sorted(abs(t["nsr"] - g["nsr"]) / max(g["nsr"], 1e-9) for t, g in zip(trace, gold["trace"]))
+    assert rel[len(rel) // 2] < 1e-3
+
+
 @pytest.mark.parametrize("name", list(cases.DWAIN_CASES))
 def test_dwain_decompose_in_place_matches_reference(dev, golden_dir, name):
     import ptdeco_b200.dwain as dwain
