@@ -253,39 +253,56 @@ def _process_module(
         uk = u_matrix[:, u_matrix.shape[1] - rank:].to(orig_dtype).to(device)
         return uk, linalg.factor_w1(orig_weight, uk)
 
-    tried = False
-    i = 1
-    rank_best = full_rank
+    # ---- the candidate ranks are data independent (D:407-421): enumerate them first ...
+    plan: list[tuple[int, int, float, float]] = []
     rank_new = full_rank
-    nsr_best, ppl_deco_best = 0.0, 0.0
+    skipped: list[int] = []
     while rank_new > min_rank:
         rank_new = int(rank_new * reduction_factor)
         previous_params = _get_params_for_proportion(1.0, dim_in, dim_out)
         current_params = _get_params_for_proportion(rank_new / full_rank, dim_in, dim_out)
         drop_in_params = previous_params - current_params
         fraction_removed = drop_in_params / num_params
-        ppl_diff_threshold = fraction_removed * trade_off_factor
         if drop_in_params == 0:
-            logger.info(f"{indent}{i=} {rank_new=} does not lead to params drop, skipping")
+            skipped.append(rank_new)
             continue
+        plan.append((rank_new, drop_in_params, fraction_removed, fraction_removed * trade_off_factor))
+    for rn in skipped:
+        logger.info(f"{indent}{rn=} does not lead to params drop, skipping")
 
-        uk, w1 = factors(rank_new)
+    # ---- ... evaluate every candidate (the reference evaluates all of them too: the smallest
+    # accepted rank wins even when a larger one was rejected). The model does not change inside
+    # one layer's search, so with a process group trial t is evaluated by rank t mod world; every
+    # rank draws every metric batch, keeping iterator positions those of the reference.
+    group = parallel.default_group()
+    my_rank, world = parallel.rank_and_world(group)
+    results = torch.zeros((max(1, len(plan)), 3), dtype=torch.float64, device=orig_device)
+    for t, (rank_t, _, _, _) in enumerate(plan):
+        batches = [next(metric_iterator) for _ in range(num_metric_steps)]
+        if t % world != my_rank:
+            continue
+        uk, w1 = factors(rank_t)
         deco_weight = linalg.deco_weight(uk, w1).to(orig_dtype)
-        tried = True
-
         acc = torch.zeros(3, dtype=torch.float64, device=orig_device)
-        ppl_orig_sample = None
-        for _ in range(num_metric_steps):
-            input_dict = utils.to_device(next(metric_iterator), device)
+        for batch in batches:
+            input_dict = utils.to_device(batch, device)
             nsr_sample, ppl_deco_sample, ppl_orig_sample = _compute_metrics(
                 input_dict=input_dict, root_module=root_module, decomposed_submodule=wrapper,
                 orig_weight=orig_weight, deco_weight=deco_weight, loss_fn=loss_fn)
             ppl_diff_sample = (ppl_deco_sample - ppl_orig_sample) / ppl_orig_sample
             acc += torch.stack([ppl_diff_sample.double(), nsr_sample.double(),
                                 ppl_deco_sample.double()])
-        acc = parallel.mean_over_ranks(acc / num_metric_steps, None)
-        ppl_diff_new, nsr_new, ppl_deco_new = acc.tolist()  # the one host sync of the trial
+        results[t] = acc / num_metric_steps
+    if group is not None and len(plan) > 0:
+        torch.distributed.all_reduce(results, group=group)  # rows of other ranks are zero here
+    measured = results.tolist() if len(plan) > 0 else []  # the one host sync of the layer
 
+    # ---- ... then apply the accept / reject rules in order (D:445-487)
+    tried = len(plan) > 0
+    rank_best = full_rank
+    nsr_best, ppl_deco_best = 0.0, 0.0
+    for i, ((rank_new, drop_in_params, fraction_removed, ppl_diff_threshold),
+            (ppl_diff_new, nsr_new, ppl_deco_new)) in enumerate(zip(plan, measured), start=1):
         logger.info(f"{indent}{i=} {ppl_deco_new=:.4f} {ppl_diff_new=:.4f} "
                     f"{ppl_diff_threshold=:.4f} {fraction_removed=:.4f} {nsr_new=:.4f}")
         reject = f"{indent}{i=} REJECTING rank {rank_new}/{full_rank}"
@@ -307,7 +324,6 @@ def _process_module(
         logger.info(f"{indent}{i=} {rank_new=}/{full_rank} {nsr_new=:.6f} {ppl_diff_new=:.6f}  "
                     f"{rank_best=} {nsr_best=:.6f} {ppl_deco_best=:.6f}")
         logger.info(f"{indent}---")
-        i += 1
 
     wrapper.set_weight(orig_weight)
     decompose_decision = False
