@@ -345,7 +345,7 @@ def main() -> None:
         barrier()
         forward_only_ms = parallel.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
 
-        originals = D._install_covariance_modules(model, names, True)
+        originals = D._install_covariance_modules(model, names, True, reduction_factor=0.5)
         last = model.get_submodule(names[-1])
 
         def e2e_step(ids_host):
@@ -367,7 +367,8 @@ def main() -> None:
         e2e = {"value": tokens_per_step / (e2e_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": SEQ * 8, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
                "model_forward_only_ms": forward_only_ms,
-               "path": "ptdeco_b200.dwain covariance-computing modules in a Llama-3-8B-shape model"}
+               "path": "ptdeco_b200.dwain covariance-computing modules in a Llama-3-8B-shape model "
+                       "(input-side covariance for gate/up, output-side elsewhere)"}
         D._restore_modules(model, originals)
         del model, originals
         torch.cuda.empty_cache()

@@ -73,14 +73,14 @@ constexpr int F_MAX_STAGES = 5;
 constexpr int F_XBYTES = F_TILE_M * F_BK * 2;    // X k-block: 128 rows x 128 B
 constexpr int F_WBYTES = 256 * F_BK * 2;         // W2 tile: 256 rows x 128 B
 constexpr int F_HBLOCK = F_TILE_M * 128;         // one 64-wide k-block of H: 16 KB
-constexpr int F_EPI_WARPS = 8;
+constexpr int F_EPI_WARPS = 16;  // 4 per TMEM lane quarter: one 64-column slice each
 constexpr int F_THREADS = 64 + 32 * F_EPI_WARPS;
-constexpr int F_STG_BYTES = F_EPI_WARPS * 2 * 4096;  // output staging, 2 x 4 KB per epilogue warp
+constexpr int F_STG_BYTES = F_EPI_WARPS * 4096;  // output staging, 4 KB per epilogue warp
 // Shared-memory plans (the ring must keep ~2 us of TMA latency covered, so it is as deep as fits):
 //   kp <= 128: 4 slots of [X 16 KB | W1 16 KB]; a 32 KB W2 tile fills a whole slot; H 32 KB;
-//              separate double-buffered 64 KB output staging                  -> 225 KB
+//              separate 64 KB output staging (4 KB per epilogue warp)         -> 225 KB
 //   kp  > 128: 3 slots of [X 16 KB | W 32 KB]; W2 tiles land in the W part; H 64 KB; the idle X
-//              parts of slots 0 and 1 are the output staging                  -> 208 KB
+//              parts of the three slots plus 16 KB are the output staging     -> 224 KB
 
 struct FusedArgs {
   int n, in_f, k, out_f, kp;
@@ -102,7 +102,7 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   const int F_STAGES = g.stages, F_STAGE = g.slot_bytes;
   uint8_t* hbuf = smem + F_STAGES * F_STAGE;
   uint8_t* stg_base = hbuf + (g.kp / F_BK) * F_HBLOCK;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + (g.stg_separate ? F_STG_BYTES : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + (g.stg_separate ? F_STG_BYTES : 4 * 4096));
   uint64_t* full = bars;
   uint64_t* empty = bars + F_MAX_STAGES;
   uint64_t* h_full = bars + 2 * F_MAX_STAGES;
@@ -118,6 +118,12 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   const int t1 = min(g.out_tiles, t0 + g.tiles_per_group);
   const int kb1 = (g.in_f + F_BK - 1) / F_BK;
   const int kb2 = g.kp / F_BK;
+  // Every CTA streams the SAME W1 k-blocks and W2 tiles; started in lockstep they all hit the
+  // same L2 lines at the same time. Each CTA therefore starts at its own offset of the k loop
+  // (a sum: order-free) and of its tile list.
+  const int ntl = t1 - t0;
+  const int rot1 = static_cast<int>((blockIdx.x * 7u) % static_cast<unsigned>(kb1));
+  const int rot3 = ntl > 0 ? static_cast<int>(rt % static_cast<unsigned>(ntl)) : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -149,7 +155,8 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < kb1; ++kb) {  // GEMM 1 operands
+      for (int kk = 0; kk < kb1; ++kk) {  // GEMM 1 operands
+        const int kb = (kk + rot1) % kb1;
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* sA = smem + stage * F_STAGE;
         mbar_expect_tx(&full[stage], F_XBYTES + g.kp * 128);
@@ -157,7 +164,8 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         tma_load_3d(sA + F_XBYTES, &tmW1, &full[stage], kb * F_BK, 0, 0);
         if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
       }
-      for (int t = t0; t < t1; ++t) {     // GEMM 2: W2 tiles
+      for (int tt = 0; tt < ntl; ++tt) {  // GEMM 2: W2 tiles
+        const int t = t0 + (tt + rot3) % ntl;
         for (int kb = 0; kb < kb2; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sB = smem + stage * F_STAGE + g.w2_off;
@@ -213,15 +221,13 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
   } else {
     const int q = warp & 3;                 // TMEM lane quarter of this warp
-    const int half = (warp - 2) >> 2;       // column half
+    const int cg = (warp - 2) >> 2;         // column group 0..3
     const int row = q * 32 + lane;
     const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
     // ---- H: TMEM -> bf16 -> swizzled shared memory (the layout TMA would have produced)
     mbar_wait(h_full, 0);
     tc_fence_after();
-    const int hcols = g.kp / 2;
-    for (int c = 0; c < hcols / 32; ++c) {
-      const int col0 = half * hcols + c * 32;
+    for (int col0 = cg * 32; col0 < g.kp; col0 += 4 * 32) {
       uint32_t r[32];
       tmem_ld_32x32(h_tmem + col0 + lane_bits, r);
       tmem_ld_wait();
@@ -240,111 +246,92 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(h_ready);
-    // ---- Y tiles
+    // ---- Y tiles: this warp owns rows [32q, 32q+32) x columns [64cg, 64cg+64) of every tile
     int acc = 0;
     uint32_t acc_phase = 0;
     const int m = m0 + row;
     const bool yvec = ((g.ldy & 7) == 0) && ((reinterpret_cast<uintptr_t>(g.Y) & 15) == 0);
-    // Output staging: the X slots of the operand ring are idle during GEMM 2 (the producer only
-    // refills the W halves), so each epilogue warp owns a 4 KB slice (32 rows x 128 B, swizzled).
-    uint8_t* stg0 = g.stg_separate ? stg_base + (warp - 2) * 8192
-                                   : smem + ((warp - 2) >> 2) * F_STAGE + ((warp - 2) & 3) * 4096;
-    int stg_flip = 0;
     const bool bias_vec = (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0;
-    for (int t = t0; t < t1; ++t) {
+    // 32 rows x 128 B, swizzled like a TMA box. Wide-rank plan: the X parts of the ring slots are
+    // idle during GEMM 2 (the producer only refills the W parts) and host 12 of the 16 slices.
+    const int ew = warp - 2;
+    uint8_t* stg = g.stg_separate ? stg_base + ew * 4096
+                   : (ew < 12 ? smem + (ew >> 2) * F_STAGE + (ew & 3) * 4096 : stg_base + (ew - 12) * 4096);
+    for (int tt = 0; tt < ntl; ++tt) {
+      const int t = t0 + (tt + rot3) % ntl;
       mbar_wait(&y_full[acc], acc_phase);
       tc_fence_after();
-      const int nbase = t * F_TILE_N + half * 128;
-      if (g.tma_store) {
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g.bias != nullptr) {
-          const int c = nbase + 4 * lane;
-          if (c + 3 < g.out_f && bias_vec) {
-            b4 = __ldg(reinterpret_cast<const float4*>(g.bias + c));
-          } else {
-            if (c < g.out_f) b4.x = __ldg(g.bias + c);
-            if (c + 1 < g.out_f) b4.y = __ldg(g.bias + c + 1);
-            if (c + 2 < g.out_f) b4.z = __ldg(g.bias + c + 2);
-            if (c + 3 < g.out_f) b4.w = __ldg(g.bias + c + 3);
-          }
-        }
-#pragma unroll 1
-        for (int rnd = 0; rnd < 2; ++rnd) {
-          uint32_t ra[32], rb[32];
-          const uint32_t taddr = tmem_base + acc * F_TILE_N + half * 128 + rnd * 64 + lane_bits;
-          tmem_ld_32x32(taddr, ra);
-          tmem_ld_32x32(taddr + 32, rb);
-          tmem_ld_wait();
-          uint8_t* stg = stg0 + (g.stg_separate ? stg_flip * 4096 : 0);
-          stg_flip ^= 1;
-          if (lane == 0) {  // the store that last used this slice has finished reading it
-            if (g.stg_separate) bulk_wait_read_1(); else bulk_wait_read_all();
-          }
-          __syncwarp();
-          const int n0 = nbase + rnd * 64;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            __align__(16) __nv_bfloat16 o[8];
-            // lane l holds the bias of columns 4l..4l+3 of this warp's 128 (one 16-byte load per
-            // tile); shuffles hand each chunk its eight values instead of eight global loads
-            const int l0 = rnd * 16 + 2 * j;
-            const float bb[8] = {__shfl_sync(0xffffffffu, b4.x, l0),     __shfl_sync(0xffffffffu, b4.y, l0),
-                                 __shfl_sync(0xffffffffu, b4.z, l0),     __shfl_sync(0xffffffffu, b4.w, l0),
-                                 __shfl_sync(0xffffffffu, b4.x, l0 + 1), __shfl_sync(0xffffffffu, b4.y, l0 + 1),
-                                 __shfl_sync(0xffffffffu, b4.z, l0 + 1), __shfl_sync(0xffffffffu, b4.w, l0 + 1)};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float x = __uint_as_float(j < 4 ? ra[8 * j + e] : rb[8 * (j - 4) + e]) + bb[e];
-              o[e] = __float2bfloat16_rn(x);
-            }
-            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                *reinterpret_cast<const uint4*>(o);
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0 && n0 < g.out_f && m0 + q * 32 < g.n) {
-            tma_store_3d(&tmY, stg, n0, m0 + q * 32, 0);
-            bulk_commit();
-          }
-        }
-      } else {
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + acc * F_TILE_N + half * 128 + c * 32 + lane_bits, r);
-        tmem_ld_wait();
-        const int n0 = nbase + c * 32;
-        if (m < g.n && n0 < g.out_f) {
-          __nv_bfloat16* yrow = g.Y + static_cast<long long>(m) * g.ldy + n0;
-          if (yvec && n0 + 32 <= g.out_f) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              __align__(16) __nv_bfloat16 o[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                float x = __uint_as_float(r[8 * j + e]);
-                if (g.bias != nullptr) x += __ldg(g.bias + n0 + 8 * j + e);
-                o[e] = __float2bfloat16_rn(x);
-              }
-              *reinterpret_cast<uint4*>(yrow + 8 * j) = *reinterpret_cast<const uint4*>(o);
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              if (n0 + e < g.out_f) {
-                float x = __uint_as_float(r[e]);
-                if (g.bias != nullptr) x += __ldg(g.bias + n0 + e);
-                yrow[e] = __float2bfloat16_rn(x);
-              }
-            }
-          }
-        }
-      }
-      }
+      const int n0 = t * F_TILE_N + cg * 64;
+      uint32_t ra[32], rb[32];
+      const uint32_t taddr = tmem_base + acc * F_TILE_N + cg * 64 + lane_bits;
+      tmem_ld_32x32(taddr, ra);
+      tmem_ld_32x32(taddr + 32, rb);
+      tmem_ld_wait();
+      // the accumulator is in registers: hand the TMEM buffer back before the stores
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&y_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (g.bias != nullptr) {  // same 64 columns for every lane: broadcast 16-byte loads (L1 hits)
+        if (bias_vec && n0 + 64 <= g.out_f) {
+          const float4* b4 = reinterpret_cast<const float4*>(g.bias + n0);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float4 lo = __ldg(b4 + e), hi = __ldg(b4 + 8 + e);
+            ra[4 * e + 0] = __float_as_uint(__uint_as_float(ra[4 * e + 0]) + lo.x);
+            ra[4 * e + 1] = __float_as_uint(__uint_as_float(ra[4 * e + 1]) + lo.y);
+            ra[4 * e + 2] = __float_as_uint(__uint_as_float(ra[4 * e + 2]) + lo.z);
+            ra[4 * e + 3] = __float_as_uint(__uint_as_float(ra[4 * e + 3]) + lo.w);
+            rb[4 * e + 0] = __float_as_uint(__uint_as_float(rb[4 * e + 0]) + hi.x);
+            rb[4 * e + 1] = __float_as_uint(__uint_as_float(rb[4 * e + 1]) + hi.y);
+            rb[4 * e + 2] = __float_as_uint(__uint_as_float(rb[4 * e + 2]) + hi.z);
+            rb[4 * e + 3] = __float_as_uint(__uint_as_float(rb[4 * e + 3]) + hi.w);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            if (n0 + e < g.out_f) ra[e] = __float_as_uint(__uint_as_float(ra[e]) + __ldg(g.bias + n0 + e));
+            if (n0 + 32 + e < g.out_f)
+              rb[e] = __float_as_uint(__uint_as_float(rb[e]) + __ldg(g.bias + n0 + 32 + e));
+          }
+        }
+      }
+      if (g.tma_store) {
+        if (lane == 0) bulk_wait_read_all();  // the previous tile's store has drained the slice
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            o[e] = __float2bfloat16_rn(__uint_as_float(j < 4 ? ra[8 * j + e] : rb[8 * (j - 4) + e]));
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+              *reinterpret_cast<const uint4*>(o);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && n0 < g.out_f && m0 + q * 32 < g.n) {
+          tma_store_3d(&tmY, stg, n0, m0 + q * 32, 0);
+          bulk_commit();
+        }
+      } else if (m < g.n && n0 < g.out_f) {
+        __nv_bfloat16* yrow = g.Y + static_cast<long long>(m) * g.ldy + n0;
+        if (yvec && n0 + 64 <= g.out_f) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              o[e] = __float2bfloat16_rn(__uint_as_float(j < 4 ? ra[8 * j + e] : rb[8 * (j - 4) + e]));
+            *reinterpret_cast<uint4*>(yrow + 8 * j) = *reinterpret_cast<const uint4*>(o);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 64; ++e)
+            if (n0 + e < g.out_f)
+              yrow[e] = __float2bfloat16_rn(__uint_as_float(e < 32 ? ra[e] : rb[e - 32]));
+        }
+      }
     }
     if (g.tma_store && lane == 0) bulk_wait_read_all();  // staging must outlive the last store
   }
@@ -417,7 +404,7 @@ int launch_fused(const void* X, long long ldx, const void* W1, long long ldw1, c
     if (v >= 2 && v <= g.stages) g.stages = v;
   }
   const int F_SMEM = g.stages * g.slot_bytes + (g.kp / F_BK) * F_HBLOCK +
-                     (g.stg_separate ? F_STG_BYTES : 0) + 1024 + 256;
+                     (g.stg_separate ? F_STG_BYTES : 4 * 4096) + 1024 + 256;
   static bool attr = false;
   if (!attr) {
     if (cudaFuncSetAttribute(lowrank_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

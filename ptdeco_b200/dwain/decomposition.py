@@ -8,7 +8,10 @@ splits, per-layer `finetune_fn`, same `decompose_config`.
 
   D:152      Eyyt += einsum(y, y) / N          -> tcgen05 SYRK, fp32 accumulation of exact bf16
                                                   products (the reference rounds each per-step
-                                                  product to bf16 for bf16 models)
+                                                  product to bf16 for bf16 models, SURVEY.md 6.1);
+                                                  for in < out layers the INPUT covariance is
+                                                  accumulated and C = W S W^T is solved as an
+                                                  in x in problem (same eigenvectors)
   D:158-162  damping + torch.linalg.eigh       -> ptdeco_cov_finalize + ptdeco_eigh (top-k)
   D:193-204  CovarianceComputingLinearModule   -> layer forward on the tcgen05 GEMM engine + SYRK
   D:427-429  U = W^T uk ; (U V)^T              -> ptdeco_gemm
@@ -77,18 +80,21 @@ def _get_eigenvectors(acc: linalg.CovarianceAccumulator, num_vectors: Optional[i
 
 class CovarianceComputingLinearModule(torch.nn.Module):
     """D:166-208: stands in for a target Linear during the precompute pass; its forward IS the
-    layer forward (y = x W^T on the tcgen05 GEMM engine) and folds y into the covariance."""
+    layer forward (y = x W^T on the tcgen05 GEMM engine) and folds the layer's activations into
+    the covariance: the output y like the reference, or -- when in < out and only eigenvectors in
+    range(W) are wanted -- the input x (linalg.eigvecs_from_input_covariance)."""
 
     def __init__(self, weight: torch.nn.Parameter, bias: Optional[torch.nn.Parameter],
-                 decompose_in_float64: bool):
+                 decompose_in_float64: bool, num_vectors: Optional[int] = None):
         super().__init__()
         self.weight = weight
         self.bias = bias
         self.in_features = weight.shape[1]
         self.out_features = weight.shape[0]
+        self.input_side = linalg.use_input_side(self.in_features, self.out_features, num_vectors)
+        d = self.in_features if self.input_side else self.out_features
         self.acc = linalg.CovarianceAccumulator(
-            self.out_features, weight.device,
-            defer_rows=linalg.default_defer_rows(self.out_features, weight.element_size()))
+            d, weight.device, defer_rows=linalg.default_defer_rows(d, weight.element_size()))
         self.use_float64 = decompose_in_float64  # accepted; see falor's use_float64 note
 
     @property
@@ -98,7 +104,7 @@ class CovarianceComputingLinearModule(torch.nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         rows = x.reshape(-1, self.in_features)
         y_rows = linalg.linear_nt(rows, self.weight.detach())
-        _update_Eyyt_in_place(self.acc, y_rows)
+        _update_Eyyt_in_place(self.acc, rows if self.input_side else y_rows)
         y = y_rows.reshape(*x.shape[:-1], self.out_features)
         if self.bias is not None:
             y = y + self.bias
@@ -107,7 +113,16 @@ class CovarianceComputingLinearModule(torch.nn.Module):
     def get_eigenvectors(self, num_vectors: Optional[int] = None, group=None) -> torch.Tensor:
         """Unlike D:206-208 the result stays on the GPU in fp32 (180 GB of HBM make the reference's
         round trip through host memory unnecessary); the rank search casts what it slices."""
+        if self.input_side:
+            return _get_eigenvectors_input_side(self.acc, self.weight.detach(), num_vectors, group)
         return _get_eigenvectors(self.acc, num_vectors, group)
+
+
+def _get_eigenvectors_input_side(acc: linalg.CovarianceAccumulator, weight: torch.Tensor,
+                                 num_vectors: int, group=None) -> torch.Tensor:
+    parallel.allreduce_accumulator(acc, group)
+    s_cov = acc.finalize(use_mean=False, damp_factor=0.0)
+    return linalg.eigvecs_from_input_covariance(s_cov, weight, num_vectors)
 
 
 def _compute_covariance_matrix_decomposition(
@@ -127,17 +142,24 @@ def _compute_covariance_matrix_decomposition(
     assert isinstance(wrapper, WrappedDWAINModule)
     logger.info("Using float64 for decomposition" if decompose_in_float64
                 else "Using float32 for decomposition")
+    input_side = linalg.use_input_side(weight.shape[1], weight.shape[0], num_vectors)
+    d = weight.shape[1] if input_side else weight.shape[0]
     acc = linalg.CovarianceAccumulator(
-        weight.shape[0], device, defer_rows=linalg.default_defer_rows(weight.shape[0], weight.element_size()))
-    wrapper.capture_output = True
+        d, device, defer_rows=linalg.default_defer_rows(d, weight.element_size()))
+    wrapper.capture_output = not input_side
     try:
         for _ in range(num_data_steps):
             inputs = utils.to_device(next(data_iterator), device)
             _ = root_module(inputs)
-            _update_Eyyt_in_place(acc, wrapper.get_last_output_rows(), sub=wrapper.get_bias())
+            if input_side:
+                _update_Eyyt_in_place(acc, wrapper.get_last_input())
+            else:
+                _update_Eyyt_in_place(acc, wrapper.get_last_output_rows(), sub=wrapper.get_bias())
     finally:
         wrapper.capture_output = False
         wrapper.output = None
+    if input_side:
+        return _get_eigenvectors_input_side(acc, weight, num_vectors)
     return _get_eigenvectors(acc, num_vectors)
 
 
@@ -372,7 +394,8 @@ def _add_meta_to_module_config(module_config: dict[str, Any], module_deco_result
 
 
 def _install_covariance_modules(module: torch.nn.Module, submodule_names: list[str],
-                                decompose_in_float64: bool) -> dict[str, torch.nn.Module]:
+                                decompose_in_float64: bool,
+                                reduction_factor: Optional[float] = None) -> dict[str, torch.nn.Module]:
     """D:592-603: swap every listed Linear for a CovarianceComputingLinearModule that shares its
     weight and bias. Returns the originals for _restore_modules."""
     originals: dict[str, torch.nn.Module] = {}
@@ -383,8 +406,10 @@ def _install_covariance_modules(module: torch.nn.Module, submodule_names: list[s
             raise ValueError(f"covariance precompute supports Linear targets only, got {name}={old}")
         originals[name] = old
         logger.info(f"Replacing {name} by covariance computing wrapper")
+        k = (None if reduction_factor is None
+             else _max_rank_consumed(old.in_features, old.out_features, reduction_factor))
         utils.replace_submodule_in_place(
-            module, name, CovarianceComputingLinearModule(old.weight, old.bias, decompose_in_float64))
+            module, name, CovarianceComputingLinearModule(old.weight, old.bias, decompose_in_float64, k))
     return originals
 
 
@@ -411,7 +436,8 @@ def _precompute_covariance_matrix_decompositions(
     rank still draws all num_data_steps batches, so iterator positions stay those of the
     reference -- partial covariances are summed over NVLink, and the eigensolves are distributed
     round-robin with the owners broadcasting their top-k blocks."""
-    originals = _install_covariance_modules(module, submodule_names, decompose_in_float64)
+    originals = _install_covariance_modules(module, submodule_names, decompose_in_float64,
+                                            reduction_factor)
 
     module.eval()
     rank, world = parallel.rank_and_world(group)

@@ -84,22 +84,32 @@ def _compute_decompositon_of_covariance_matrix(
     root_module.eval()
     wrapper = root_module.get_submodule(decomposed_submodule_name)
     assert isinstance(wrapper, WrappedFALORModule)
-    n_out = weight.shape[0]
-    acc = linalg.CovarianceAccumulator(n_out, device, with_mean=use_mean,
-                                       defer_rows=linalg.default_defer_rows(n_out, weight.element_size()))
-    wrapper.capture_output = True
+    n_out, n_in = weight.shape
+    input_side = linalg.use_input_side(n_in, n_out, num_vectors)
+    d = n_in if input_side else n_out
+    acc = linalg.CovarianceAccumulator(d, device, with_mean=use_mean,
+                                       defer_rows=linalg.default_defer_rows(d, weight.element_size()))
+    wrapper.capture_output = not input_side
     try:
         for _ in range(num_data_steps):
             inputs = next(data_iterator).to(device)
             _ = root_module(inputs)
-            _accumulate_Ey_and_Eyyt(acc, wrapper)
+            if input_side:  # C = W S W^T: accumulate S = E[x x^T] (and E[x]) instead of C
+                acc.update(wrapper.get_last_input())
+            else:
+                _accumulate_Ey_and_Eyyt(acc, wrapper)
     finally:
         wrapper.capture_output = False
         wrapper.output = None
     logger.info("Using mean for covariance" if use_mean else "Not using mean for covariance")
-    damp = EIGEN_DAMPEN_FACTOR if (use_damping and not use_mean) else 0.0
     if use_damping:
         logger.info("Using damping")
+    if input_side:
+        # centring carries over (E[y] = W E[x]); damping is a multiple of I on C and moves no
+        # eigenvector, so it has no input-side counterpart
+        s_cov = acc.finalize(use_mean=use_mean, damp_factor=0.0)
+        return linalg.eigvecs_from_input_covariance(s_cov, weight, num_vectors)
+    damp = EIGEN_DAMPEN_FACTOR if (use_damping and not use_mean) else 0.0
     cov = acc.finalize(use_mean=use_mean, damp_factor=damp)
     _, u = linalg.eigh(cov, k=num_vectors)
     return u

@@ -152,6 +152,43 @@ def eigh(cov: torch.Tensor, k: Optional[int] = None) -> tuple[torch.Tensor, torc
     return evals, (U if ldu == k else U[:, :k])
 
 
+def use_input_side(in_features: int, out_features: int, num_vectors: Optional[int]) -> bool:
+    """Whether the layer's covariance is accumulated on the INPUT side (see
+    eigvecs_from_input_covariance): only when that is the smaller problem and the wanted
+    eigenvectors all lie in range(W). PTDECO_B200_INPUT_SIDE=0 forces the reference formulation."""
+    if os.environ.get("PTDECO_B200_INPUT_SIDE", "1") == "0":
+        return False
+    return (in_features < out_features and num_vectors is not None
+            and 1 <= num_vectors <= in_features)
+
+
+def eigvecs_from_input_covariance(S: torch.Tensor, weight: torch.Tensor, k: int) -> torch.Tensor:
+    """Top-k eigenvectors (ascending, [out, k]) of the OUTPUT covariance C = W S W^T computed from
+    the input covariance S = E[x x^T] ([in, in], finalized) when in < out.
+
+    The reference accumulates C directly (F:159-160, D:194-200); with y = x W^T one has
+    C = W S W^T of rank <= in, and its nonzero eigenpairs follow from an in x in problem
+    (SURVEY.md fact 1): S = Vs L Vs^T, B = W Vs L^(1/2) ([out, in]) gives C = B B^T; the
+    eigenvectors of B^T B = Vg Lg Vg^T map to those of C as U = B Vg Lg^(-1/2). For Llama gate/up
+    (14336 x 4096) that is two 4096-eigensolves and three tensor-core GEMMs instead of one
+    14336-eigensolve, and a 12x smaller accumulator. The reference's damping (a multiple of I on
+    C) moves no eigenvector and is not needed here."""
+    out_f, in_f = weight.shape
+    if S.shape != (in_f, in_f) or not 1 <= k <= in_f:
+        raise ValueError(f"S{tuple(S.shape)} / W{tuple(weight.shape)} / k={k} do not fit")
+    ev_s, vs = eigh(S)
+    scale = ev_s.clamp_min(0.0).sqrt()
+    w32 = weight if weight.dtype == torch.float32 else weight.float()
+    b = gemm(w32, False, vs * scale, True, out_f, in_f, in_f)             # B = W Vs L^(1/2)
+    acc = CovarianceAccumulator(in_f, S.device)
+    acc._syrk(b, None, 1.0)                                                 # B^T B (lower) ...
+    acc.steps = 1
+    g = acc.finalize(use_mean=False, damp_factor=0.0)                       # ... mirrored
+    _, vg = eigh(g, k=k)
+    u = gemm(b, False, vg.contiguous(), True, out_f, k, in_f)               # B Vg
+    return u / torch.linalg.vector_norm(u, dim=0, keepdim=True).clamp_min(1e-30)
+
+
 def gemm(a: torch.Tensor, a_mn_major: bool, b: torch.Tensor, b_mn_major: bool, m: int, n: int, k: int,
          out_dtype: torch.dtype = torch.float32, alpha: float = 1.0,
          bias: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -193,6 +193,28 @@ def test_eigh_input_not_modified_and_uplo(dev):
     assert np.abs(ev.cpu().numpy() - ref).max() / np.abs(ref).max() < EVAL_TOL
 
 
+@pytest.mark.parametrize("in_f,out_f,k", [(48, 96, 47), (64, 176, 32), (192, 768, 96), (256, 1024, 128)])
+def test_input_side_eigenvectors_match_output_side(dev, in_f, out_f, k):
+    """C = W S W^T: the in x in route (linalg.eigvecs_from_input_covariance) spans the same top-k
+    subspace as the eigensolve of the out x out covariance the reference accumulates."""
+    from ptdeco_b200 import linalg
+    g = torch.Generator().manual_seed(in_f + out_f)
+    w = torch.randn(out_f, in_f, generator=g) / in_f ** 0.5
+    x = torch.randn(6 * in_f, in_f, generator=g) * torch.logspace(0, -1.5, in_f)
+    y = x @ w.T
+    acc_s = linalg.CovarianceAccumulator(in_f, dev)
+    acc_s.update(x.to(dev))
+    u_in = linalg.eigvecs_from_input_covariance(acc_s.finalize(False, 0.0), w.to(dev), k)
+    c = (y.double().T @ y.double() / y.shape[0]).numpy()
+    c += 0.01 * np.mean(np.diag(c)) * np.eye(out_f)
+    u_ref = P.eigenvectors_ascending(c)
+    u_in = u_in.double().cpu().numpy()
+    assert u_in.shape == (out_f, k)
+    assert np.abs(u_in.T @ u_in - np.eye(k)).max() < 2e-5
+    for kk in sorted({k, max(1, k // 2), max(1, k // 4)}):
+        assert P.min_principal_cosine(P.top_k(u_ref, kk), u_in[:, k - kk:]) >= COS_TOL
+
+
 # ------------------------------------------------------------------------------------ K4 / K5 / K7
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("out_f,in_f,k", [(32, 64, 32), (96, 48, 13), (192, 768, 96), (576, 192, 100)])
