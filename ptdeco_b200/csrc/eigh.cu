@@ -197,7 +197,8 @@ struct PanelArgs {
   float* Wp;      // [d][NB]
   float* colbuf;  // [d] (local row index)
   double* nacc;   // [NB] per-column sum of squares, accumulated with atomics (pre-zeroed)
-  float* gacc;    // [NB][GP_STRIDE] per-column W^T v | V^T v | v^T A v, atomics (pre-zeroed)
+  double* gacc;   // [NB][GP_STRIDE] per-column W^T v | V^T v | v^T A v; fp64 atomics make the sum
+                  // independent of arrival order to ~1e-16, i.e. reproducible after rounding
   float* ptop;    // [NB]
   float* dvec;    // [d]
   float* evec;    // [d]
@@ -408,12 +409,12 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
         if ((tid & (NB - 1)) < i && R > 0) {
           float s = 0.f;
           for (int w = 0; w < PANEL_WARPS; ++w) s += red[w * 2 * NB + tid];
-          atomicAdd(g.gacc + i * GP_STRIDE + tid, s);
+          atomicAdd(g.gacc + i * GP_STRIDE + tid, static_cast<double>(s));
         }
       } else if (tid == 2 * NB && R > 0) {
         double s = 0.0;
         for (int w = 0; w < PANEL_WARPS; ++w) s += sred[w];
-        atomicAdd(g.gacc + i * GP_STRIDE + 2 * NB, static_cast<float>(s));
+        atomicAdd(g.gacc + i * GP_STRIDE + 2 * NB, s);
       }
     }
     PTD_PHASE(3)
@@ -423,10 +424,10 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
     // ---------------------------------------------------------------- P3: w column
     if (tau != 0.f) {
       if (tid <= 2 * NB) {
-        const float s = __ldcg(g.gacc + i * GP_STRIDE + tid);
-        if (tid < NB) gWs[tid] = s;
-        else if (tid < 2 * NB) gVs[tid - NB] = s;
-        else s_scal[1] = static_cast<double>(s);
+        const double s = __ldcg(g.gacc + i * GP_STRIDE + tid);
+        if (tid < NB) gWs[tid] = static_cast<float>(s);
+        else if (tid < 2 * NB) gVs[tid - NB] = static_cast<float>(s);
+        else s_scal[1] = s;
       } else if (tid >= 256 && tid < 256 + NB) {  // one parallel fetch of the top rows' symv results
         const int r = tid - 256;
         pts[r] = (r > i && r < m) ? __ldcg(g.ptop + r) : 0.f;
@@ -947,8 +948,8 @@ struct Carver {
 struct Plan {
   float* Aw; long long ldA;
   __nv_bfloat16* Vs; long long ldv;
-  float *Vp, *Wp, *colbuf, *gacc, *ptop, *dvec, *evec, *taus, *Tmats, *X1;
-  double* nacc;
+  float *Vp, *Wp, *colbuf, *ptop, *dvec, *evec, *taus, *Tmats, *X1;
+  double *nacc, *gacc;
   unsigned* bars;
   __nv_bfloat16 *VW, *WV, *Zs, *Xs;
   TriBufs tb;
@@ -982,7 +983,7 @@ Plan make_plan(void* ws, int d, int k) {
   p.colbuf = cv.take<float>(D);
   // per-panel accumulators for the cross-CTA reductions, zeroed once for all panels
   p.nacc = cv.take<double>(static_cast<size_t>(p.npanels) * NB);
-  p.gacc = cv.take<float>(static_cast<size_t>(p.npanels) * NB * GP_STRIDE);
+  p.gacc = cv.take<double>(static_cast<size_t>(p.npanels) * NB * GP_STRIDE);
   p.ptop = cv.take<float>(NB);
   p.dvec = cv.take<float>(D);
   p.evec = cv.take<float>(D);
@@ -1075,7 +1076,7 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
   cudaMemsetAsync(p.Tmats, 0, static_cast<size_t>(p.npanels) * NB * NB * sizeof(float), st);
   cudaMemsetAsync(p.bars, 0, static_cast<size_t>(p.npanels) * sizeof(unsigned), st);
   cudaMemsetAsync(p.nacc, 0, static_cast<size_t>(p.npanels) * NB * sizeof(double), st);
-  cudaMemsetAsync(p.gacc, 0, static_cast<size_t>(p.npanels) * NB * GP_STRIDE * sizeof(float), st);
+  cudaMemsetAsync(p.gacc, 0, static_cast<size_t>(p.npanels) * NB * GP_STRIDE * sizeof(double), st);
   cudaMemsetAsync(p.Vp, 0, static_cast<size_t>(d) * NB * sizeof(float), st);
   cudaMemsetAsync(p.Wp, 0, static_cast<size_t>(d) * NB * sizeof(float), st);
   cudaMemsetAsync(p.evec, 0, static_cast<size_t>(d) * sizeof(float), st);

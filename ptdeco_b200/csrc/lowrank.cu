@@ -89,7 +89,7 @@ struct FusedArgs {
   long long ldy;
   const float* bias;
   int tma_store;  // 1: Y tiles leave through shared memory + cp.async.bulk.tensor stores
-  int stages, slot_bytes, w2_off, stg_separate;
+  int stages, slot_bytes, w2_off, stg_separate, rotate;
 };
 
 __global__ void __launch_bounds__(F_THREADS, 1)
@@ -122,8 +122,8 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   // same L2 lines at the same time. Each CTA therefore starts at its own offset of the k loop
   // (a sum: order-free) and of its tile list.
   const int ntl = t1 - t0;
-  const int rot1 = static_cast<int>((blockIdx.x * 7u) % static_cast<unsigned>(kb1));
-  const int rot3 = ntl > 0 ? static_cast<int>(rt % static_cast<unsigned>(ntl)) : 0;
+  const int rot1 = g.rotate ? static_cast<int>((blockIdx.x * 7u) % static_cast<unsigned>(kb1)) : 0;
+  const int rot3 = (g.rotate && ntl > 0) ? static_cast<int>(rt % static_cast<unsigned>(ntl)) : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -399,6 +399,8 @@ int launch_fused(const void* X, long long ldx, const void* W1, long long ldw1, c
   } else {
     g.stages = 3; g.slot_bytes = 49152; g.w2_off = F_XBYTES; g.stg_separate = 0;
   }
+  g.rotate = 1;
+  if (const char* e = std::getenv("PTDECO_B200_FUSED_ROT")) g.rotate = atoi(e);
   if (const char* e = std::getenv("PTDECO_B200_FUSED_STAGES")) {  // experiment knob
     const int v = atoi(e);
     if (v >= 2 && v <= g.stages) g.stages = v;

@@ -155,11 +155,14 @@ def eigh(cov: torch.Tensor, k: Optional[int] = None) -> tuple[torch.Tensor, torc
 def use_input_side(in_features: int, out_features: int, num_vectors: Optional[int]) -> bool:
     """Whether the layer's covariance is accumulated on the INPUT side (see
     eigvecs_from_input_covariance): only when that is the smaller problem and the wanted
-    eigenvectors all lie in range(W). PTDECO_B200_INPUT_SIDE=0 forces the reference formulation."""
+    eigenvectors are at most the leading half of range(W) (dwain's default descent; falor's
+    bisection may ask for rank min(in,out)-1 and stays on the reference formulation). PTDECO_B200_INPUT_SIDE=0 forces the reference formulation."""
     if os.environ.get("PTDECO_B200_INPUT_SIDE", "1") == "0":
         return False
+    # eigenvectors come back as B v / sqrt(lambda): errors grow like sqrt(lambda_max / lambda), so
+    # the route is taken only when the wanted ones are the leading half of the spectrum
     return (in_features < out_features and num_vectors is not None
-            and 1 <= num_vectors <= in_features)
+            and 1 <= 2 * num_vectors <= in_features)
 
 
 def eigvecs_from_input_covariance(S: torch.Tensor, weight: torch.Tensor, k: int) -> torch.Tensor:
