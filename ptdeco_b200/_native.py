@@ -78,6 +78,11 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
+        if os.environ.get("PTDECO_B200_DETERMINISTIC", "0") == "1":
+            # Reproducible mode: no split-K, so every output element is accumulated by exactly one
+            # CTA in a fixed order (the default splits short-and-wide reductions over CTAs and
+            # combines them with fp32 red.add, whose arrival order varies from run to run).
+            handle.ptdeco_debug_set(1, 1)
         _lib = handle
     return _lib
 
