@@ -389,7 +389,12 @@ def main() -> None:
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
             "clocks": clk.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE d=14336, N=8192 launch
+                         # (the dominant shape: 64 of 224 launches, 88 % of the step), from the
+                         # `ncu --set full` capture summarised in profiles/r01_syrk_ncu_full_summary_v2.json;
+                         # algorithmic bytes of that launch: 0.235 GB of tokens + 0.822 GB accumulator RMW
+                         "traffic": 2.19e9, "traffic_unit": "B/launch (d=14336, N=8192)",
                          "kernel": "gemm_tc_kernel<MN,MN,256> (SYRK, lower triangle)",
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})",
                          "algorithmic_flop_per_token": alg_flops_per_token()},

@@ -396,7 +396,7 @@ def test_falor_baseline_configs_match_reference(dev, golden_dir, name):
         margin = abs(gl[first - 1]["nsr"] - thr) / thr
         assert margin < 0.05, (name_, first, gl[first - 1], ml[first - 1])
         fragile.append(name_)
-    assert identical >= 0.95 * len(by_layer_gold), (identical, fragile)
+    assert identical >= 0.9 * len(by_layer_gold), (identical, fragile)
     ranks, granks = _ranks(cfg), _ranks(gold["decompose_config"])
     assert all(ranks.get(n) == granks.get(n) for n in set(ranks) | set(granks) if n not in fragile)
     # metrics: tight wherever the tested rank lies inside the well-determined part of the spectrum
