@@ -344,6 +344,270 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   }
 }
 
+// ------------------------------------------------------------------------------ persistent kernel
+// Large-N variant (token tiles >= SMs, k <= 128). One CTA per SM walks over its token tiles and
+// OVERLAPS the two phases of consecutive tiles: while the epilogue warps stream the Y tiles of
+// token tile j to HBM (store-bound), the producer and the tensor core already accumulate
+// H = X W1^T of token tile j+1 (load-bound), so HBM reads and writes are in flight together
+// instead of all SMs reading, then all SMs writing. Producer and MMA issuer follow the same
+// static op schedule:  K1(0,*) | for j: lead K1(j+1,*) , { T(j,t) , a share of K1(j+1,*) }_t
+//   TMEM   H accumulators double-buffered [0,128) [128,256); Y accumulator [256,512)
+//   smem   4 slots x 32 KB ([X 16|W1 16] or one 32 KB W2 k-block) | Hs 32 KB | staging 64 KB
+constexpr int P_STAGES = 4;
+constexpr int P_SLOT = 32768;
+constexpr int P_LEAD = 8;
+constexpr int P_SMEM = P_STAGES * P_SLOT + 2 * F_HBLOCK + F_STG_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(F_THREADS, 1)
+lowrank_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                          const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmY,
+                          const FusedArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* hbuf = smem + P_STAGES * P_SLOT;
+  uint8_t* stg_base = hbuf + 2 * F_HBLOCK;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + F_STG_BYTES);
+  uint64_t* full = bars;                 // [P_STAGES]
+  uint64_t* empty = bars + P_STAGES;     // [P_STAGES]
+  uint64_t* h_full = bars + 2 * P_STAGES;  // [2] GEMM 1 of a token tile complete (per H buffer)
+  uint64_t* h_ready = h_full + 2;        // Hs holds the bf16 tile
+  uint64_t* hs_free = h_ready + 1;       // GEMM 2 of the token tile finished reading Hs
+  uint64_t* y_full = hs_free + 1;
+  uint64_t* y_empty = y_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_tiles = (g.n + F_TILE_M - 1) / F_TILE_M;
+  const int J = (row_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                static_cast<int>(gridDim.x);  // token tiles of this CTA: blockIdx.x + j * gridDim.x
+  const int kb1 = (g.in_f + F_BK - 1) / F_BK;
+  const int kb2 = g.kp / F_BK;
+  const int ntiles = g.out_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmY);
+    for (int s = 0; s < P_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(&h_full[0], 1);
+    mbar_init(&h_full[1], 1);
+    mbar_init(h_ready, F_EPI_WARPS);
+    mbar_init(hs_free, 1);
+    mbar_init(y_full, 1);
+    mbar_init(y_empty, F_EPI_WARPS);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t y_tmem = tmem_base + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto load_k1 = [&](int j, int kb) {
+        const int m0 = (static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x)) * F_TILE_M;
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* slot = smem + stage * P_SLOT;
+        mbar_expect_tx(&full[stage], F_XBYTES + g.kp * 128);
+        tma_load_3d(slot, &tmX, &full[stage], kb * F_BK, m0, 0);
+        tma_load_3d(slot + F_XBYTES, &tmW1, &full[stage], kb * F_BK, 0, 0);
+        if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+      };
+      auto load_tile = [&](int t) {
+        for (int kb = 0; kb < kb2; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], F_WBYTES);
+          tma_load_3d(smem + stage * P_SLOT, &tmW2, &full[stage], kb * F_BK, t * F_TILE_N, 0);
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+        }
+      };
+      for (int kb = 0; kb < kb1; ++kb) load_k1(0, kb);
+      for (int j = 0; j < J; ++j) {
+        const bool has_next = j + 1 < J;
+        int kk = 0;
+        if (has_next)
+          for (; kk < min(kb1, P_LEAD); ++kk) load_k1(j + 1, kk);
+        for (int t = 0; t < ntiles; ++t) {
+          load_tile(t);
+          if (has_next) {
+            const int quota = (kb1 - kk + (ntiles - t) - 1) / (ntiles - t);
+            for (int q = 0; q < quota; ++q) load_k1(j + 1, kk++);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc1 = umma_idesc_bf16(F_TILE_M, g.kp, 0, 0);
+      const uint32_t idesc2 = umma_idesc_bf16(F_TILE_M, F_TILE_N, 0, 0);
+      const uint32_t sH = smem_u32(hbuf);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t ytile = 0;  // running count of Y tiles (parity of y_full / y_empty)
+      auto mma_k1 = [&](int j, int kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + stage * P_SLOT);
+        const uint32_t sB = sA + F_XBYTES;
+        const uint32_t d_tmem = tmem_base + (j & 1) * 128;
+#pragma unroll
+        for (int ks = 0; ks < F_BK / 16; ++ks)
+          umma_bf16(d_tmem, umma_smem_desc_sw128(sA + ks * 32, 16, 1024),
+                    umma_smem_desc_sw128(sB + ks * 32, 16, 1024), idesc1, (kb > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(&empty[stage]);
+        if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+        if (kb == kb1 - 1) umma_commit(&h_full[j & 1]);
+      };
+      auto mma_tile = [&](int j, int t) {
+        if (t == 0) {
+          mbar_wait(h_ready, j & 1);  // Hs holds token tile j
+          tc_fence_after();
+        }
+        mbar_wait(y_empty, (ytile & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < kb2; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sB = smem_u32(smem + stage * P_SLOT);
+          const uint32_t sA = sH + kb * F_HBLOCK;
+#pragma unroll
+          for (int ks = 0; ks < F_BK / 16; ++ks)
+            umma_bf16(y_tmem, umma_smem_desc_sw128(sA + ks * 32, 16, 1024),
+                      umma_smem_desc_sw128(sB + ks * 32, 16, 1024), idesc2, (kb > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(y_full);
+        ++ytile;
+        if (t == ntiles - 1) umma_commit(hs_free);
+      };
+      for (int kb = 0; kb < kb1; ++kb) mma_k1(0, kb);
+      for (int j = 0; j < J; ++j) {
+        const bool has_next = j + 1 < J;
+        int kk = 0;
+        if (has_next)
+          for (; kk < min(kb1, P_LEAD); ++kk) mma_k1(j + 1, kk);
+        for (int t = 0; t < ntiles; ++t) {
+          mma_tile(j, t);
+          if (has_next) {
+            const int quota = (kb1 - kk + (ntiles - t) - 1) / (ntiles - t);
+            for (int q = 0; q < quota; ++q) mma_k1(j + 1, kk++);
+          }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int cg = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
+    const bool bias_vec = (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0;
+    uint8_t* stg = stg_base + (warp - 2) * 4096;
+    uint32_t ytile = 0;
+    for (int j = 0; j < J; ++j) {
+      const int m0 = (static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x)) * F_TILE_M;
+      // ---- drain H of token tile j into Hs (bf16, 128B-swizzled K-major tile)
+      mbar_wait(&h_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      if (j > 0) mbar_wait(hs_free, (j - 1) & 1);  // GEMM 2 of tile j-1 no longer reads Hs
+      for (int col0 = cg * 32; col0 < g.kp; col0 += 4 * 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (j & 1) * 128 + col0 + lane_bits, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = __float2bfloat16_rn(__uint_as_float(r[8 * jj + e]));
+          const int col = col0 + 8 * jj;
+          const int chunk = (col & 63) >> 3;
+          uint8_t* dst = hbuf + (col >> 6) * F_HBLOCK + row * 128 + ((chunk ^ (row & 7)) << 4);
+          *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(h_ready);
+      // ---- Y tiles of token tile j
+      for (int t = 0; t < ntiles; ++t) {
+        mbar_wait(y_full, ytile & 1);
+        tc_fence_after();
+        ++ytile;
+        const int n0 = t * F_TILE_N + cg * 64;
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(y_tmem + cg * 64 + lane_bits, ra);
+        tmem_ld_32x32(y_tmem + cg * 64 + 32 + lane_bits, rb);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(y_empty);
+        if (g.bias != nullptr) {
+          if (bias_vec && n0 + 64 <= g.out_f) {
+            const float4* b4 = reinterpret_cast<const float4*>(g.bias + n0);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float4 lo = __ldg(b4 + e), hi = __ldg(b4 + 8 + e);
+              ra[4 * e + 0] = __float_as_uint(__uint_as_float(ra[4 * e + 0]) + lo.x);
+              ra[4 * e + 1] = __float_as_uint(__uint_as_float(ra[4 * e + 1]) + lo.y);
+              ra[4 * e + 2] = __float_as_uint(__uint_as_float(ra[4 * e + 2]) + lo.z);
+              ra[4 * e + 3] = __float_as_uint(__uint_as_float(ra[4 * e + 3]) + lo.w);
+              rb[4 * e + 0] = __float_as_uint(__uint_as_float(rb[4 * e + 0]) + hi.x);
+              rb[4 * e + 1] = __float_as_uint(__uint_as_float(rb[4 * e + 1]) + hi.y);
+              rb[4 * e + 2] = __float_as_uint(__uint_as_float(rb[4 * e + 2]) + hi.z);
+              rb[4 * e + 3] = __float_as_uint(__uint_as_float(rb[4 * e + 3]) + hi.w);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              if (n0 + e < g.out_f) ra[e] = __float_as_uint(__uint_as_float(ra[e]) + __ldg(g.bias + n0 + e));
+              if (n0 + 32 + e < g.out_f)
+                rb[e] = __float_as_uint(__uint_as_float(rb[e]) + __ldg(g.bias + n0 + 32 + e));
+            }
+          }
+        }
+        if (lane == 0) bulk_wait_read_all();
+        __syncwarp();
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            o[e] = __float2bfloat16_rn(__uint_as_float(jj < 4 ? ra[8 * jj + e] : rb[8 * (jj - 4) + e]));
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((jj ^ (lane & 7)) << 4)) =
+              *reinterpret_cast<const uint4*>(o);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && n0 < g.out_f && m0 + q * 32 < g.n) {
+          tma_store_3d(&tmY, stg, n0, m0 + q * 32, 0);
+          bulk_commit();
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_read_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 bool fused_eligible(const void* X, long long ldx, const void* W1, long long ldw1, const void* W2,
                     long long ldw2, int is_bf16, int k) {
   return is_bf16 && k <= 256 && aligned16(X) && aligned16(W1) && aligned16(W2) && (ldx % 8) == 0 &&
@@ -385,6 +649,8 @@ int launch_fused(const void* X, long long ldx, const void* W1, long long ldw1, c
   }
   CUtensorMap tx, tw1, tw2, ty;
   int rc;
+  const bool persistent = g.kp <= 128 && row_tiles >= sms && aligned16(Y) && (ldy % 8) == 0 &&
+                          std::getenv("PTDECO_B200_NO_PERSISTENT") == nullptr;
   g.tma_store = (aligned16(Y) && (ldy % 8) == 0 && std::getenv("PTDECO_B200_NO_TMA_STORE") == nullptr) ? 1 : 0;
   if (g.tma_store) {
     if ((rc = make_tma_2d_bf16(&ty, Y, out_f, n, ldy, 32))) return rc;
@@ -413,6 +679,19 @@ int launch_fused(const void* X, long long ldx, const void* W1, long long ldw1, c
                              227 * 1024) != cudaSuccess)
       return -12;
     attr = true;
+  }
+  if (persistent) {
+    static bool pattr = false;
+    if (!pattr) {
+      if (cudaFuncSetAttribute(lowrank_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               227 * 1024) != cudaSuccess)
+        return -12;
+      pattr = true;
+    }
+    g.groups = 1;
+    g.tiles_per_group = g.out_tiles;
+    lowrank_persistent_kernel<<<sms, F_THREADS, P_SMEM, st>>>(tx, tw1, tw2, ty, g);
+    return cudaGetLastError() == cudaSuccess ? 0 : -5;
   }
   const long long grid = static_cast<long long>(row_tiles) * g.groups;
   if (grid > 0x7fffffffLL) return -22;

@@ -67,6 +67,31 @@ def _lowrank_vectors(index: int, bs: int, dim: int, latent: int, noise: float) -
     return 3.0 * z @ basis + noise * torch.randn(bs, dim, generator=g)
 
 
+class EdgeNet(nn.Module):
+    """Edge cases of target selection in one small net: a rank-1 Linear (skipped, F:309-317), a
+    1x1 conv, a grouped 1x1 conv and a 3x3 conv (not targets), a blacklisted Linear, a layer whose
+    decomposition cannot reduce parameters, and a head."""
+
+    def __init__(self, seed=MODEL_SEED):
+        super().__init__()
+        self.stem = nn.Conv2d(3, 12, kernel_size=3, padding=1)
+        self.pw = nn.Conv2d(12, 20, kernel_size=1)
+        self.grouped = nn.Conv2d(20, 20, kernel_size=1, groups=4)
+        self.gate = nn.Linear(20, 1)
+        self.wide = nn.Linear(20, 36)
+        self.keep = nn.Linear(36, 36)
+        self.tiny = nn.Linear(36, 3)
+        self.head = nn.Linear(3, 10)
+        models._seeded_init(self, seed)
+
+    def forward(self, x):
+        h = F.gelu(self.grouped(F.gelu(self.pw(F.gelu(self.stem(x))))))
+        h = h.mean(dim=(2, 3))
+        h = h * torch.sigmoid(self.gate(h))
+        h = F.gelu(self.keep(F.gelu(self.wide(h))))
+        return 30.0 * self.head(self.tiny(h))  # random-init logits are tiny next to NSR epsilon 1e-3
+
+
 FALOR_CASES = ("mlp", "convmlp", "deit_small", "deit_tiny", "convnext_tiny")
 
 
@@ -99,6 +124,12 @@ def falor_case(name: str):
         # and fp64 runs disagree by 20 % in NSR on blocks.0.attn.proj), which makes parity ill-posed.
         kw.update(nsr_final_threshold=0.05, kl_final_threshold=0.02, num_data_steps=8,
                   num_metric_steps=2, use_float64=True)
+    elif name == "edge":  # not a golden case: compared against the oracle directly
+        model = EdgeNet()
+        stream = IndexedStream(lambda i: streams.lowrank_image_batch(5, i, 16, 3, 8, 40, noise=0.3))
+        kw.update(nsr_final_threshold=0.0005, kl_final_threshold=0.05, num_data_steps=3,
+                  num_metric_steps=2, blacklisted_module_names=["keep", "nonexistent.name"],
+                  proportion_threshold=0.8)
     elif name == "convnext_tiny":
         # BASELINE.json configs[1]: torchvision convnext_tiny (random init, 37 Linear targets; it has
         # no 1x1 convs), synthetic ImageNet-shape batches; layer_scale set to 1 so that the block

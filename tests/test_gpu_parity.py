@@ -236,7 +236,9 @@ def test_factors_match_oracle(dev, dtype, out_f, in_f, k):
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-6), (torch.bfloat16, 2e-2)])
 @pytest.mark.parametrize("n,in_f,k,out_f", [(1, 64, 8, 32), (16, 192, 48, 160), (300, 200, 50, 168),
-                                            (1024, 768, 96, 3072), (2048, 1024, 256, 1024)])
+                                            (1024, 768, 96, 3072), (2048, 1024, 256, 1024),
+                                            # >= 148 token tiles: the persistent phase-overlapped kernel
+                                            (19000, 320, 64, 520), (37999, 256, 128, 768), (18944, 128, 100, 256)])
 def test_lowrank_forward(dev, dtype, tol, n, in_f, k, out_f):
     from ptdeco_b200 import linalg
     g = torch.Generator().manual_seed(n + k)
@@ -362,6 +364,59 @@ def test_falor_decompose_in_place_matches_reference(dev, golden_dir, name):
     xb = next(stream).to(dev)
     with torch.no_grad():
         torch.testing.assert_close(fresh(xb), model(xb))
+
+
+def test_falor_edge_cases_match_oracle(dev):
+    """Rank-1 target, grouped / 3x3 convs, blacklist (incl. a name that does not exist), a layer
+    that cannot reduce parameters, the proportion_threshold gate: product (GPU) vs oracle (CPU)."""
+    import ptdeco_b200.falor as falor
+    from oracle import drivers as OD
+    m_cpu, s_cpu, kw = cases.falor_case("edge")
+    t_cpu = []
+    cfg_cpu = OD.falor_decompose_in_place(module=m_cpu, data_iterator=s_cpu, trace=t_cpu, **kw)
+    m_gpu, s_gpu, kw = cases.falor_case("edge")
+    m_gpu.to(dev)
+    t_gpu = []
+    cfg_gpu = falor.decompose_in_place(module=m_gpu, device=dev, data_iterator=s_gpu, trace=t_gpu, **kw)
+    assert s_gpu.position == s_cpu.position
+    assert [(t["name"], t["rank"], t["accepted"]) for t in t_gpu] == \
+        [(t["name"], t["rank"], t["accepted"]) for t in t_cpu]
+    assert {t["name"] for t in t_gpu} == {"pw", "wide", "tiny", "head"}  # gate: rank 1; keep: blacklisted
+    assert list(cfg_gpu.keys()) == list(cfg_cpu.keys()) and _ranks(cfg_gpu) == _ranks(cfg_cpu)
+    assert json.loads(json.dumps(cfg_gpu))["pw"]["modules"]["0"]["type"] == "Conv2d"
+    assert isinstance(m_gpu.gate, torch.nn.Linear) and isinstance(m_gpu.keep, torch.nn.Linear)
+    for t, o in zip(t_gpu, t_cpu):
+        assert t["nsr"] == pytest.approx(o["nsr"], rel=2e-2, abs=2e-6)
+
+
+def test_dwain_edge_cases_match_oracle(dev):
+    """min_rank above some layers' full rank (no trial runs), a candidate rank that does not reduce
+    parameters (skipped without consuming metric batches), float32 decomposition flag."""
+    import ptdeco_b200.dwain as dwain
+    from oracle import drivers as OD
+    outs = []
+    for side in ("cpu", "gpu"):
+        model, stream, mstream, kw = cases.dwain_case("llama_tiny")
+        kw.update(min_rank=20, decompose_in_float64=False, nsr_final_threshold=0.05,
+                  blacklisted_module_names=["lm_head", "model.layers.0.mlp.up_proj"])
+        trace = []
+        if side == "cpu":
+            cfg = OD.dwain_decompose_in_place(
+                module=model, data_iterator=stream, metric_iterator=mstream,
+                loss_fn=cases.dwain_loss_fn("llama_tiny"), finetune_fn=lambda m, d, n: m, trace=trace, **kw)
+        else:
+            model.to(dev)
+            cfg = dwain.decompose_in_place(
+                module=model, device=dev, data_iterator=stream, metric_iterator=mstream,
+                loss_fn=cases.dwain_loss_fn("llama_tiny"), finetune_fn=lambda m, d, n: m, trace=trace, **kw)
+        outs.append((cfg, trace, stream.position, mstream.position))
+    (c0, t0, p0, q0), (c1, t1, p1, q1) = outs
+    assert (p0, q0) == (p1, q1)
+    assert [(t["name"], t["rank"], t["accepted"]) for t in t0] == [(t["name"], t["rank"], t["accepted"]) for t in t1]
+    assert list(c0.keys()) == list(c1.keys()) and _ranks(c0) == _ranks(c1)
+    assert "model.layers.0.mlp.up_proj" not in c1
+    for n in c1:
+        assert c1[n]["__meta__"]["drop_in_params"] == c0[n]["__meta__"]["drop_in_params"]
 
 
 @pytest.mark.parametrize("name", ["deit_tiny", "convnext_tiny"])

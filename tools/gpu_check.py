@@ -293,6 +293,9 @@ def main():
         rec("lowrank_bf16_ragged", "lowrank", dict(n=333, **{"in": 200, "k": 72, "out": 520}))
         rec("lowrank_bf16_4096_k128_n32768", "lowrank", dict(n=32768, **{"in": 4096, "k": 128, "out": 4096}, time=True))
         rec("lowrank_bf16_4096_k64_n32768", "lowrank", dict(n=32768, **{"in": 4096, "k": 64, "out": 4096}, time=True))
+        rec("lowrank_bf16_4096_k128_n37888", "lowrank", dict(n=37888, **{"in": 4096, "k": 128, "out": 4096}, time=True, bias=False))
+        rec("lowrank_bf16_4096_k128_n75776", "lowrank", dict(n=75776, **{"in": 4096, "k": 128, "out": 4096}, time=True, bias=False))
+        rec("lowrank_bf16_14336_k128_n32768", "lowrank", dict(n=32768, **{"in": 4096, "k": 128, "out": 14336}, time=True, bias=False))
         rec("lowrank_bf16_14336x4096_k256_n8192", "lowrank", dict(n=8192, **{"in": 4096, "k": 256, "out": 14336}, time=True))
         rec("lowrank_bf16_4096_k128_n16", "lowrank", dict(n=16, **{"in": 4096, "k": 128, "out": 4096}, time=True))
     if "falor" in what:
