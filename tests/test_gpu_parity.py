@@ -385,8 +385,11 @@ def test_falor_edge_cases_match_oracle(dev):
     assert list(cfg_gpu.keys()) == list(cfg_cpu.keys()) and _ranks(cfg_gpu) == _ranks(cfg_cpu)
     assert json.loads(json.dumps(cfg_gpu))["pw"]["modules"]["0"]["type"] == "Conv2d"
     assert isinstance(m_gpu.gate, torch.nn.Linear) and isinstance(m_gpu.keep, torch.nn.Linear)
-    for t, o in zip(t_gpu, t_cpu):  # NSR values here are ~1e-4 (differences of nearly equal logits)
-        assert t["nsr"] == pytest.approx(o["nsr"], rel=0.1, abs=2e-5)
+    for t, o in zip(t_gpu, t_cpu):
+        # `tiny` / `head` see an effectively rank-1 input: their second eigenvector comes out of the
+        # degenerate damping-level cluster (eigenvalue spread 1e-9), so only decisions are compared
+        if t["name"] in ("pw", "wide"):
+            assert t["nsr"] == pytest.approx(o["nsr"], rel=2e-2, abs=2e-6)
 
 
 def test_dwain_edge_cases_match_oracle(dev):

@@ -249,3 +249,31 @@ def test_lowrank_sequential_is_a_sequential():
     assert utils.get_module_config(model["a"]) == cfg_before
     assert list(model.state_dict().keys()) == list(before.keys())
     torch.testing.assert_close(model["a"](x), y_before)  # CPU input: the reference's own path
+
+
+def test_capi_argument_errors_return_codes_without_touching_the_gpu():
+    """Error convention of the boundary: negative errno-style codes, no exceptions, validated before
+    any CUDA call (so these run on the CPU-only box)."""
+    from ptdeco_b200 import _native as nat
+    L = nat.lib()
+    buf = ctypes.create_string_buffer(64)  # a non-null dummy pointer; never dereferenced
+    p = ctypes.addressof(buf)
+    EINVAL, ENOMEM = -22, -12
+    assert L.ptdeco_syrk_accumulate(None, nat.F32, 8, 4, 4, None, p, 4, None, 1.0, None, 0, None) == EINVAL
+    assert L.ptdeco_syrk_accumulate(p, 7, 8, 4, 4, None, p, 4, None, 1.0, None, 0, None) == EINVAL  # dtype
+    assert L.ptdeco_syrk_accumulate(p, nat.F32, 8, 4, 2, None, p, 4, None, 1.0, None, 0, None) == EINVAL  # ldy < d
+    assert L.ptdeco_syrk_accumulate(p, nat.F32, 0, 4, 4, None, p, 4, None, 1.0, None, 0, None) == 0  # empty batch
+    assert L.ptdeco_syrk_accumulate(p, nat.F32, 8, 4, 4, None, p, 4, None, 1.0, None, 0, None) == ENOMEM  # no workspace
+    assert L.ptdeco_cov_finalize(None, 4, 4, None, 1, 0, 0.0, None, None) == EINVAL
+    assert L.ptdeco_cov_finalize(p, 4, 4, None, 0, 0, 0.0, None, None) == EINVAL  # n_steps
+    assert L.ptdeco_eigh(p, 200, 200, 0, p, p, 8, None, 0, None) == EINVAL       # k out of range
+    assert L.ptdeco_eigh(p, 200, 100, 10, p, p, 16, None, 0, None) == EINVAL     # lda < d
+    assert L.ptdeco_eigh(p, 200, 200, 10, p, p, 16, None, 0, None) == ENOMEM     # no workspace
+    assert L.ptdeco_gemm(None, 0, 0, 4, p, 0, 0, 4, 4, 4, 4, 1.0, None, p, 0, 4, 0, None, 0, None) == EINVAL
+    assert L.ptdeco_gemm(p, 0, 0, 4, p, 0, 0, 4, 4, 4, 4, 1.0, None, p, nat.BF16, 4, 1, None, 0, None) == EINVAL
+    assert L.ptdeco_lowrank_forward(None, 4, p, 4, p, 4, None, p, 4, nat.BF16, 4, 4, 2, 4, None, 0, None) == EINVAL
+    assert L.ptdeco_lowrank_forward(p, 4, p, 4, p, 4, None, p, 4, 9, 4, 4, 2, 4, None, 0, None) == EINVAL
+    assert L.ptdeco_nsr_metric(p, p, 0, 4, 4, 1e-3, None, 0, p, None) == ENOMEM
+    assert L.ptdeco_kl_metric(None, p, 0, 4, 4, p, None) == EINVAL
+    for code in (EINVAL, ENOMEM, -5, -34, -38, -1003):
+        assert len(L.ptdeco_strerror(code)) > 3
