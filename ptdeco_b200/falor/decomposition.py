@@ -26,7 +26,7 @@ from typing import Any, Optional
 import torch
 
 from .. import _native as nat
-from .. import _wrap, linalg, utils
+from .. import _graphs, _wrap, linalg, utils
 
 EIGEN_DAMPEN_FACTOR = 0.01  # F:22
 
@@ -70,6 +70,7 @@ def _compute_decompositon_of_covariance_matrix(
     use_mean: bool,
     use_damping: bool,
     num_vectors: Optional[int] = None,
+    forward_fn=None,
 ) -> torch.Tensor:
     """F:165-208. Returns eigenvectors in columns, ascending by eigenvalue: all `d` of them like
     torch.linalg.eigh, or only the last `num_vectors` (what the rank search consumes; slicing
@@ -82,6 +83,7 @@ def _compute_decompositon_of_covariance_matrix(
     further effect. The falor damping quirk is kept: damping reaches `cov` only when
     use_mean=False (F:196-205)."""
     root_module.eval()
+    forward_fn = forward_fn or root_module
     wrapper = root_module.get_submodule(decomposed_submodule_name)
     assert isinstance(wrapper, WrappedFALORModule)
     n_out, n_in = weight.shape
@@ -93,7 +95,7 @@ def _compute_decompositon_of_covariance_matrix(
     try:
         for _ in range(num_data_steps):
             inputs = next(data_iterator).to(device)
-            _ = root_module(inputs)
+            _ = forward_fn(inputs)
             if input_side:  # C = W S W^T: accumulate S = E[x x^T] (and E[x]) instead of C
                 acc.update(wrapper.get_last_input())
             else:
@@ -122,15 +124,17 @@ def _compute_metrics(
     decomposed_submodule: torch.nn.Module,
     orig_weight: torch.Tensor,
     deco_weight: torch.Tensor,
+    forward_fn=None,
 ) -> tuple[torch.Tensor, torch.Tensor]:
     """F:211-233: two full forwards (decomposed weight, original weight), NSR over the batch dim
     and symmetric-max KL of the logits; both returned as 0-dim device tensors (no host sync)."""
     assert isinstance(decomposed_submodule, WrappedFALORModule)
     root_module.eval()
+    forward_fn = forward_fn or root_module
     decomposed_submodule.set_weight(deco_weight)
-    y_deco = root_module(x)
+    y_deco = forward_fn(x)
     decomposed_submodule.set_weight(orig_weight)
-    y_orig = root_module(x)
+    y_orig = forward_fn(x)
     nsr_final = utils.calc_per_channel_noise_to_signal_ratio(y=y_orig, x=y_deco, non_channel_dim=(0,))
     kl_final = utils.calc_kl_loss(y_deco, y_orig)
     return nsr_final, kl_final
@@ -194,11 +198,13 @@ def _process_module(
     # The bisection asks for rank_best - rank_width; while every trial is rejected rank_best stays
     # full_rank and the width halves, so any rank up to full_rank - 1 can be requested (F:340-375).
     k_max = max(1, full_rank - 1)
+    root_module.eval()
+    forward_fn = _graphs.GraphedForward(root_module)  # eager warm-up, then CUDA-graph replay
     u = _compute_decompositon_of_covariance_matrix(
         root_module=root_module, decomposed_submodule_name=decomposed_submodule_name,
         data_iterator=data_iterator, weight=orig_weight, num_data_steps=num_data_steps,
         device=device, use_float64=use_float64, use_mean=use_mean, use_damping=use_damping,
-        num_vectors=k_max)
+        num_vectors=k_max, forward_fn=forward_fn)
 
     w32 = orig_weight if orig_weight.dtype == torch.float32 else orig_weight.float()
     w1 = uk = None
@@ -219,7 +225,7 @@ def _process_module(
             x = next(data_iterator).to(device)
             nsr_sample, kl_sample = _compute_metrics(
                 x=x, root_module=root_module, decomposed_submodule=wrapper,
-                orig_weight=orig_weight, deco_weight=deco_weight)
+                orig_weight=orig_weight, deco_weight=deco_weight, forward_fn=forward_fn)
             nsr_acc += nsr_sample.double()
             kl_acc += kl_sample.double()
         nsr_new, kl_new = (torch.stack([nsr_acc, kl_acc]) / num_metric_steps).tolist()  # one sync

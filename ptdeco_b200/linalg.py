@@ -13,6 +13,10 @@ import torch
 from . import _native as nat
 
 
+def _tma_ready(t: torch.Tensor) -> bool:
+    return t.dtype == torch.bfloat16 and (t.data_ptr() & 15) == 0 and (t.stride(0) & 7) == 0
+
+
 def _check_2d(t: torch.Tensor, name: str) -> torch.Tensor:
     nat.require_cuda(t, name)
     if t.dim() != 2:
@@ -64,7 +68,8 @@ class CovarianceAccumulator:
     def _syrk(self, y: torch.Tensor, sub: Optional[torch.Tensor], alpha: float) -> None:
         L = nat.lib()
         n = y.shape[0]
-        need = L.ptdeco_syrk_workspace_bytes(nat.dtype_code(y), n, self.d)
+        need = 0 if (sub is None and _tma_ready(y)) else L.ptdeco_syrk_workspace_bytes(
+            nat.dtype_code(y), n, self.d)
         ws = nat.WORKSPACE.get(y.device, need)
         nat.check(
             L.ptdeco_syrk_accumulate(y.data_ptr(), nat.dtype_code(y), n, self.d, y.stride(0),
@@ -210,7 +215,12 @@ def gemm(a: torch.Tensor, a_mn_major: bool, b: torch.Tensor, b_mn_major: bool, m
     if bias is not None:
         bias = bias.detach().to(device=a.device, dtype=torch.float32).contiguous()
     L = nat.lib()
-    need = L.ptdeco_gemm_workspace_bytes(nat.dtype_code(a), nat.dtype_code(b), m, n, k)
+    # bf16 operands that TMA can read in place need no staging: skip the size query (this call sits
+    # in every wrapped layer's forward during calibration, so host overhead matters)
+    if _tma_ready(a) and _tma_ready(b):
+        need = 0
+    else:
+        need = L.ptdeco_gemm_workspace_bytes(nat.dtype_code(a), nat.dtype_code(b), m, n, k)
     ws = nat.WORKSPACE.get(a.device, need)
     nat.check(
         L.ptdeco_gemm(a.data_ptr(), nat.dtype_code(a), int(a_mn_major), a.stride(0), b.data_ptr(),
