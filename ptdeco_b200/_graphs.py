@@ -18,12 +18,41 @@ import torch
 logger = logging.getLogger("ptdeco.falor.decomposition")
 
 
+class ActivationRecorder:
+    """Forward hooks on the target layers that remember the last input / output tensor of each.
+    In eager mode they see fresh tensors on every call; during graph capture they see the graph's
+    static tensors, which every later replay refills in place -- so ONE captured graph serves the
+    analysis of every layer (the per-layer wrappers only need to know where to look)."""
+
+    def __init__(self, root: torch.nn.Module, names: list[str]):
+        self.inputs: dict[str, torch.Tensor] = {}
+        self.outputs: dict[str, torch.Tensor] = {}
+        self._handles = []
+        for name in names:
+            mod = root.get_submodule(name)
+            self._handles.append(mod.register_forward_hook(self._make_hook(name)))
+
+    def _make_hook(self, name: str):
+        def hook(_mod, inp, out):
+            self.inputs[name] = inp[0]
+            self.outputs[name] = out
+        return hook
+
+    def close(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles.clear()
+        self.inputs.clear()
+        self.outputs.clear()
+
+
 class GraphedForward:
     WARMUP_CALLS = 2
 
-    def __init__(self, module: torch.nn.Module, enabled: bool = True):
+    def __init__(self, module: torch.nn.Module, enabled: bool = True, recorder=None):
         self.module = module
         self.enabled = enabled and os.environ.get("PTDECO_B200_CUDA_GRAPHS", "1") != "0"
+        self.recorder = recorder
         self._entries: dict = {}
         self._calls: dict = {}
         self.replays = 0
@@ -50,11 +79,6 @@ class GraphedForward:
     def _capture(self, x: torch.Tensor, key):
         try:
             static_x = x.clone()
-            side = torch.cuda.Stream(device=x.device)
-            side.wait_stream(torch.cuda.current_stream(x.device))
-            with torch.cuda.stream(side):
-                self.module(static_x)
-            torch.cuda.current_stream(x.device).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 static_y = self.module(static_x)

@@ -96,6 +96,7 @@ def _compute_decompositon_of_covariance_matrix(
         for _ in range(num_data_steps):
             inputs = next(data_iterator).to(device)
             _ = forward_fn(inputs)
+            _sync_wrapper_with_recorder(wrapper, forward_fn)
             if input_side:  # C = W S W^T: accumulate S = E[x x^T] (and E[x]) instead of C
                 acc.update(wrapper.get_last_input())
             else:
@@ -115,6 +116,16 @@ def _compute_decompositon_of_covariance_matrix(
     cov = acc.finalize(use_mean=use_mean, damp_factor=damp)
     _, u = linalg.eigh(cov, k=num_vectors)
     return u
+
+
+def _sync_wrapper_with_recorder(wrapper: WrappedFALORModule, forward_fn) -> None:
+    """When the forward ran as a CUDA-graph replay the wrapper's Python forward did not execute;
+    its last input / output are the static tensors the recorder saw at capture time."""
+    rec = getattr(forward_fn, "recorder", None)
+    name = getattr(wrapper, "name", None)
+    if rec is not None and name in rec.inputs:
+        wrapper.input = rec.inputs[name]
+        wrapper.output = rec.outputs[name]
 
 
 def _compute_metrics(
@@ -173,6 +184,7 @@ def _process_module(
     use_mean: bool,
     use_damping: bool,
     trace: Optional[list] = None,
+    forward_fn=None,
 ) -> dict[str, Any]:
     """F:284-399: covariance -> eigenvectors -> bisection on the rank. `trace` (not in the
     reference) collects one record per trial for the parity harness."""
@@ -199,7 +211,7 @@ def _process_module(
     # full_rank and the width halves, so any rank up to full_rank - 1 can be requested (F:340-375).
     k_max = max(1, full_rank - 1)
     root_module.eval()
-    forward_fn = _graphs.GraphedForward(root_module)  # eager warm-up, then CUDA-graph replay
+    forward_fn = forward_fn or root_module
     u = _compute_decompositon_of_covariance_matrix(
         root_module=root_module, decomposed_submodule_name=decomposed_submodule_name,
         data_iterator=data_iterator, weight=orig_weight, num_data_steps=num_data_steps,
@@ -304,6 +316,14 @@ def decompose_in_place(
 
     names = _get_decomposeable_submodule_names(module)
     n = len(names)
+    # One CUDA graph of the model forward serves every layer: hooks on the targets remember where
+    # the graph keeps each layer's input / output (see _graphs.py). Eager until the third call.
+    module.eval()
+    recorder = _graphs.ActivationRecorder(module, [nm for nm in names if nm not in blacklisted_module_names])
+    forward_fn = _graphs.GraphedForward(module, recorder=recorder)
+    if not forward_fn.enabled:
+        recorder.close()
+        forward_fn.recorder = None
     for i, name in enumerate(names, start=1):
         msg_prefix = f"Processing {name}: module {i} of {n}"
         if name in blacklisted_module_names:
@@ -315,7 +335,10 @@ def decompose_in_place(
                 root_module=module, decomposed_submodule_name=name, data_iterator=data_iterator,
                 nsr_final_threshold=nsr_final_threshold, kl_final_threshold=kl_final_threshold,
                 num_data_steps=num_data_steps, num_metric_steps=num_metric_steps, device=device,
-                use_float64=use_float64, use_mean=use_mean, use_damping=use_damping, trace=trace)
+                use_float64=use_float64, use_mean=use_mean, use_damping=use_damping, trace=trace,
+                forward_fn=forward_fn)
+    recorder.close()
+    del forward_fn
 
     counter: collections.Counter[str] = collections.Counter()
     for name in names:
