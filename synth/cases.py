@@ -154,7 +154,23 @@ def falor_case(name: str):
 
 
 # ------------------------------------------------------------------ dwain cases
-DWAIN_CASES = ("llama_tiny", "llama_tiny_splits")
+class DictInputNet(nn.Module):
+    """dwain's model contract for vision (examples/trainer_vision/dwain_wrapper_module.py): the
+    model takes the batch dict and returns logits; `raw_model` holds the actual network."""
+
+    def __init__(self, raw_model: nn.Module):
+        super().__init__()
+        self.raw_model = raw_model
+
+    def forward(self, d):
+        return self.raw_model(d["inp"])
+
+
+def vision_ce_loss(input_dict, logits):
+    return F.cross_entropy(logits.float(), input_dict["labels"])
+
+
+DWAIN_CASES = ("llama_tiny", "llama_tiny_splits", "convmlp")
 
 
 def dwain_case(name: str):
@@ -162,6 +178,23 @@ def dwain_case(name: str):
     over distinct index ranges so that consumption order of each is observable."""
     if name not in DWAIN_CASES:
         raise KeyError(name)
+    if name == "convmlp":  # 1x1-conv targets through dwain's per-layer path (no precompute)
+        model = DictInputNet(models.ConvMLPNet(dims=(16, 32), depths=(1, 1), expand=4, num_classes=10))
+        model.eval()
+
+        def batch(stream_id):
+            def make(i):
+                g = torch.Generator()
+                g.manual_seed(DATA_SEED + 977 * stream_id + i)
+                return {"inp": streams.lowrank_image_batch(stream_id, i, 8, 3, 32, 24),
+                        "labels": torch.randint(0, 10, (8,), generator=g)}
+            return make
+
+        kw = dict(num_data_steps=4, num_metric_steps=2, blacklisted_module_names=["raw_model.head"],
+                  nsr_final_threshold=3.15e-5, min_rank=4, trade_off_factor=0.5, reduction_factor=0.5,
+                  max_accepted_ppl_diff=0.1, decompose_in_float64=True,
+                  precomputing_covariance_num_splits=None)
+        return model, IndexedStream(batch(6)), IndexedStream(batch(7)), kw
     model = models.LlamaLikeDecoder(vocab=256, hidden=64, inter=176, layers=2, heads=4, kv_heads=2,
                                     theta=10000.0)
     model.eval()
@@ -176,4 +209,4 @@ def dwain_case(name: str):
 
 
 def dwain_loss_fn(name: str):
-    return models.llama_ce_loss
+    return vision_ce_loss if name == "convmlp" else models.llama_ce_loss
