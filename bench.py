@@ -8,7 +8,7 @@ Linears (32 x {q 4096, k 1024, v 1024, o 4096, gate 14336, up 14336, down 4096})
 sharded over GPUs (weak scaling), the only exchange is the final d x d reduction, timed separately.
 
   value   tokens/s with the layer outputs already resident in HBM; batches are staged and folded
-          in 8192 tokens per tcgen05 SYRK launch (the accumulator RMW costs 8 d^2 bytes per
+          in up to 16384 tokens per tcgen05 SYRK launch (the accumulator RMW costs 8 d^2 bytes per
           launch whatever N is); the final flush is inside the timed region
   e2e     tokens/s through the public API path (ptdeco_b200.dwain covariance-computing modules
           installed in a random-init Llama-3-8B-shape model): pinned host token ids -> H2D ->
@@ -53,26 +53,62 @@ def load_peaks() -> tuple[dict, str]:
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clock, power and throttle reasons through NVML every 5 ms while the timed region
+    runs (nvidia-smi as a subprocess returns 2-3 samples per second: too slow for a sub-second
+    region); falls back to nvidia-smi when pynvml is unavailable."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+               ("sw_power_cap", 0x4))
 
     def __init__(self, index: int):
         self.index = index
-        self.rows: list[list[str]] = []
+        self.rows: list[tuple[float, float, int]] = []  # (sm MHz, watts, reason bits)
+        self.max_mhz = None
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
+        self._nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._nv = pynvml
+        except Exception:
+            self._nv = None
+
+    @staticmethod
+    def _physical_index(index: int) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[index])
+            except Exception:
+                return index
+        return index
 
     def _run(self):
+        nv = self._nv
         while not self._stop.is_set():
             try:
+                if nv is not None:
+                    self.rows.append((float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)),
+                                      nv.nvmlDeviceGetPowerUsage(self._h) / 1e3,
+                                      int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))))
+                    self._stop.wait(0.005)
+                    continue
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True,
                                      timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                c = [x.strip() for x in out.split(",")]
+                bits = 0
+                for (name, bit), col in zip(self.REASONS, (3, 5, 4, 6)):
+                    if len(c) > col and c[col].lower().startswith("active"):
+                        bits |= bit
+                self.rows.append((float(c[0]), float(c[2]), bits))
+                self.max_mhz = float(c[1])
             except Exception:
                 pass
             self._stop.wait(0.1)
@@ -86,16 +122,17 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self) -> dict:
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        reasons = set()
+        # samples "under load": board power above half of the maximum seen
+        wmax = max((r[1] for r in self.rows), default=0.0)
+        load = [r for r in self.rows if r[1] >= 0.5 * wmax] or self.rows
+        sm = sorted(r[0] for r in load)
+        bits = 0
         for r in self.rows:
-            for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4),
-                              ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
-                if len(r) > col and r[col].lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+            bits |= r[2]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": [name for name, bit in self.REASONS if bits & bit],
+                "samples": len(self.rows), "watts_max": wmax or None,
+                "source": "nvml" if self._nv is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------ CPU arm
@@ -395,7 +432,7 @@ def main() -> None:
                          # `ncu --set full` capture summarised in profiles/r01_syrk_ncu_full_summary_v2.json;
                          # algorithmic bytes of that launch: 0.235 GB of tokens + 0.822 GB accumulator RMW
                          "traffic": 2.19e9, "traffic_unit": "B/launch (d=14336, N=8192)",
-                         "kernel": "gemm_tc_kernel<MN,MN,256> (SYRK, lower triangle)",
+                         "kernel": "gemm_tc2_kernel<MN,MN> (SYRK, lower triangle, 256x256 tiles on CTA pairs, cta_group::2)",
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})",
                          "algorithmic_flop_per_token": alg_flops_per_token()},
             "gpu_launches": gpu_launches,

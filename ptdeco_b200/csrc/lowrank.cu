@@ -111,7 +111,7 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   uint64_t* y_empty = y_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const int rt = blockIdx.x / g.groups, og = blockIdx.x % g.groups;
   const int m0 = rt * F_TILE_M;
   const int t0 = og * g.tiles_per_group;
@@ -151,73 +151,86 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t h_tmem = tmem_base + 256;  // H accumulates in the upper half; Y tile 0 uses the lower
 
+  // Producer and MMA warps walk their loops converged (uniform control flow); one elected lane
+  // issues, so TMA / tcgen05 instructions stay on the uniform datapath (see gemm_tc.cu).
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kk = 0; kk < kb1; ++kk) {  // GEMM 1 operands
-        const int kb = (kk + rot1) % kb1;
-        mbar_wait(&empty[stage], phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kk = 0; kk < kb1; ++kk) {  // GEMM 1 operands
+      const int kb = (kk + rot1) % kb1;
+      mbar_wait(&empty[stage], phase ^ 1);
+      if (elect_one()) {
         uint8_t* sA = smem + stage * F_STAGE;
         mbar_expect_tx(&full[stage], F_XBYTES + g.kp * 128);
         tma_load_3d(sA, &tmX, &full[stage], kb * F_BK, m0, 0);
         tma_load_3d(sA + F_XBYTES, &tmW1, &full[stage], kb * F_BK, 0, 0);
-        if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
       }
-      for (int tt = 0; tt < ntl; ++tt) {  // GEMM 2: W2 tiles
-        const int t = t0 + (tt + rot3) % ntl;
-        for (int kb = 0; kb < kb2; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+      __syncwarp();
+      if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+    }
+    for (int tt = 0; tt < ntl; ++tt) {  // GEMM 2: W2 tiles
+      const int t = t0 + (tt + rot3) % ntl;
+      for (int kb = 0; kb < kb2; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sB = smem + stage * F_STAGE + g.w2_off;
           mbar_expect_tx(&full[stage], F_WBYTES);
           tma_load_3d(sB, &tmW2, &full[stage], kb * F_BK, t * F_TILE_N, 0);
-          if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc1 = umma_idesc_bf16(F_TILE_M, g.kp, 0, 0);
-      const uint32_t idesc2 = umma_idesc_bf16(F_TILE_M, F_TILE_N, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < kb1; ++kb) {
+    const uint32_t idesc1 = umma_idesc_bf16(F_TILE_M, g.kp, 0, 0);
+    const uint32_t idesc2 = umma_idesc_bf16(F_TILE_M, F_TILE_N, 0, 0);
+    const uint64_t desc0 = umma_smem_desc_sw128(0, 16, 1024);  // + (address >> 4) in the low word
+    const uint32_t smem_base = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < kb1; ++kb) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sA = smem_base + stage * F_STAGE;
+        const uint64_t ad = desc0 + (sA >> 4), bd = desc0 + ((sA + F_XBYTES) >> 4);
+        umma_bf16(h_tmem, ad, bd, idesc1, kb > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 1; ks < F_BK / 16; ++ks) umma_bf16_acc(h_tmem, ad + 2 * ks, bd + 2 * ks, idesc1);
+        umma_commit(&empty[stage]);
+      }
+      __syncwarp();
+      if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+    }
+    if (elect_one()) umma_commit(h_full);
+    __syncwarp();
+    mbar_wait(h_ready, 0);  // H is in shared memory as a swizzled bf16 K-major tile
+    tc_fence_after();
+    const uint32_t sH = smem_u32(hbuf);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = t0; t < t1; ++t) {
+      mbar_wait(&y_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * F_TILE_N;
+      for (int kb = 0; kb < kb2; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t sA = smem_u32(smem + stage * F_STAGE);
-        const uint32_t sB = sA + F_XBYTES;
+        if (elect_one()) {
+          const uint32_t sB = smem_base + stage * F_STAGE + g.w2_off;
+          const uint32_t sA = sH + kb * F_HBLOCK;
+          const uint64_t ad = desc0 + (sA >> 4), bd = desc0 + (sB >> 4);
+          umma_bf16(d_tmem, ad, bd, idesc2, kb > 0 ? 1u : 0u);
 #pragma unroll
-        for (int ks = 0; ks < F_BK / 16; ++ks)
-          umma_bf16(h_tmem, umma_smem_desc_sw128(sA + ks * 32, 16, 1024),
-                    umma_smem_desc_sw128(sB + ks * 32, 16, 1024), idesc1, (kb > 0 || ks > 0) ? 1u : 0u);
-        umma_commit(&empty[stage]);
+          for (int ks = 1; ks < F_BK / 16; ++ks) umma_bf16_acc(d_tmem, ad + 2 * ks, bd + 2 * ks, idesc2);
+          umma_commit(&empty[stage]);
+        }
+        __syncwarp();
         if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
       }
-      umma_commit(h_full);
-      mbar_wait(h_ready, 0);  // H is in shared memory as a swizzled bf16 K-major tile
-      tc_fence_after();
-      const uint32_t sH = smem_u32(hbuf);
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int t = t0; t < t1; ++t) {
-        mbar_wait(&y_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * F_TILE_N;
-        for (int kb = 0; kb < kb2; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t sB = smem_u32(smem + stage * F_STAGE + g.w2_off);
-          const uint32_t sA = sH + kb * F_HBLOCK;
-#pragma unroll
-          for (int ks = 0; ks < F_BK / 16; ++ks)
-            umma_bf16(d_tmem, umma_smem_desc_sw128(sA + ks * 32, 16, 1024),
-                      umma_smem_desc_sw128(sB + ks * 32, 16, 1024), idesc2, (kb > 0 || ks > 0) ? 1u : 0u);
-          umma_commit(&empty[stage]);
-          if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(&y_full[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      }
+      if (elect_one()) umma_commit(&y_full[acc]);
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     const int q = warp & 3;                 // TMEM lane quarter of this warp
@@ -377,7 +390,7 @@ lowrank_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
   uint64_t* y_empty = y_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const int row_tiles = (g.n + F_TILE_M - 1) / F_TILE_M;
   const int J = (row_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                 static_cast<int>(gridDim.x);  // token tiles of this CTA: blockIdx.x + j * gridDim.x
@@ -413,98 +426,111 @@ lowrank_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
   const uint32_t y_tmem = tmem_base + 256;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      auto load_k1 = [&](int j, int kb) {
-        const int m0 = (static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x)) * F_TILE_M;
-        mbar_wait(&empty[stage], phase ^ 1);
+    // converged warp, one elected lane issues (see gemm_tc.cu)
+    int stage = 0;
+    uint32_t phase = 0;
+    auto load_k1 = [&](int j, int kb) {
+      const int m0 = (static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x)) * F_TILE_M;
+      mbar_wait(&empty[stage], phase ^ 1);
+      if (elect_one()) {
         uint8_t* slot = smem + stage * P_SLOT;
         mbar_expect_tx(&full[stage], F_XBYTES + g.kp * 128);
         tma_load_3d(slot, &tmX, &full[stage], kb * F_BK, m0, 0);
         tma_load_3d(slot + F_XBYTES, &tmW1, &full[stage], kb * F_BK, 0, 0);
-        if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
-      };
-      auto load_tile = [&](int t) {
-        for (int kb = 0; kb < kb2; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+      }
+      __syncwarp();
+      if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+    };
+    auto load_tile = [&](int t) {
+      for (int kb = 0; kb < kb2; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&full[stage], F_WBYTES);
           tma_load_3d(smem + stage * P_SLOT, &tmW2, &full[stage], kb * F_BK, t * F_TILE_N, 0);
-          if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
         }
-      };
-      for (int kb = 0; kb < kb1; ++kb) load_k1(0, kb);
-      for (int j = 0; j < J; ++j) {
-        const bool has_next = j + 1 < J;
-        int kk = 0;
-        if (has_next)
-          for (; kk < min(kb1, P_LEAD); ++kk) load_k1(j + 1, kk);
-        for (int t = 0; t < ntiles; ++t) {
-          load_tile(t);
-          if (has_next) {
-            const int quota = (kb1 - kk + (ntiles - t) - 1) / (ntiles - t);
-            for (int q = 0; q < quota; ++q) load_k1(j + 1, kk++);
-          }
+        __syncwarp();
+        if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+      }
+    };
+    for (int kb = 0; kb < kb1; ++kb) load_k1(0, kb);
+    for (int j = 0; j < J; ++j) {
+      const bool has_next = j + 1 < J;
+      int kk = 0;
+      if (has_next)
+        for (; kk < min(kb1, P_LEAD); ++kk) load_k1(j + 1, kk);
+      for (int t = 0; t < ntiles; ++t) {
+        load_tile(t);
+        if (has_next) {
+          const int quota = (kb1 - kk + (ntiles - t) - 1) / (ntiles - t);
+          for (int q = 0; q < quota; ++q) load_k1(j + 1, kk++);
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc1 = umma_idesc_bf16(F_TILE_M, g.kp, 0, 0);
-      const uint32_t idesc2 = umma_idesc_bf16(F_TILE_M, F_TILE_N, 0, 0);
-      const uint32_t sH = smem_u32(hbuf);
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t ytile = 0;  // running count of Y tiles (parity of y_full / y_empty)
-      auto mma_k1 = [&](int j, int kb) {
+    const uint32_t idesc1 = umma_idesc_bf16(F_TILE_M, g.kp, 0, 0);
+    const uint32_t idesc2 = umma_idesc_bf16(F_TILE_M, F_TILE_N, 0, 0);
+    const uint64_t desc0 = umma_smem_desc_sw128(0, 16, 1024);  // + (address >> 4) in the low word
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t sH = smem_u32(hbuf);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t ytile = 0;  // running count of Y tiles (parity of y_full / y_empty)
+    auto mma_k1 = [&](int j, int kb) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sA = smem_base + stage * P_SLOT;
+        const uint64_t ad = desc0 + (sA >> 4), bd = desc0 + ((sA + F_XBYTES) >> 4);
+        const uint32_t d_tmem = tmem_base + (j & 1) * 128;
+        umma_bf16(d_tmem, ad, bd, idesc1, kb > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 1; ks < F_BK / 16; ++ks) umma_bf16_acc(d_tmem, ad + 2 * ks, bd + 2 * ks, idesc1);
+        umma_commit(&empty[stage]);
+        if (kb == kb1 - 1) umma_commit(&h_full[j & 1]);
+      }
+      __syncwarp();
+      if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+    };
+    auto mma_tile = [&](int j, int t) {
+      if (t == 0) {
+        mbar_wait(h_ready, j & 1);  // Hs holds token tile j
+        tc_fence_after();
+      }
+      mbar_wait(y_empty, (ytile & 1) ^ 1);
+      tc_fence_after();
+      for (int kb = 0; kb < kb2; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t sA = smem_u32(smem + stage * P_SLOT);
-        const uint32_t sB = sA + F_XBYTES;
-        const uint32_t d_tmem = tmem_base + (j & 1) * 128;
-#pragma unroll
-        for (int ks = 0; ks < F_BK / 16; ++ks)
-          umma_bf16(d_tmem, umma_smem_desc_sw128(sA + ks * 32, 16, 1024),
-                    umma_smem_desc_sw128(sB + ks * 32, 16, 1024), idesc1, (kb > 0 || ks > 0) ? 1u : 0u);
-        umma_commit(&empty[stage]);
-        if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
-        if (kb == kb1 - 1) umma_commit(&h_full[j & 1]);
-      };
-      auto mma_tile = [&](int j, int t) {
-        if (t == 0) {
-          mbar_wait(h_ready, j & 1);  // Hs holds token tile j
-          tc_fence_after();
-        }
-        mbar_wait(y_empty, (ytile & 1) ^ 1);
-        tc_fence_after();
-        for (int kb = 0; kb < kb2; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t sB = smem_u32(smem + stage * P_SLOT);
+        if (elect_one()) {
+          const uint32_t sB = smem_base + stage * P_SLOT;
           const uint32_t sA = sH + kb * F_HBLOCK;
+          const uint64_t ad = desc0 + (sA >> 4), bd = desc0 + (sB >> 4);
+          umma_bf16(y_tmem, ad, bd, idesc2, kb > 0 ? 1u : 0u);
 #pragma unroll
-          for (int ks = 0; ks < F_BK / 16; ++ks)
-            umma_bf16(y_tmem, umma_smem_desc_sw128(sA + ks * 32, 16, 1024),
-                      umma_smem_desc_sw128(sB + ks * 32, 16, 1024), idesc2, (kb > 0 || ks > 0) ? 1u : 0u);
+          for (int ks = 1; ks < F_BK / 16; ++ks) umma_bf16_acc(y_tmem, ad + 2 * ks, bd + 2 * ks, idesc2);
           umma_commit(&empty[stage]);
-          if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) {
         umma_commit(y_full);
-        ++ytile;
         if (t == ntiles - 1) umma_commit(hs_free);
-      };
-      for (int kb = 0; kb < kb1; ++kb) mma_k1(0, kb);
-      for (int j = 0; j < J; ++j) {
-        const bool has_next = j + 1 < J;
-        int kk = 0;
-        if (has_next)
-          for (; kk < min(kb1, P_LEAD); ++kk) mma_k1(j + 1, kk);
-        for (int t = 0; t < ntiles; ++t) {
-          mma_tile(j, t);
-          if (has_next) {
-            const int quota = (kb1 - kk + (ntiles - t) - 1) / (ntiles - t);
-            for (int q = 0; q < quota; ++q) mma_k1(j + 1, kk++);
-          }
+      }
+      __syncwarp();
+      ++ytile;
+    };
+    for (int kb = 0; kb < kb1; ++kb) mma_k1(0, kb);
+    for (int j = 0; j < J; ++j) {
+      const bool has_next = j + 1 < J;
+      int kk = 0;
+      if (has_next)
+        for (; kk < min(kb1, P_LEAD); ++kk) mma_k1(j + 1, kk);
+      for (int t = 0; t < ntiles; ++t) {
+        mma_tile(j, t);
+        if (has_next) {
+          const int quota = (kb1 - kk + (ntiles - t) - 1) / (ntiles - t);
+          for (int q = 0; q < quota; ++q) mma_k1(j + 1, kk++);
         }
       }
     }
