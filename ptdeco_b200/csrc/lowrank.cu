@@ -634,6 +634,366 @@ lowrank_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
   }
 }
 
+// ------------------------------------------------------------------------------ decode kernel
+// Small token counts (N <= 128: decode / short prefill). The op is pure weight streaming
+// (2 k (in + out) bytes), so the weights take the M side of the tensor core ("swap AB") and the
+// tokens the N side (padded to a multiple of 16 instead of to a 128-row tile):
+//   phase 1   H^T[k, N] = W1[k, in] X^T : units = (128-row tiles of W1) x (splits of `in`), so every
+//             SM streams a slice of W1; partial sums meet in an fp32 H[N, k] with red.add; the
+//             last unit of a row tile (ticket counter) rounds its 128 columns of H to bf16
+//   grid barrier (cooperative launch)
+//   phase 2   Y^T[out, N] = W2[out, k] H^T : units = 128-row tiles of W2, H k-blocks ride the same
+//             TMA ring as the W2 k-blocks; bias + bf16 store, coalesced along `out`
+// One launch, one grid barrier, one memset of the (small) H / ticket workspace before it.
+constexpr int D_TILE = 128;
+constexpr int D_BK = 64;
+constexpr int D_WBYTES = D_TILE * D_BK * 2;  // 16 KB weight k-block
+constexpr int D_STAGES = 6;
+constexpr int D_THREADS = 64 + 128;  // producer, MMA, 4 epilogue warps (one per TMEM lane quarter)
+constexpr int D_CTRL_BYTES = 4096;   // [0] grid barrier, [16 + t] ticket of row tile t
+
+struct DecodeArgs {
+  int n, npad, in_f, k, out_f;
+  int kb_in, kb_k;         // k-blocks of the two reductions
+  int rt1, rt2;            // 128-row tiles of W1 / W2
+  int s1, kb_per_split;    // phase 1 split of `in`
+  long long ldh;           // row pitch of H (fp32) and Hb (bf16), elements (multiple of 128)
+  unsigned* ctrl;
+  float* H;
+  __nv_bfloat16* Hb;
+  __nv_bfloat16* Y;
+  long long ldy;
+  const float* bias;
+};
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(D_THREADS, 1)
+lowrank_decode_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmX,
+                      const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmH,
+                      const DecodeArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int stage_bytes = D_WBYTES + g.npad * 128;  // weight k-block + token-side k-block
+  // stages are placed 32 KB apart so every operand stays 1024-byte aligned
+  constexpr int D_SLOT = 32768;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + D_STAGES * D_SLOT);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + D_STAGES;
+  uint64_t* acc_full = bars + 2 * D_STAGES;   // [2]
+  uint64_t* acc_empty = acc_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  int* last_flag = reinterpret_cast<int*>(tmem_slot + 1);
+
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
+  const int G = static_cast<int>(gridDim.x), cta = static_cast<int>(blockIdx.x);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmH);
+    for (int s = 0; s < D_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);  // two accumulators of up to 128 columns
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int units1 = g.rt1 * g.s1;
+  // pipeline state carried across the two phases by each role
+  int stage = 0;
+  uint32_t phase = 0;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+
+  // ================================================================== phase 1
+  if (warp == 0) {
+    for (int u = cta; u < units1; u += G) {
+      const int rt = u / g.s1, sp = u % g.s1;
+      const int kb0 = sp * g.kb_per_split, kb1 = min(g.kb_in, kb0 + g.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* sW = smem + stage * D_SLOT;
+          mbar_expect_tx(&full[stage], stage_bytes);
+          tma_load_3d(sW, &tmW1, &full[stage], kb * D_BK, rt * D_TILE, 0);
+          tma_load_3d(sW + D_WBYTES, &tmX, &full[stage], kb * D_BK, 0, 0);
+        }
+        __syncwarp();
+        if (++stage == D_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = umma_idesc_bf16(D_TILE, g.npad, 0, 0);
+    const uint64_t desc0 = umma_smem_desc_sw128(0, 16, 1024);
+    const uint32_t smem_base = smem_u32(smem);
+    for (int u = cta; u < units1; u += G) {
+      const int sp = u % g.s1;
+      const int kb0 = sp * g.kb_per_split, kb1 = min(g.kb_in, kb0 + g.kb_per_split);
+      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 128;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sW = smem_base + stage * D_SLOT;
+          const uint64_t ad = desc0 + (sW >> 4), bd = desc0 + ((sW + D_WBYTES) >> 4);
+          umma_bf16(d_tmem, ad, bd, idesc, kb > kb0 ? 1u : 0u);
+#pragma unroll
+          for (int ks = 1; ks < D_BK / 16; ++ks) umma_bf16_acc(d_tmem, ad + 2 * ks, bd + 2 * ks, idesc);
+          umma_commit(&empty[stage]);
+        }
+        __syncwarp();
+        if (++stage == D_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) umma_commit(&acc_full[acc]);
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter (warps 2..5 -> 2,3,0,1)
+    const int row = q * 32 + lane;
+    const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
+    for (int u = cta; u < units1; u += G) {
+      const int rt = u / g.s1;
+      const int kcol = rt * D_TILE + row;  // column of H this thread owns
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      for (int c0 = 0; c0 < g.npad; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld_32x16(tmem_base + acc * 128 + c0 + lane_bits, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)  // lanes of a warp hit 32 consecutive floats of row (c0 + j)
+          atomicAdd(g.H + static_cast<long long>(c0 + j) * g.ldh + kcol, __uint_as_float(r[j]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      // ticket: the unit that completes a row tile rounds its 128 columns of H to bf16
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        const unsigned old = atomicAdd(g.ctrl + 16 + rt, 1u);
+        *last_flag = (old == static_cast<unsigned>(g.s1 - 1)) ? 1 : 0;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (*last_flag) {
+        __threadfence();
+        if ((g.npad & 31) == 0) {  // 32 independent loads in flight, then the stores
+          for (int n0 = 0; n0 < g.npad; n0 += 32) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __ldcg(g.H + static_cast<long long>(n0 + j) * g.ldh + kcol);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              g.Hb[static_cast<long long>(n0 + j) * g.ldh + kcol] = __float2bfloat16_rn(v[j]);
+          }
+        } else {
+          for (int n0 = 0; n0 < g.npad; n0 += 16) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __ldcg(g.H + static_cast<long long>(n0 + j) * g.ldh + kcol);
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              g.Hb[static_cast<long long>(n0 + j) * g.ldh + kcol] = __float2bfloat16_rn(v[j]);
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // last_flag is rewritten by the next unit
+    }
+  }
+
+  // ================================================================== grid barrier
+  __threadfence();
+  asm volatile("fence.proxy.async;" ::: "memory");  // Hb (generic stores) -> TMA loads of phase 2
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(g.ctrl, 1u);
+    unsigned v = 0;
+    unsigned polls = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(g.ctrl) : "memory");
+      if (++polls > (1u << 28)) __trap();  // never hang the box on a lost CTA
+    } while (v < static_cast<unsigned>(G));
+    __threadfence();
+  }
+  __syncthreads();
+  asm volatile("fence.proxy.async;" ::: "memory");
+
+  // ================================================================== phase 2
+  if (warp == 0) {
+    for (int t = cta; t < g.rt2; t += G) {
+      for (int kb = 0; kb < g.kb_k; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* sW = smem + stage * D_SLOT;
+          mbar_expect_tx(&full[stage], stage_bytes);
+          tma_load_3d(sW, &tmW2, &full[stage], kb * D_BK, t * D_TILE, 0);
+          tma_load_3d(sW + D_WBYTES, &tmH, &full[stage], kb * D_BK, 0, 0);
+        }
+        __syncwarp();
+        if (++stage == D_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = umma_idesc_bf16(D_TILE, g.npad, 0, 0);
+    const uint64_t desc0 = umma_smem_desc_sw128(0, 16, 1024);
+    const uint32_t smem_base = smem_u32(smem);
+    for (int t = cta; t < g.rt2; t += G) {
+      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 128;
+      for (int kb = 0; kb < g.kb_k; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sW = smem_base + stage * D_SLOT;
+          const uint64_t ad = desc0 + (sW >> 4), bd = desc0 + ((sW + D_WBYTES) >> 4);
+          umma_bf16(d_tmem, ad, bd, idesc, kb > 0 ? 1u : 0u);
+#pragma unroll
+          for (int ks = 1; ks < D_BK / 16; ++ks) umma_bf16_acc(d_tmem, ad + 2 * ks, bd + 2 * ks, idesc);
+          umma_commit(&empty[stage]);
+        }
+        __syncwarp();
+        if (++stage == D_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) umma_commit(&acc_full[acc]);
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
+    for (int t = cta; t < g.rt2; t += G) {
+      const int orow = t * D_TILE + row;  // output feature this thread owns
+      const float b = (g.bias != nullptr && orow < g.out_f) ? __ldg(g.bias + orow) : 0.f;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      for (int c0 = 0; c0 < g.npad; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld_32x16(tmem_base + acc * 128 + c0 + lane_bits, r);
+        tmem_ld_wait();
+        if (orow < g.out_f) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)  // a warp writes 32 consecutive bf16 of token row (c0 + j)
+            if (c0 + j < g.n)
+              g.Y[static_cast<long long>(c0 + j) * g.ldy + orow] =
+                  __float2bfloat16_rn(__uint_as_float(r[j]) + b);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+size_t decode_workspace_bytes(long long n, int k) {
+  const long long npad = round_up(n, 16);
+  const long long ldh = round_up(k, 128);
+  return D_CTRL_BYTES + static_cast<size_t>(npad * ldh) * 6 + 1024;
+}
+
+// Weight streaming only pays once there are weights to stream: below ~2 MB of factors the fused /
+// two-launch paths (no grid barrier, no workspace memset) are as fast or faster (measured).
+bool decode_eligible(const void* X, long long ldx, const void* W1, long long ldw1, const void* W2,
+                     long long ldw2, int is_bf16, long long n, int in_f, int k, int out_f) {
+  const bool big = static_cast<long long>(k) * (in_f + out_f) >= (1ll << 20) ||
+                   std::getenv("PTDECO_B200_FORCE_DECODE") != nullptr;
+  return is_bf16 && big && n <= 128 && k >= 16 && aligned16(X) && aligned16(W1) && aligned16(W2) &&
+         (ldx % 8) == 0 && (ldw1 % 8) == 0 && (ldw2 % 8) == 0 &&
+         (round_up(k, 128) / 128) <= (D_CTRL_BYTES / 4 - 16);
+}
+
+int launch_decode(const void* X, long long ldx, const void* W1, long long ldw1, const void* W2,
+                  long long ldw2, const float* bias, void* Y, long long ldy, long long n, int in_f,
+                  int k, int out_f, void* ws, cudaStream_t st) {
+  DecodeArgs g;
+  memset(&g, 0, sizeof(g));
+  g.n = static_cast<int>(n);
+  g.npad = static_cast<int>(round_up(n, 16));
+  g.in_f = in_f;
+  g.k = k;
+  g.out_f = out_f;
+  g.kb_in = (in_f + D_BK - 1) / D_BK;
+  g.kb_k = static_cast<int>(round_up(k, D_BK)) / D_BK;
+  g.rt1 = (k + D_TILE - 1) / D_TILE;
+  g.rt2 = (out_f + D_TILE - 1) / D_TILE;
+  g.ldh = round_up(k, 128);
+  const int sms = device_sm_count();
+  int s1 = std::max(1, std::min(g.kb_in, sms / g.rt1));
+  g.kb_per_split = (g.kb_in + s1 - 1) / s1;
+  g.s1 = (g.kb_in + g.kb_per_split - 1) / g.kb_per_split;
+  uint8_t* base = static_cast<uint8_t*>(ws);
+  base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(base) + 255) & ~uintptr_t(255));
+  g.ctrl = reinterpret_cast<unsigned*>(base);
+  g.H = reinterpret_cast<float*>(base + D_CTRL_BYTES);
+  g.Hb = reinterpret_cast<__nv_bfloat16*>(base + D_CTRL_BYTES + static_cast<size_t>(g.npad) * g.ldh * 4);
+  g.Y = static_cast<__nv_bfloat16*>(Y);
+  g.ldy = ldy;
+  g.bias = bias;
+  // zero the barrier / tickets and the fp32 H (Hb is fully rewritten by the kernel)
+  if (cudaMemsetAsync(base, 0, D_CTRL_BYTES + static_cast<size_t>(g.npad) * g.ldh * 4, st) != cudaSuccess)
+    return -5;
+  CUtensorMap tw1, tx, tw2, th;
+  int rc;
+  if ((rc = make_tma_2d_bf16(&tw1, W1, in_f, k, ldw1, D_TILE))) return rc;
+  if ((rc = make_tma_2d_bf16(&tx, X, in_f, n, ldx, g.npad))) return rc;
+  if ((rc = make_tma_2d_bf16(&tw2, W2, k, out_f, ldw2, D_TILE))) return rc;
+  if ((rc = make_tma_2d_bf16(&th, g.Hb, g.ldh, g.npad, g.ldh, g.npad))) return rc;
+  constexpr int D_SMEM = D_STAGES * 32768 + 1024 + 256;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(lowrank_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             D_SMEM) != cudaSuccess)
+      return -12;
+    attr = true;
+  }
+  const int units = std::max(g.rt1 * g.s1, g.rt2);
+  const int grid = std::min(sms, units);
+  void* params[] = {&tw1, &tx, &tw2, &th, &g};
+  if (cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lowrank_decode_kernel), dim3(grid),
+                                  dim3(D_THREADS), params, D_SMEM, st) != cudaSuccess)
+    return -5;
+  return cudaGetLastError() == cudaSuccess ? 0 : -5;
+}
+
 bool fused_eligible(const void* X, long long ldx, const void* W1, long long ldw1, const void* W2,
                     long long ldw2, int is_bf16, int k) {
   return is_bf16 && k <= 256 && aligned16(X) && aligned16(W1) && aligned16(W2) && (ldx % 8) == 0 &&
@@ -735,7 +1095,9 @@ size_t lowrank_workspace_bytes(int is_bf16, long long n, int in_f, int k, int ou
   stage(nullptr, is_bf16, out_f, k, k, cv, &op, nullptr, true);
   const int nseg = is_bf16 ? 1 : 3;
   cv.take(2ull * nseg * n * round_up(k, 8));
-  return cv.off + 512;
+  size_t need = cv.off + 512;
+  if (is_bf16 && n <= 128) need = std::max(need, decode_workspace_bytes(n, k));
+  return need;
 }
 
 int lowrank_forward(const void* X, long long ldx, const void* W1, long long ldw1, const void* W2,
@@ -745,6 +1107,10 @@ int lowrank_forward(const void* X, long long ldx, const void* W1, long long ldw1
   if (X == nullptr || W1 == nullptr || W2 == nullptr || Y == nullptr) return -22;
   if (n <= 0 || in_f <= 0 || k <= 0 || out_f <= 0 || n > 0x7fffffffLL) return -22;
   if (ldx < in_f || ldw1 < in_f || ldw2 < k || ldy < out_f) return -22;
+  if (decode_eligible(X, ldx, W1, ldw1, W2, ldw2, is_bf16, n, in_f, k, out_f) && ws != nullptr &&
+      ws_bytes >= decode_workspace_bytes(n, k) + 256 && (reinterpret_cast<uintptr_t>(Y) & 1) == 0 &&
+      std::getenv("PTDECO_B200_NO_DECODE") == nullptr)
+    return launch_decode(X, ldx, W1, ldw1, W2, ldw2, bias, Y, ldy, n, in_f, k, out_f, ws, st);
   if (fused_eligible(X, ldx, W1, ldw1, W2, ldw2, is_bf16, k) && std::getenv("PTDECO_B200_NO_FUSED") == nullptr)
     return launch_fused(X, ldx, W1, ldw1, W2, ldw2, bias, Y, ldy, n, in_f, k, out_f, st);
   if (ws == nullptr || ws_bytes < lowrank_workspace_bytes(is_bf16, n, in_f, k, out_f)) return -12;

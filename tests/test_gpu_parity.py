@@ -276,6 +276,61 @@ def test_lowrank_forward(dev, dtype, tol, n, in_f, k, out_f):
     assert (y.double().cpu() - ref).abs().max() <= tol * ref.abs().max()
 
 
+@pytest.mark.parametrize("n,in_f,k,out_f,bias", [
+    (1, 256, 32, 256, False), (5, 320, 96, 1000, True), (16, 4096, 512, 4096, True),
+    (33, 768, 200, 3072, True), (128, 2048, 1024, 2048, False), (100, 1024, 1000, 520, True),
+    (7, 4096, 40, 14336, True)])
+def test_lowrank_forward_decode_kernel(dev, monkeypatch, n, in_f, k, out_f, bias):
+    """N <= 128: the single-launch weight-streaming kernel (swap-AB, split-`in` phase 1 with fp32
+    red.add + ticketed bf16 rounding, grid barrier, phase 2). Forced on for every shape here (small
+    factors are normally routed to the fused kernel), compared with the two-launch path and with an
+    fp64 product that rounds the rank-k intermediate to bf16 like the module pair does."""
+    from ptdeco_b200 import linalg
+    g = torch.Generator().manual_seed(1000 * n + k)
+    x = torch.randn(n, in_f, generator=g).to(torch.bfloat16)
+    w1 = (torch.randn(k, in_f, generator=g) / in_f ** 0.5).to(torch.bfloat16)
+    w2 = (torch.randn(out_f, k, generator=g) / k ** 0.5).to(torch.bfloat16)
+    b = torch.randn(out_f, generator=g) if bias else None
+    args = (x.to(dev), w1.to(dev), w2.to(dev), None if b is None else b.to(dev))
+    monkeypatch.setenv("PTDECO_B200_FORCE_DECODE", "1")
+    y = linalg.lowrank_forward(*args)
+    y_again = linalg.lowrank_forward(*args)  # the workspace is reused: tickets / H must be reset
+    monkeypatch.delenv("PTDECO_B200_FORCE_DECODE")
+    monkeypatch.setenv("PTDECO_B200_NO_DECODE", "1")
+    y_two_launch = linalg.lowrank_forward(*args)
+    h = (x.double() @ w1.double().T).to(torch.bfloat16).double()
+    ref = h @ w2.double().T + (0.0 if b is None else b.double())
+    scale = ref.abs().max()
+    assert y.dtype == torch.bfloat16 and tuple(y.shape) == (n, out_f)
+    assert (y.double().cpu() - ref).abs().max() <= 1e-2 * scale
+    assert (y_again.double().cpu() - ref).abs().max() <= 1e-2 * scale
+    assert (y.double() - y_two_launch.double()).abs().max().cpu() <= 2e-2 * scale
+
+
+@pytest.mark.parametrize("m,n,k", [(8192, 4096, 1024), (1000, 520, 328), (300, 264, 72)])
+def test_gemm_cta_pair_matches_single_cta(dev, m, n, k):
+    """The 256 x 256 CTA-pair (cta_group::2) instance of the engine against the single-CTA one and
+    an fp64 product: ragged M / N / K go through TMA zero fill and the row / column guards."""
+    from ptdeco_b200 import _native as nat
+    from ptdeco_b200 import linalg
+    g = torch.Generator().manual_seed(m + n + k)
+    x = torch.randn(m, k, generator=g).to(torch.bfloat16).to(dev)
+    w = torch.randn(n, k, generator=g).to(torch.bfloat16).to(dev)
+    L = nat.lib()
+    try:
+        L.ptdeco_debug_set(7, 0)
+        y_pair = linalg.linear_nt(x, w, out_dtype=torch.float32)
+        assert L.ptdeco_debug_get(5) == 1
+        L.ptdeco_debug_set(7, 1)
+        y_single = linalg.linear_nt(x, w, out_dtype=torch.float32)
+        assert L.ptdeco_debug_get(5) == 0
+    finally:
+        L.ptdeco_debug_set(7, 0)
+    ref = x.double() @ w.double().T
+    assert (y_pair.double() - ref).abs().max() <= 2e-6 * ref.abs().max() * (k ** 0.5)
+    assert (y_pair - y_single).abs().max() <= 1e-5 * ref.abs().max()
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
 def test_lowrank_sequential_matches_torch_sequential(dev, dtype, tol):
     from ptdeco_b200 import modules
