@@ -196,8 +196,8 @@ def workload_config(n_gpus: int) -> dict:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ptdeco_b200")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
@@ -427,11 +427,15 @@ def main() -> None:
             "clocks": clk.summary(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE d=14336, N=8192 launch
-                         # (the dominant shape: 64 of 224 launches, 88 % of the step), from the
-                         # `ncu --set full` capture summarised in profiles/r01_syrk_ncu_full_summary_v2.json;
-                         # algorithmic bytes of that launch: 0.235 GB of tokens + 0.822 GB accumulator RMW
-                         "traffic": 2.19e9, "traffic_unit": "B/launch (d=14336, N=8192)",
+                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE d=14336, N=16384 launch
+                         # (the dominant shape: 64 of 224 launches, 88 % of the step), from the ncu
+                         # capture in profiles/r01_syrk_traffic_by_tokens_and_band.txt (4.97 GB read +
+                         # 0.41 GB written). Algorithmic bytes of that launch: 0.470 GB of tokens +
+                         # 0.822 GB accumulator RMW; the excess is operand re-reads between waves (the
+                         # ~145 MB working set of one wave of 74 tile pairs exceeds the L2). The kernel
+                         # is tensor / power bound: this traffic is 2.0 TB/s, 31 % of the HBM peak.
+                         "traffic": 5.38e9, "traffic_unit": "B/launch (d=14336, N=16384)",
+                         "algorithmic_bytes_per_launch": 1.292e9,
                          "kernel": "gemm_tc2_kernel<MN,MN> (SYRK, lower triangle, 256x256 tiles on CTA pairs, cta_group::2)",
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})",
                          "algorithmic_flop_per_token": alg_flops_per_token()},
