@@ -7,7 +7,8 @@ consumes directly, so the projection y = x W^T is not recomputed outside the mod
 """
 from __future__ import annotations
 
-from typing import Optional
+import os
+from typing import Any, Optional
 
 import torch
 
@@ -20,6 +21,9 @@ class WrappedModule(torch.nn.Module):
         self.input = torch.zeros(size=(0,))
         self.output: Optional[torch.Tensor] = None
         self.capture_output = False
+        # paired rank trial (see PairState): when set, the first half of the batch goes through
+        # this [out, in] weight and the second half through the layer's own
+        self.pair_weight: Optional[torch.Tensor] = None
 
     def get_weight_copy(self) -> torch.Tensor:
         raise NotImplementedError()
@@ -54,6 +58,11 @@ class WrappedLinear(WrappedModule):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         self.input = x
+        if self.pair_weight is not None:
+            b = x.shape[0] // 2
+            bias = self.lin_orig.bias
+            return torch.cat([torch.nn.functional.linear(x[:b], self.pair_weight, bias),
+                              torch.nn.functional.linear(x[b:], self.lin_orig.weight, bias)], 0)
         y = self.lin_orig(x)
         if self.capture_output:
             self.output = y
@@ -99,6 +108,11 @@ class WrappedConv2d1x1(WrappedModule):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         self.input = x
+        if self.pair_weight is not None:
+            b = x.shape[0] // 2
+            conv = self.conv_orig
+            return torch.cat([conv._conv_forward(x[:b], self.pair_weight[:, :, None, None], conv.bias),
+                              conv._conv_forward(x[b:], conv.weight, conv.bias)], 0)
         y = self.conv_orig(x)
         if self.capture_output:
             self.output = y
@@ -147,3 +161,75 @@ def is_num_params_reduced(proportion: float, in_features: int, out_features: int
     original_rank = min(in_features, out_features)
     proposed = (in_features + out_features) * proportion * original_rank
     return proposed < baseline
+
+
+class PairState:
+    """Paired rank trials. The reference evaluates a trial with two full
+    forwards of the same batch, one with the decomposed weight copied into the layer and one with
+    the original (F:211-233, D:247-278). The library owns the wrapped layer, so both variants can
+    share ONE forward of the batch concatenated with itself: the wrapper sends the first half
+    through the decomposed weight and the second half through the original. Same arithmetic per
+    sample for any model that treats batch elements independently in eval mode; half the kernel
+    launches (small models are launch-bound) and better-filled GEMMs.
+
+    Safety: the first trial batch of a decompose call is evaluated BOTH ways; pairing is kept only
+    if the two agree (relative Frobenius error of the logits within the dtype's rounding noise),
+    so a model with a batch-dependent forward or an unusual batch layout silently keeps the
+    reference's two-forward path. PTDECO_B200_PAIRED_TRIALS=0 disables pairing."""
+
+    def __init__(self) -> None:
+        self.mode = "off" if os.environ.get("PTDECO_B200_PAIRED_TRIALS", "1") == "0" else "unknown"
+        self.paired_forwards = 0
+
+    @staticmethod
+    def _double(inputs: Any) -> tuple[Optional[Any], int]:
+        if isinstance(inputs, torch.Tensor):
+            if inputs.dim() < 1 or inputs.shape[0] == 0:
+                return None, 0
+            return torch.cat([inputs, inputs], 0), inputs.shape[0]
+        if isinstance(inputs, dict):
+            bs = {v.shape[0] for v in inputs.values() if isinstance(v, torch.Tensor) and v.dim() >= 1}
+            if len(bs) != 1 or any(isinstance(v, torch.Tensor) and v.dim() < 1 for v in inputs.values()):
+                return None, 0
+            return {k: (torch.cat([v, v], 0) if isinstance(v, torch.Tensor) else v)
+                    for k, v in inputs.items()}, bs.pop()
+        return None, 0
+
+    def _paired(self, forward_fn, wrapper: WrappedModule, inputs: Any,
+                deco_weight: torch.Tensor) -> Optional[tuple[torch.Tensor, torch.Tensor]]:
+        doubled, b = self._double(inputs)
+        if doubled is None:
+            return None
+        wrapper.pair_weight = deco_weight
+        try:
+            yy = forward_fn(doubled)
+        finally:
+            wrapper.pair_weight = None
+        if not isinstance(yy, torch.Tensor) or yy.dim() < 1 or yy.shape[0] != 2 * b:
+            return None
+        self.paired_forwards += 1
+        return yy[:b], yy[b:]
+
+    def forward_pair(self, forward_fn, wrapper: WrappedModule, inputs: Any, orig_weight: torch.Tensor,
+                     deco_weight: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        """(y_deco, y_orig) of one trial batch. Leaves the original weight in the layer."""
+        if self.mode == "on":
+            out = self._paired(forward_fn, wrapper, inputs, deco_weight)
+            if out is not None:
+                return out
+            self.mode = "off"
+        wrapper.set_weight(deco_weight)
+        y_deco = forward_fn(inputs)
+        wrapper.set_weight(orig_weight)
+        y_orig = forward_fn(inputs)
+        if self.mode == "unknown":
+            self.mode = "off"
+            out = self._paired(forward_fn, wrapper, inputs, deco_weight)
+            if out is not None and isinstance(y_orig, torch.Tensor) and out[0].shape == y_deco.shape:
+                tol = 1e-4 if y_orig.dtype in (torch.float32, torch.float64) else 3e-2
+                ref = torch.linalg.vector_norm(y_orig.float()).clamp_min(1e-30)
+                err = max(float(torch.linalg.vector_norm(out[0].float() - y_deco.float()) / ref),
+                          float(torch.linalg.vector_norm(out[1].float() - y_orig.float()) / ref))
+                if err <= tol:  # NaN fails the comparison and keeps pairing off
+                    self.mode = "on"
+        return y_deco, y_orig

@@ -171,15 +171,21 @@ def _compute_metrics(
     orig_weight: torch.Tensor,
     deco_weight: torch.Tensor,
     loss_fn: collections.abc.Callable[[dict[str, torch.Tensor], torch.Tensor], torch.Tensor],
+    pair_state: Optional[_wrap.PairState] = None,
 ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """D:247-278."""
+    """D:247-278. With a verified `pair_state` the two forwards share one pass over the doubled
+    batch (see _wrap.PairState); the losses are still taken per variant on the original batch."""
     assert isinstance(input_dict, dict)
     assert isinstance(decomposed_submodule, WrappedDWAINModule)
     root_module.eval()
-    decomposed_submodule.set_weight(deco_weight)
-    y_deco = root_module(input_dict)
-    decomposed_submodule.set_weight(orig_weight)
-    y_orig = root_module(input_dict)
+    if pair_state is not None:
+        y_deco, y_orig = pair_state.forward_pair(root_module, decomposed_submodule, input_dict,
+                                                 orig_weight, deco_weight)
+    else:
+        decomposed_submodule.set_weight(deco_weight)
+        y_deco = root_module(input_dict)
+        decomposed_submodule.set_weight(orig_weight)
+        y_orig = root_module(input_dict)
     loss_deco = loss_fn(input_dict, y_deco)
     loss_orig = loss_fn(input_dict, y_orig)
     nsr_final = utils.calc_per_channel_noise_to_signal_ratio(
@@ -235,6 +241,7 @@ def _process_module(
     decompose_in_float64: bool = True,
     u_matrix: Optional[torch.Tensor] = None,
     trace: Optional[list] = None,
+    pair_state: Optional[_wrap.PairState] = None,
 ) -> dict[str, Any]:
     """D:333-537."""
     indent = "    "
@@ -310,7 +317,8 @@ def _process_module(
             input_dict = utils.to_device(batch, device)
             nsr_sample, ppl_deco_sample, ppl_orig_sample = _compute_metrics(
                 input_dict=input_dict, root_module=root_module, decomposed_submodule=wrapper,
-                orig_weight=orig_weight, deco_weight=deco_weight, loss_fn=loss_fn)
+                orig_weight=orig_weight, deco_weight=deco_weight, loss_fn=loss_fn,
+                pair_state=pair_state)
             ppl_diff_sample = (ppl_deco_sample - ppl_orig_sample) / ppl_orig_sample
             acc += torch.stack([ppl_diff_sample.double(), nsr_sample.double(),
                                 ppl_deco_sample.double()])
@@ -542,6 +550,7 @@ def decompose_in_place(
         logger.info("Skipping precomputing convariance matrices")
         u_dict = {}
     utils.free_gpu_reserved_memory()
+    pair_state = _wrap.PairState()
 
     for i, name in enumerate(reversed(names), start=1):
         logger.info(f"PROCESSING {name} MODULE {i} OUT OF {n}")
@@ -555,7 +564,8 @@ def decompose_in_place(
                 trade_off_factor=trade_off_factor, reduction_factor=reduction_factor,
                 max_accepted_ppl_diff=max_accepted_ppl_diff, min_rank=min_rank,
                 decompose_in_float64=decompose_in_float64,
-                u_matrix=u_dict.pop(name) if len(u_dict) > 0 else None, trace=trace)
+                u_matrix=u_dict.pop(name) if len(u_dict) > 0 else None, trace=trace,
+                pair_state=pair_state)
             logger.info(f"stop reserved gpu mem={utils.get_gpu_reserved_memory_gb():.2f} GB")
         current_params -= result.get("drop_in_params", 0)
         logger.info(f"CURRENT PARAMS IN M: {current_params / 1e6}")

@@ -136,16 +136,23 @@ def _compute_metrics(
     orig_weight: torch.Tensor,
     deco_weight: torch.Tensor,
     forward_fn=None,
+    pair_state: Optional[_wrap.PairState] = None,
 ) -> tuple[torch.Tensor, torch.Tensor]:
-    """F:211-233: two full forwards (decomposed weight, original weight), NSR over the batch dim
-    and symmetric-max KL of the logits; both returned as 0-dim device tensors (no host sync)."""
+    """F:211-233: two full forwards (decomposed weight, original weight) -- or, once `pair_state`
+    has verified it on this model, one forward of the doubled batch (see _wrap.PairState) -- then
+    NSR over the batch dim and symmetric-max KL of the logits; both returned as 0-dim device
+    tensors (no host sync)."""
     assert isinstance(decomposed_submodule, WrappedFALORModule)
     root_module.eval()
     forward_fn = forward_fn or root_module
-    decomposed_submodule.set_weight(deco_weight)
-    y_deco = forward_fn(x)
-    decomposed_submodule.set_weight(orig_weight)
-    y_orig = forward_fn(x)
+    if pair_state is not None and getattr(forward_fn, "recorder", None) is None:
+        y_deco, y_orig = pair_state.forward_pair(forward_fn, decomposed_submodule, x, orig_weight,
+                                                 deco_weight)
+    else:
+        decomposed_submodule.set_weight(deco_weight)
+        y_deco = forward_fn(x)
+        decomposed_submodule.set_weight(orig_weight)
+        y_orig = forward_fn(x)
     nsr_final = utils.calc_per_channel_noise_to_signal_ratio(y=y_orig, x=y_deco, non_channel_dim=(0,))
     kl_final = utils.calc_kl_loss(y_deco, y_orig)
     return nsr_final, kl_final
@@ -185,6 +192,7 @@ def _process_module(
     use_damping: bool,
     trace: Optional[list] = None,
     forward_fn=None,
+    pair_state: Optional[_wrap.PairState] = None,
 ) -> dict[str, Any]:
     """F:284-399: covariance -> eigenvectors -> bisection on the rank. `trace` (not in the
     reference) collects one record per trial for the parity harness."""
@@ -237,7 +245,8 @@ def _process_module(
             x = next(data_iterator).to(device)
             nsr_sample, kl_sample = _compute_metrics(
                 x=x, root_module=root_module, decomposed_submodule=wrapper,
-                orig_weight=orig_weight, deco_weight=deco_weight, forward_fn=forward_fn)
+                orig_weight=orig_weight, deco_weight=deco_weight, forward_fn=forward_fn,
+                pair_state=pair_state)
             nsr_acc += nsr_sample.double()
             kl_acc += kl_sample.double()
         nsr_new, kl_new = (torch.stack([nsr_acc, kl_acc]) / num_metric_steps).tolist()  # one sync
@@ -324,6 +333,7 @@ def decompose_in_place(
     if not forward_fn.enabled:
         recorder.close()
         forward_fn.recorder = None
+    pair_state = _wrap.PairState()
     for i, name in enumerate(names, start=1):
         msg_prefix = f"Processing {name}: module {i} of {n}"
         if name in blacklisted_module_names:
@@ -336,7 +346,7 @@ def decompose_in_place(
                 nsr_final_threshold=nsr_final_threshold, kl_final_threshold=kl_final_threshold,
                 num_data_steps=num_data_steps, num_metric_steps=num_metric_steps, device=device,
                 use_float64=use_float64, use_mean=use_mean, use_damping=use_damping, trace=trace,
-                forward_fn=forward_fn)
+                forward_fn=forward_fn, pair_state=pair_state)
     recorder.close()
     del forward_fn
 

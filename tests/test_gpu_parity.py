@@ -349,6 +349,48 @@ def test_lowrank_sequential_matches_torch_sequential(dev, dtype, tol):
     assert (out_c.float() - ref_c).abs().max() <= tol * ref_c.abs().max()
 
 
+def test_paired_trials_verify_before_pairing(dev):
+    """_wrap.PairState: one forward of the doubled batch replaces the trial's two forwards only
+    after the first batch was evaluated both ways and agreed; a model whose forward mixes batch
+    elements keeps the reference's two-forward path."""
+    import ptdeco_b200.falor.decomposition as F
+    from ptdeco_b200 import _wrap
+
+    class Net(torch.nn.Module):
+        def __init__(self, mix):
+            super().__init__()
+            self.fc1, self.fc2, self.mix = torch.nn.Linear(24, 40), torch.nn.Linear(40, 7), mix
+
+        def forward(self, x):
+            h = torch.relu(self.fc1(x))
+            if self.mix:
+                h = h - h.mean(0, keepdim=True)
+            return self.fc2(h)
+
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(6, 24, generator=g).to(dev)
+    for mix, want in ((False, "on"), (True, "off")):
+        torch.manual_seed(3)
+        net = Net(mix).to(dev).eval()
+        F._wrap_in_place(net, "fc1")
+        wrapper = net.get_submodule("fc1")
+        w = wrapper.get_weight_copy()
+        deco = w * 0.5
+        st = _wrap.PairState()
+        with torch.no_grad():
+            y_deco, y_orig = st.forward_pair(net, wrapper, x, w, deco)
+            assert st.mode == want
+            wrapper.set_weight(deco)
+            ref_deco = net(x)
+            wrapper.set_weight(w)
+            ref_orig = net(x)
+            assert torch.allclose(y_deco, ref_deco, atol=1e-5) and torch.allclose(y_orig, ref_orig, atol=1e-5)
+            y_deco2, y_orig2 = st.forward_pair(net, wrapper, x, w, deco)  # second batch: paired iff verified
+            assert (st.paired_forwards == 2) == (want == "on")
+            assert torch.allclose(y_deco2, ref_deco, atol=1e-5) and torch.allclose(y_orig2, ref_orig, atol=1e-5)
+            assert torch.equal(wrapper.get_weight_copy(), w) and wrapper.pair_weight is None
+
+
 # ------------------------------------------------------------------------------------ K6
 def test_metrics_match_reference(dev, golden_dir):
     from ptdeco_b200 import utils
