@@ -81,7 +81,12 @@ int ptdeco_eigh(const float* A, int d, long long lda, int k, float* evals, float
  * Replaces the forward of the nn.Sequential(Linear(in->k, no bias), Linear(k->out, bias)) built at
  * F:84-95 / D:74-85 (and its 1x1-conv twin on NHWC rows):
  * Y[n][ldy] = (X[n][ldx] W1[k][ldw1]^T) W2[out][ldw2]^T + bias[out]; X, W1, W2, Y of `dtype`,
- * bias fp32 or NULL. */
+ * bias fp32 or NULL.
+ * Three kernels behind the one entry point (bf16): n <= 128 with >= 2 MB of factors runs the
+ * single-launch weight-streaming kernel (needs the workspace: fp32 partial sums, bf16 intermediate,
+ * grid-barrier / ticket words; zeroed by the call); k <= 256 runs the fused kernel that keeps the
+ * [128, k] intermediate on chip (no workspace); everything else, and fp32, runs two tcgen05 GEMMs
+ * with the intermediate in the workspace. */
 size_t ptdeco_lowrank_workspace_bytes(int dtype, long long n, int in_features, int k,
                                       int out_features);
 int ptdeco_lowrank_forward(const void* X, long long ldx, const void* W1, long long ldw1,

@@ -173,13 +173,15 @@ class PairState:
     launches (small models are launch-bound) and better-filled GEMMs.
 
     Safety: the first trial batch of a decompose call is evaluated BOTH ways; pairing is kept only
-    if the two agree (relative Frobenius error of the logits within the dtype's rounding noise),
-    so a model with a batch-dependent forward or an unusual batch layout silently keeps the
-    reference's two-forward path. PTDECO_B200_PAIRED_TRIALS=0 disables pairing."""
+    if the two agree (relative Frobenius error of the logits within the dtype's rounding noise)
+    and the paired forward is measurably faster, so a model with a batch-dependent forward, an
+    unusual batch layout, or a forward that already fills the GPU (an LLM at 2048 tokens: measured
+    slower paired) keeps the reference's two-forward path. PTDECO_B200_PAIRED_TRIALS=0 disables it."""
 
     def __init__(self) -> None:
         self.mode = "off" if os.environ.get("PTDECO_B200_PAIRED_TRIALS", "1") == "0" else "unknown"
         self.paired_forwards = 0
+        self.probe: Optional[dict] = None  # what the verification measured
 
     @staticmethod
     def _double(inputs: Any) -> tuple[Optional[Any], int]:
@@ -218,18 +220,37 @@ class PairState:
             if out is not None:
                 return out
             self.mode = "off"
+        probing = self.mode == "unknown" and deco_weight.is_cuda
+        if probing:
+            torch.cuda.synchronize(deco_weight.device)
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            e[0].record()
         wrapper.set_weight(deco_weight)
         y_deco = forward_fn(inputs)
         wrapper.set_weight(orig_weight)
         y_orig = forward_fn(inputs)
-        if self.mode == "unknown":
+        if probing:
+            # First trial batch of the call: evaluate it the paired way too (once to warm the
+            # allocator up for the doubled shapes, once timed). Pairing is kept only if the results
+            # agree AND the paired forward is faster -- it halves kernel launches, which pays for
+            # launch-bound models and not for ones whose forward already fills the GPU.
+            e[1].record()
             self.mode = "off"
             out = self._paired(forward_fn, wrapper, inputs, deco_weight)
             if out is not None and isinstance(y_orig, torch.Tensor) and out[0].shape == y_deco.shape:
+                e[2].record()
+                out = self._paired(forward_fn, wrapper, inputs, deco_weight)
+                e[3].record()
                 tol = 1e-4 if y_orig.dtype in (torch.float32, torch.float64) else 3e-2
                 ref = torch.linalg.vector_norm(y_orig.float()).clamp_min(1e-30)
                 err = max(float(torch.linalg.vector_norm(out[0].float() - y_deco.float()) / ref),
                           float(torch.linalg.vector_norm(out[1].float() - y_orig.float()) / ref))
-                if err <= tol:  # NaN fails the comparison and keeps pairing off
+                self.probe = {"rel_err": err, "two_forwards_ms": e[0].elapsed_time(e[1]),
+                              "paired_ms": e[2].elapsed_time(e[3])}
+                # NaN fails the comparisons and keeps pairing off
+                if err <= tol and self.probe["paired_ms"] < 0.9 * self.probe["two_forwards_ms"]:
                     self.mode = "on"
+            self.paired_forwards = 0
+        elif self.mode == "unknown":
+            self.mode = "off"
         return y_deco, y_orig

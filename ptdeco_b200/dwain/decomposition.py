@@ -455,7 +455,7 @@ def _precompute_covariance_matrix_decompositions(
             if step % world != rank:
                 continue
             _ = module(utils.to_device(batch, device))
-    utils.free_gpu_reserved_memory()
+    utils.relieve_gpu_memory_pressure()
 
     logger.info("Computing eigenvectors ...")
     u_dict: dict[str, torch.Tensor] = {}
@@ -465,7 +465,7 @@ def _precompute_covariance_matrix_decompositions(
         u_dict[name] = parallel.owner_computes(
             idx, group, lambda: sub.get_eigenvectors(k, group=None), sub.acc, (sub.out_features, k))
     _restore_modules(module, originals)
-    utils.free_gpu_reserved_memory()
+    utils.relieve_gpu_memory_pressure()
     return u_dict
 
 
@@ -549,7 +549,7 @@ def decompose_in_place(
     else:
         logger.info("Skipping precomputing convariance matrices")
         u_dict = {}
-    utils.free_gpu_reserved_memory()
+    utils.relieve_gpu_memory_pressure()
     pair_state = _wrap.PairState()
 
     for i, name in enumerate(reversed(names), start=1):
@@ -575,13 +575,13 @@ def decompose_in_place(
             decomposed_submodules.append(name)
             utils.replace_submodule_in_place(module, name, new_module)
             module = finetune_fn(module, device, decomposed_submodules)
-            utils.free_gpu_reserved_memory()
+            utils.relieve_gpu_memory_pressure()
             module_config = utils.get_module_config(new_module)
             _add_meta_to_module_config(module_config, result)
             decompose_config[name] = module_config
             logger.info(f"{name} decomposed with rank {proportion=:.4f}")
             n_decomposed += 1
-        utils.free_gpu_reserved_memory()
+        utils.relieve_gpu_memory_pressure()
 
     logger.info(f"Decomposed {n_decomposed} out of {n} modules")
     logger.info(f"Decomposition took {time.perf_counter() - start_time:.1f} seconds")

@@ -11,6 +11,7 @@ __all__ = [
     "to_device",
     "get_gpu_reserved_memory_gb",
     "free_gpu_reserved_memory",
+    "relieve_gpu_memory_pressure",
     "get_num_params",
     "is_compound_module",
     "get_type_name",
@@ -50,6 +51,23 @@ def free_gpu_reserved_memory() -> None:
     torch.cuda.empty_cache()
     after = get_gpu_reserved_memory_gb()
     logger.info(f"GPU memory: {before:.2f} -> {after:.2f} GB ({(after - before):.2f} GB)")
+
+
+def relieve_gpu_memory_pressure(threshold: float = 0.6) -> bool:
+    """The reference calls free_gpu_reserved_memory() (gc.collect + empty_cache) between layers
+    (D:737,787,795) so that a fragmented caching allocator does not run a small GPU out of memory.
+    Each call costs a Python GC pass plus re-cudaMalloc of every activation on the next forward
+    (measured ~0.1 s per call on the 8B-shape model: tens of seconds over 224 layers). Here the
+    cache is dropped only when the current device's reserved memory exceeds `threshold` of its
+    capacity. Returns whether it was dropped."""
+    if not torch.cuda.is_available():
+        return False
+    dev = torch.cuda.current_device()
+    total = torch.cuda.get_device_properties(dev).total_memory
+    if torch.cuda.memory_reserved(dev) <= threshold * total:
+        return False
+    free_gpu_reserved_memory()
+    return True
 
 
 def get_num_params(m: torch.nn.Module, only_trainable: bool = False) -> int:
