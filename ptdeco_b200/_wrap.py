@@ -7,6 +7,7 @@ consumes directly, so the projection y = x W^T is not recomputed outside the mod
 """
 from __future__ import annotations
 
+import logging
 import os
 from typing import Any, Optional
 
@@ -250,6 +251,9 @@ class PairState:
                 # NaN fails the comparisons and keeps pairing off
                 if err <= tol and self.probe["paired_ms"] < 0.9 * self.probe["two_forwards_ms"]:
                     self.mode = "on"
+                logging.getLogger("ptdeco.utils.common").info(
+                    f"paired rank trials {self.mode}: rel_err={err:.2e} "
+                    f"two_forwards={self.probe['two_forwards_ms']:.2f} ms paired={self.probe['paired_ms']:.2f} ms")
             self.paired_forwards = 0
         elif self.mode == "unknown":
             self.mode = "off"
