@@ -805,7 +805,16 @@ lowrank_decode_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_con
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (*last_flag) {
         __threadfence();
-        if ((g.npad & 31) == 0) {  // 32 independent loads in flight, then the stores
+        if ((g.npad & 63) == 0) {  // 64 independent loads in flight, then the stores
+          for (int n0 = 0; n0 < g.npad; n0 += 64) {
+            float v[64];
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = __ldcg(g.H + static_cast<long long>(n0 + j) * g.ldh + kcol);
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+              g.Hb[static_cast<long long>(n0 + j) * g.ldh + kcol] = __float2bfloat16_rn(v[j]);
+          }
+        } else if ((g.npad & 31) == 0) {  // 32 independent loads in flight, then the stores
           for (int n0 = 0; n0 < g.npad; n0 += 32) {
             float v[32];
 #pragma unroll

@@ -630,3 +630,53 @@ def test_full_size_properties_d4096(dev):
     assert abs(ev.double().sum().item() - tr) / tr < 1e-4
     resid = (cov.double() @ ud - ud * ev[d - k:].double()).abs().max().item() / ev.max().item()
     assert resid < 5e-5
+
+
+def test_full_size_syrk_d14336_properties(dev):
+    """The bench's dominant launch (d = 14336, 16384 staged bf16 tokens, CTA-pair kernel) checked
+    through size-independent properties against fp64 on the device: trace(C) = mean ||y||^2,
+    C v = Y^T (Y v) / N for random v, symmetry after finalize, and linearity in the batches
+    (accumulating two batches = one launch over their concatenation)."""
+    from ptdeco_b200 import linalg
+    d, n = 14336, 8192
+    g = torch.Generator(device=dev).manual_seed(99)
+    scale = torch.logspace(0, -1.5, d, device=dev)
+    ya = (torch.randn(n, d, generator=g, device=dev) * scale).to(torch.bfloat16)
+    yb = (torch.randn(n, d, generator=g, device=dev) * scale).to(torch.bfloat16)
+    acc = linalg.CovarianceAccumulator(d, dev, defer_rows=2 * n)  # one 16384-token launch
+    acc.update(ya)
+    acc.update(yb)
+    two = linalg.CovarianceAccumulator(d, dev)  # two 8192-token launches
+    two.update(ya)
+    two.update(yb)
+    assert acc.launches == 1 and two.launches == 2
+    c1 = acc.finalize(False, 0.0)
+    c2 = two.finalize(False, 0.0)
+    assert torch.equal(c1, c1.T)
+    tr_ref = ((ya.double() ** 2).sum() + (yb.double() ** 2).sum()) / n / 2
+    assert abs(float(torch.trace(c1.double()) - tr_ref)) <= COV_TOL * float(tr_ref)
+    v = torch.randn(d, 4, generator=g, device=dev, dtype=torch.float64)
+    ref = (ya.double().T @ (ya.double() @ v) + yb.double().T @ (yb.double() @ v)) / n / 2
+    got = c1.double() @ v
+    assert float((got - ref).norm() / ref.norm()) <= COV_TOL
+    assert float((c1 - c2).norm() / c2.norm()) <= 2e-6
+
+
+def test_full_size_decode_forward_70b_shapes(dev):
+    """Decode-size forward at a Llama-3-70B MLP shape (in 8192, out 28672, k 3584, N = 16 and 128):
+    linearity in x and agreement with an fp32 torch product that rounds the intermediate to bf16."""
+    from ptdeco_b200 import linalg
+    in_f, out_f, k = 8192, 28672, 3584
+    g = torch.Generator(device=dev).manual_seed(123)
+    w1 = (torch.randn(k, in_f, generator=g, device=dev) / in_f ** 0.5).to(torch.bfloat16)
+    w2 = (torch.randn(out_f, k, generator=g, device=dev) / k ** 0.5).to(torch.bfloat16)
+    b = torch.randn(out_f, generator=g, device=dev)
+    for n in (16, 128):
+        x = torch.randn(n, in_f, generator=g, device=dev).to(torch.bfloat16)
+        y = linalg.lowrank_forward(x, w1, w2, b).float()
+        h = (x.float() @ w1.float().T).to(torch.bfloat16).float()
+        ref = h @ w2.float().T + b
+        assert float((y - ref).abs().max() / ref.abs().max()) <= 1e-2
+        y2 = linalg.lowrank_forward((2 * x), w1, w2, None).float()  # exact in bf16: doubling x
+        y1 = linalg.lowrank_forward(x, w1, w2, None).float()
+        assert float((y2 - 2 * y1).abs().max() / y2.abs().max()) <= 1e-2
