@@ -9,7 +9,7 @@ from ptdeco_b200 import linalg
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 k = int(sys.argv[2]) if len(sys.argv) > 2 else 128
-fin = fout = 4096
+fin = fout = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
 g = torch.Generator(device="cuda").manual_seed(0)
 x = torch.randn(n, fin, generator=g, device="cuda").to(torch.bfloat16)
 w1 = (torch.randn(k, fin, generator=g, device="cuda") / 64).to(torch.bfloat16)
