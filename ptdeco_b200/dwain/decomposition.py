@@ -55,171 +55,93 @@ is_decomposeable_module = _wrap.is_decomposeable_module
 _is_num_params_reduced = _wrap.is_num_params_reduced
 
 
-def _max_rank_consumed(dim_in: int, dim_out: int, reduction_factor: float) -> int:
-    """Largest rank the descent of D:407-408 can ask for: int(full_rank * reduction_factor)."""
-    full_rank = min(dim_in, dim_out)
-    return max(1, min(full_rank, int(full_rank * reduction_factor)))
-
-
-def _update_Eyyt_in_place(acc: linalg.CovarianceAccumulator, y_reshaped: torch.Tensor,
-                          sub: Optional[torch.Tensor] = None) -> None:
-    """D:147-152: Eyyt += y^T y / N for one batch of rows."""
-    acc.update(y_reshaped, sub=sub)
-
-
-def _get_eigenvectors(acc: linalg.CovarianceAccumulator, num_vectors: Optional[int] = None,
-                      group=None) -> torch.Tensor:
-    """D:155-163 on the accumulated covariance: /steps, damping 0.01*mean(diag), eigenvectors
-    ascending (all, or the last `num_vectors`). With a process group the partial covariances are
-    summed over ranks first."""
-    parallel.allreduce_accumulator(acc, group)
-    cov = acc.finalize(use_mean=False, damp_factor=EIGEN_DAMPEN_FACTOR)
-    _, u = linalg.eigh(cov, k=num_vectors)
-    return u
-
-
-class CovarianceComputingLinearModule(torch.nn.Module):
-    """D:166-208: stands in for a target Linear during the precompute pass; its forward IS the
-    layer forward (y = x W^T on the tcgen05 GEMM engine) and folds the layer's activations into
-    the covariance: the output y like the reference, or -- when in < out and only eigenvectors in
-    range(W) are wanted -- the input x (linalg.eigvecs_from_input_covariance)."""
-
-    def __init__(self, weight: torch.nn.Parameter, bias: Optional[torch.nn.Parameter],
-                 decompose_in_float64: bool, num_vectors: Optional[int] = None):
-        super().__init__()
-        self.weight = weight
-        self.bias = bias
-        self.in_features = weight.shape[1]
-        self.out_features = weight.shape[0]
-        self.input_side = linalg.use_input_side(self.in_features, self.out_features, num_vectors)
-        d = self.in_features if self.input_side else self.out_features
-        self.acc = linalg.CovarianceAccumulator(
-            d, weight.device, defer_rows=linalg.default_defer_rows(d, weight.element_size()))
-        self.use_float64 = decompose_in_float64  # accepted; see falor's use_float64 note
-
-    @property
-    def num_data_steps(self) -> int:
-        return self.acc.steps
-
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        rows = x.reshape(-1, self.in_features)
-        y_rows = linalg.linear_nt(rows, self.weight.detach())
-        _update_Eyyt_in_place(self.acc, rows if self.input_side else y_rows)
-        y = y_rows.reshape(*x.shape[:-1], self.out_features)
-        if self.bias is not None:
-            y = y + self.bias
-        return y
-
-    def get_eigenvectors(self, num_vectors: Optional[int] = None, group=None) -> torch.Tensor:
-        """Unlike D:206-208 the result stays on the GPU in fp32 (180 GB of HBM make the reference's
-        round trip through host memory unnecessary); the rank search casts what it slices."""
-        if self.input_side:
-            return _get_eigenvectors_input_side(self.acc, self.weight.detach(), num_vectors, group)
-        return _get_eigenvectors(self.acc, num_vectors, group)
-
-
-def _get_eigenvectors_input_side(acc: linalg.CovarianceAccumulator, weight: torch.Tensor,
-                                 num_vectors: int, group=None) -> torch.Tensor:
-    parallel.allreduce_accumulator(acc, group)
-    s_cov = acc.finalize(use_mean=False, damp_factor=0.0)
-    return linalg.eigvecs_from_input_covariance(s_cov, weight, num_vectors)
-
-
-def _compute_covariance_matrix_decomposition(
+def decompose_in_place(
     *,
-    root_module: torch.nn.Module,
-    decomposed_submodule_name: str,
-    data_iterator: collections.abc.Iterator[dict[str, torch.Tensor]],
-    weight: torch.Tensor,
-    num_data_steps: int,
+    module: torch.nn.Module,
     device: torch.device,
-    decompose_in_float64: bool,
-    num_vectors: Optional[int] = None,
-) -> torch.Tensor:
-    """D:211-244: per-layer calibration (num_data_steps full forwards) -> eigenvectors."""
-    root_module.eval()
-    wrapper = root_module.get_submodule(decomposed_submodule_name)
-    assert isinstance(wrapper, WrappedDWAINModule)
-    logger.info("Using float64 for decomposition" if decompose_in_float64
-                else "Using float32 for decomposition")
-    input_side = linalg.use_input_side(weight.shape[1], weight.shape[0], num_vectors)
-    d = weight.shape[1] if input_side else weight.shape[0]
-    acc = linalg.CovarianceAccumulator(
-        d, device, defer_rows=linalg.default_defer_rows(d, weight.element_size()))
-    wrapper.capture_output = not input_side
-    try:
-        for _ in range(num_data_steps):
-            inputs = utils.to_device(next(data_iterator), device)
-            _ = root_module(inputs)
-            if input_side:
-                _update_Eyyt_in_place(acc, wrapper.get_last_input())
-            else:
-                _update_Eyyt_in_place(acc, wrapper.get_last_output_rows(), sub=wrapper.get_bias())
-    finally:
-        wrapper.capture_output = False
-        wrapper.output = None
-    if input_side:
-        return _get_eigenvectors_input_side(acc, weight, num_vectors)
-    return _get_eigenvectors(acc, num_vectors)
-
-
-def _compute_metrics(
-    *,
-    input_dict: dict[str, torch.Tensor],
-    root_module: torch.nn.Module,
-    decomposed_submodule: torch.nn.Module,
-    orig_weight: torch.Tensor,
-    deco_weight: torch.Tensor,
+    data_iterator: collections.abc.Iterator[dict[str, torch.Tensor]],
     loss_fn: collections.abc.Callable[[dict[str, torch.Tensor], torch.Tensor], torch.Tensor],
-    pair_state: Optional[_wrap.PairState] = None,
-) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """D:247-278. With a verified `pair_state` the two forwards share one pass over the doubled
-    batch (see _wrap.PairState); the losses are still taken per variant on the original batch."""
-    assert isinstance(input_dict, dict)
-    assert isinstance(decomposed_submodule, WrappedDWAINModule)
-    root_module.eval()
-    if pair_state is not None:
-        y_deco, y_orig = pair_state.forward_pair(root_module, decomposed_submodule, input_dict,
-                                                 orig_weight, deco_weight)
+    num_data_steps: int,
+    metric_iterator: collections.abc.Iterator[dict[str, torch.Tensor]],
+    num_metric_steps: int,
+    blacklisted_module_names: Optional[list[str]] = None,
+    nsr_final_threshold: float,
+    finetune_fn: collections.abc.Callable[[torch.nn.Module, torch.device, list[str]], torch.nn.Module],
+    min_rank: int = 32,
+    trade_off_factor: float = 0.5,
+    reduction_factor: float = 0.5,
+    max_accepted_ppl_diff: float = 0.1,
+    decompose_in_float64: bool = True,
+    precomputing_covariance_num_splits: Optional[int] = None,
+    trace: Optional[list] = None,
+) -> dict[str, Any]:
+    """D:677-800. Returns the decompose_config (insertion order = reversed module order)."""
+    start_time = time.perf_counter()
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise nat.NativeError("ptdeco_b200.dwain runs on CUDA (sm_100a) only; there is no CPU path")
+    nat.lib()
+    num_params = utils.get_num_params(module)
+    current_params = num_params
+    if blacklisted_module_names is None:
+        blacklisted_module_names = []
+    names = _get_decomposeable_submodule_names(module, blacklisted_module_names)
+    n = len(names)
+    n_decomposed = 0
+    logger.info("\n".join([f"There are {n} linear modules that can be decomposed:"]
+                          + [f"  {i}. {nm}" for i, nm in enumerate(names, start=1)]))
+
+    decompose_config: dict[str, Any] = {}
+    decomposed_submodules: list[str] = []
+    group = parallel.default_group()
+
+    if precomputing_covariance_num_splits is not None and precomputing_covariance_num_splits > 0:
+        u_dict = _precompute_covariance_matrix_decompositions_in_splits(
+            module=module, modules_to_decompose=names,
+            num_splits=precomputing_covariance_num_splits, data_iterator=data_iterator,
+            num_data_steps=num_data_steps, device=device,
+            decompose_in_float64=decompose_in_float64, reduction_factor=reduction_factor,
+            group=group)
     else:
-        decomposed_submodule.set_weight(deco_weight)
-        y_deco = root_module(input_dict)
-        decomposed_submodule.set_weight(orig_weight)
-        y_orig = root_module(input_dict)
-    loss_deco = loss_fn(input_dict, y_deco)
-    loss_orig = loss_fn(input_dict, y_orig)
-    nsr_final = utils.calc_per_channel_noise_to_signal_ratio(
-        y=y_orig, x=y_deco, non_channel_dim=(0, 1), mode="mean")
-    ppl_deco = torch.exp(loss_deco).mean()
-    ppl_orig = torch.exp(loss_orig).mean()
-    return nsr_final, ppl_deco, ppl_orig
+        logger.info("Skipping precomputing convariance matrices")
+        u_dict = {}
+    utils.relieve_gpu_memory_pressure()
+    pair_state = _wrap.PairState()
 
+    for i, name in enumerate(reversed(names), start=1):
+        logger.info(f"PROCESSING {name} MODULE {i} OUT OF {n}")
+        with torch.no_grad():
+            logger.info(f"start reserved gpu mem={utils.get_gpu_reserved_memory_gb():.2f} GB")
+            result = _process_module(
+                root_module=module, decomposed_submodule_name=name, data_iterator=data_iterator,
+                loss_fn=loss_fn, metric_iterator=metric_iterator,
+                nsr_final_threshold=nsr_final_threshold, num_data_steps=num_data_steps,
+                num_metric_steps=num_metric_steps, device=device, num_params=num_params,
+                trade_off_factor=trade_off_factor, reduction_factor=reduction_factor,
+                max_accepted_ppl_diff=max_accepted_ppl_diff, min_rank=min_rank,
+                decompose_in_float64=decompose_in_float64,
+                u_matrix=u_dict.pop(name) if len(u_dict) > 0 else None, trace=trace,
+                pair_state=pair_state)
+            logger.info(f"stop reserved gpu mem={utils.get_gpu_reserved_memory_gb():.2f} GB")
+        current_params -= result.get("drop_in_params", 0)
+        logger.info(f"CURRENT PARAMS IN M: {current_params / 1e6}")
+        new_module = result["decomposed_module"]
+        proportion = result["proportion"]
+        if new_module is not None:
+            decomposed_submodules.append(name)
+            utils.replace_submodule_in_place(module, name, new_module)
+            module = finetune_fn(module, device, decomposed_submodules)
+            utils.relieve_gpu_memory_pressure()
+            module_config = utils.get_module_config(new_module)
+            _add_meta_to_module_config(module_config, result)
+            decompose_config[name] = module_config
+            logger.info(f"{name} decomposed with rank {proportion=:.4f}")
+            n_decomposed += 1
+        utils.relieve_gpu_memory_pressure()
 
-def _wrap_in_place(root_module: torch.nn.Module, decomposed_submodule_name: str) -> None:
-    """D:281-304."""
-    sub = root_module.get_submodule(decomposed_submodule_name)
-    if isinstance(sub, torch.nn.Linear):
-        wrapped: WrappedDWAINModule = WrappedDWAINLinear(sub, decomposed_submodule_name)
-    elif is_decomposeable_module(sub):
-        wrapped = WrappedDWAINConv2d1x1(sub, decomposed_submodule_name)
-    else:
-        raise ValueError(f"Cannot decompose {decomposed_submodule_name}={sub}")
-    utils.replace_submodule_in_place(root_module, decomposed_submodule_name, wrapped)
-
-
-def _unwrap_in_place(root_module: torch.nn.Module, decomposed_submodule_name: str) -> None:
-    """D:307-316."""
-    sub = root_module.get_submodule(decomposed_submodule_name)
-    assert isinstance(sub, WrappedDWAINModule)
-    utils.replace_submodule_in_place(root_module, decomposed_submodule_name, sub.get_orig_module())
-
-
-def _get_params_for_proportion(proportion: float, in_features: int, out_features: int) -> int:
-    """D:319-330 (int() truncation included)."""
-    baseline = in_features * out_features
-    original_rank = min(in_features, out_features)
-    proposed = (in_features + out_features) * proportion * original_rank
-    return int(proposed) if proposed < baseline else baseline
+    logger.info(f"Decomposed {n_decomposed} out of {n} modules")
+    logger.info(f"Decomposition took {time.perf_counter() - start_time:.1f} seconds")
+    return decompose_config
 
 
 def _process_module(
@@ -382,50 +304,74 @@ def _process_module(
             "drop_in_params": drop_in_params, "decomposed_module": new_module}
 
 
-def _get_decomposeable_submodule_names(module: torch.nn.Module,
-                                       blacklisted_module_names: list[str]) -> list[str]:
-    """D:549-559."""
-    res = []
-    for name, mod in module.named_modules():
-        if is_decomposeable_module(mod):
-            if name in blacklisted_module_names:
-                logger.info(f"Skipping blacklisted module {name}")
-            else:
-                res.append(name)
-    return res
+def _compute_metrics(
+    *,
+    input_dict: dict[str, torch.Tensor],
+    root_module: torch.nn.Module,
+    decomposed_submodule: torch.nn.Module,
+    orig_weight: torch.Tensor,
+    deco_weight: torch.Tensor,
+    loss_fn: collections.abc.Callable[[dict[str, torch.Tensor], torch.Tensor], torch.Tensor],
+    pair_state: Optional[_wrap.PairState] = None,
+) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """D:247-278. With a verified `pair_state` the two forwards share one pass over the doubled
+    batch (see _wrap.PairState); the losses are still taken per variant on the original batch."""
+    assert isinstance(input_dict, dict)
+    assert isinstance(decomposed_submodule, WrappedDWAINModule)
+    root_module.eval()
+    if pair_state is not None:
+        y_deco, y_orig = pair_state.forward_pair(root_module, decomposed_submodule, input_dict,
+                                                 orig_weight, deco_weight)
+    else:
+        decomposed_submodule.set_weight(deco_weight)
+        y_deco = root_module(input_dict)
+        decomposed_submodule.set_weight(orig_weight)
+        y_orig = root_module(input_dict)
+    loss_deco = loss_fn(input_dict, y_deco)
+    loss_orig = loss_fn(input_dict, y_orig)
+    nsr_final = utils.calc_per_channel_noise_to_signal_ratio(
+        y=y_orig, x=y_deco, non_channel_dim=(0, 1), mode="mean")
+    ppl_deco = torch.exp(loss_deco).mean()
+    ppl_orig = torch.exp(loss_orig).mean()
+    return nsr_final, ppl_deco, ppl_orig
 
 
-def _add_meta_to_module_config(module_config: dict[str, Any], module_deco_results: dict[str, Any]) -> None:
-    """D:562-566."""
-    module_config[utils.MODCONFIG_META_KEY] = {
-        k: v for k, v in module_deco_results.items() if k != "decomposed_module"}
+def _get_params_for_proportion(proportion: float, in_features: int, out_features: int) -> int:
+    """D:319-330 (int() truncation included)."""
+    baseline = in_features * out_features
+    original_rank = min(in_features, out_features)
+    proposed = (in_features + out_features) * proportion * original_rank
+    return int(proposed) if proposed < baseline else baseline
 
 
-def _install_covariance_modules(module: torch.nn.Module, submodule_names: list[str],
-                                decompose_in_float64: bool,
-                                reduction_factor: Optional[float] = None) -> dict[str, torch.nn.Module]:
-    """D:592-603: swap every listed Linear for a CovarianceComputingLinearModule that shares its
-    weight and bias. Returns the originals for _restore_modules."""
-    originals: dict[str, torch.nn.Module] = {}
-    for name in submodule_names:
-        old = module.get_submodule(name)
-        if not isinstance(old, torch.nn.Linear):
-            # the reference crashes here on 1x1 convs (D:194 with a 4-D weight)
-            raise ValueError(f"covariance precompute supports Linear targets only, got {name}={old}")
-        originals[name] = old
-        logger.info(f"Replacing {name} by covariance computing wrapper")
-        k = (None if reduction_factor is None
-             else _max_rank_consumed(old.in_features, old.out_features, reduction_factor))
-        utils.replace_submodule_in_place(
-            module, name, CovarianceComputingLinearModule(old.weight, old.bias, decompose_in_float64, k))
-    return originals
-
-
-def _restore_modules(module: torch.nn.Module, originals: dict[str, torch.nn.Module]) -> None:
-    """D:624-630."""
-    for name, old in originals.items():
-        logger.info(f"Replacing {name} by original linear")
-        utils.replace_submodule_in_place(module, name, old)
+def _precompute_covariance_matrix_decompositions_in_splits(
+    *,
+    module: torch.nn.Module,
+    modules_to_decompose: list[str],
+    num_splits: int,
+    num_data_steps: int,
+    data_iterator: collections.abc.Iterator[dict[str, torch.Tensor]],
+    device: torch.device,
+    decompose_in_float64: bool,
+    reduction_factor: float = 1.0,
+    group=None,
+) -> dict[str, torch.Tensor]:
+    """D:636-674: chunks of len // num_splits names, plus one more partition for the remainder."""
+    chunk_size = len(modules_to_decompose) // num_splits
+    if chunk_size == 0:
+        chunk_size = 1
+        num_splits = len(modules_to_decompose)
+    num_partitions = num_splits if len(modules_to_decompose) % num_splits == 0 else num_splits + 1
+    u_dict: dict[str, torch.Tensor] = {}
+    for p in range(num_partitions):
+        sublist = modules_to_decompose[p * chunk_size:(p + 1) * chunk_size]
+        logger.info(f"Pre computing covariance matrices for {len(sublist)} modules")
+        u_dict.update(_precompute_covariance_matrix_decompositions(
+            module=module, submodule_names=sublist, num_data_steps=num_data_steps,
+            data_iterator=data_iterator, device=device, decompose_in_float64=decompose_in_float64,
+            reduction_factor=reduction_factor, group=group))
+    assert len(u_dict) == len(modules_to_decompose)
+    return u_dict
 
 
 def _precompute_covariance_matrix_decompositions(
@@ -469,120 +415,174 @@ def _precompute_covariance_matrix_decompositions(
     return u_dict
 
 
-def _precompute_covariance_matrix_decompositions_in_splits(
+def _install_covariance_modules(module: torch.nn.Module, submodule_names: list[str],
+                                decompose_in_float64: bool,
+                                reduction_factor: Optional[float] = None) -> dict[str, torch.nn.Module]:
+    """D:592-603: swap every listed Linear for a CovarianceComputingLinearModule that shares its
+    weight and bias. Returns the originals for _restore_modules."""
+    originals: dict[str, torch.nn.Module] = {}
+    for name in submodule_names:
+        old = module.get_submodule(name)
+        if not isinstance(old, torch.nn.Linear):
+            # the reference crashes here on 1x1 convs (D:194 with a 4-D weight)
+            raise ValueError(f"covariance precompute supports Linear targets only, got {name}={old}")
+        originals[name] = old
+        logger.info(f"Replacing {name} by covariance computing wrapper")
+        k = (None if reduction_factor is None
+             else _max_rank_consumed(old.in_features, old.out_features, reduction_factor))
+        utils.replace_submodule_in_place(
+            module, name, CovarianceComputingLinearModule(old.weight, old.bias, decompose_in_float64, k))
+    return originals
+
+
+def _restore_modules(module: torch.nn.Module, originals: dict[str, torch.nn.Module]) -> None:
+    """D:624-630."""
+    for name, old in originals.items():
+        logger.info(f"Replacing {name} by original linear")
+        utils.replace_submodule_in_place(module, name, old)
+
+
+class CovarianceComputingLinearModule(torch.nn.Module):
+    """D:166-208: stands in for a target Linear during the precompute pass; its forward IS the
+    layer forward (y = x W^T on the tcgen05 GEMM engine) and folds the layer's activations into
+    the covariance: the output y like the reference, or -- when in < out and only eigenvectors in
+    range(W) are wanted -- the input x (linalg.eigvecs_from_input_covariance)."""
+
+    def __init__(self, weight: torch.nn.Parameter, bias: Optional[torch.nn.Parameter],
+                 decompose_in_float64: bool, num_vectors: Optional[int] = None):
+        super().__init__()
+        self.weight = weight
+        self.bias = bias
+        self.in_features = weight.shape[1]
+        self.out_features = weight.shape[0]
+        self.input_side = linalg.use_input_side(self.in_features, self.out_features, num_vectors)
+        d = self.in_features if self.input_side else self.out_features
+        self.acc = linalg.CovarianceAccumulator(
+            d, weight.device, defer_rows=linalg.default_defer_rows(d, weight.element_size()))
+        self.use_float64 = decompose_in_float64  # accepted; see falor's use_float64 note
+
+    @property
+    def num_data_steps(self) -> int:
+        return self.acc.steps
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        rows = x.reshape(-1, self.in_features)
+        y_rows = linalg.linear_nt(rows, self.weight.detach())
+        _update_Eyyt_in_place(self.acc, rows if self.input_side else y_rows)
+        y = y_rows.reshape(*x.shape[:-1], self.out_features)
+        if self.bias is not None:
+            y = y + self.bias
+        return y
+
+    def get_eigenvectors(self, num_vectors: Optional[int] = None, group=None) -> torch.Tensor:
+        """Unlike D:206-208 the result stays on the GPU in fp32 (180 GB of HBM make the reference's
+        round trip through host memory unnecessary); the rank search casts what it slices."""
+        if self.input_side:
+            return _get_eigenvectors_input_side(self.acc, self.weight.detach(), num_vectors, group)
+        return _get_eigenvectors(self.acc, num_vectors, group)
+
+
+def _compute_covariance_matrix_decomposition(
     *,
-    module: torch.nn.Module,
-    modules_to_decompose: list[str],
-    num_splits: int,
-    num_data_steps: int,
+    root_module: torch.nn.Module,
+    decomposed_submodule_name: str,
     data_iterator: collections.abc.Iterator[dict[str, torch.Tensor]],
+    weight: torch.Tensor,
+    num_data_steps: int,
     device: torch.device,
     decompose_in_float64: bool,
-    reduction_factor: float = 1.0,
-    group=None,
-) -> dict[str, torch.Tensor]:
-    """D:636-674: chunks of len // num_splits names, plus one more partition for the remainder."""
-    chunk_size = len(modules_to_decompose) // num_splits
-    if chunk_size == 0:
-        chunk_size = 1
-        num_splits = len(modules_to_decompose)
-    num_partitions = num_splits if len(modules_to_decompose) % num_splits == 0 else num_splits + 1
-    u_dict: dict[str, torch.Tensor] = {}
-    for p in range(num_partitions):
-        sublist = modules_to_decompose[p * chunk_size:(p + 1) * chunk_size]
-        logger.info(f"Pre computing covariance matrices for {len(sublist)} modules")
-        u_dict.update(_precompute_covariance_matrix_decompositions(
-            module=module, submodule_names=sublist, num_data_steps=num_data_steps,
-            data_iterator=data_iterator, device=device, decompose_in_float64=decompose_in_float64,
-            reduction_factor=reduction_factor, group=group))
-    assert len(u_dict) == len(modules_to_decompose)
-    return u_dict
+    num_vectors: Optional[int] = None,
+) -> torch.Tensor:
+    """D:211-244: per-layer calibration (num_data_steps full forwards) -> eigenvectors."""
+    root_module.eval()
+    wrapper = root_module.get_submodule(decomposed_submodule_name)
+    assert isinstance(wrapper, WrappedDWAINModule)
+    logger.info("Using float64 for decomposition" if decompose_in_float64
+                else "Using float32 for decomposition")
+    input_side = linalg.use_input_side(weight.shape[1], weight.shape[0], num_vectors)
+    d = weight.shape[1] if input_side else weight.shape[0]
+    acc = linalg.CovarianceAccumulator(
+        d, device, defer_rows=linalg.default_defer_rows(d, weight.element_size()))
+    wrapper.capture_output = not input_side
+    try:
+        for _ in range(num_data_steps):
+            inputs = utils.to_device(next(data_iterator), device)
+            _ = root_module(inputs)
+            if input_side:
+                _update_Eyyt_in_place(acc, wrapper.get_last_input())
+            else:
+                _update_Eyyt_in_place(acc, wrapper.get_last_output_rows(), sub=wrapper.get_bias())
+    finally:
+        wrapper.capture_output = False
+        wrapper.output = None
+    if input_side:
+        return _get_eigenvectors_input_side(acc, weight, num_vectors)
+    return _get_eigenvectors(acc, num_vectors)
 
 
-def decompose_in_place(
-    *,
-    module: torch.nn.Module,
-    device: torch.device,
-    data_iterator: collections.abc.Iterator[dict[str, torch.Tensor]],
-    loss_fn: collections.abc.Callable[[dict[str, torch.Tensor], torch.Tensor], torch.Tensor],
-    num_data_steps: int,
-    metric_iterator: collections.abc.Iterator[dict[str, torch.Tensor]],
-    num_metric_steps: int,
-    blacklisted_module_names: Optional[list[str]] = None,
-    nsr_final_threshold: float,
-    finetune_fn: collections.abc.Callable[[torch.nn.Module, torch.device, list[str]], torch.nn.Module],
-    min_rank: int = 32,
-    trade_off_factor: float = 0.5,
-    reduction_factor: float = 0.5,
-    max_accepted_ppl_diff: float = 0.1,
-    decompose_in_float64: bool = True,
-    precomputing_covariance_num_splits: Optional[int] = None,
-    trace: Optional[list] = None,
-) -> dict[str, Any]:
-    """D:677-800. Returns the decompose_config (insertion order = reversed module order)."""
-    start_time = time.perf_counter()
-    device = torch.device(device)
-    if device.type != "cuda":
-        raise nat.NativeError("ptdeco_b200.dwain runs on CUDA (sm_100a) only; there is no CPU path")
-    nat.lib()
-    num_params = utils.get_num_params(module)
-    current_params = num_params
-    if blacklisted_module_names is None:
-        blacklisted_module_names = []
-    names = _get_decomposeable_submodule_names(module, blacklisted_module_names)
-    n = len(names)
-    n_decomposed = 0
-    logger.info("\n".join([f"There are {n} linear modules that can be decomposed:"]
-                          + [f"  {i}. {nm}" for i, nm in enumerate(names, start=1)]))
+def _get_eigenvectors_input_side(acc: linalg.CovarianceAccumulator, weight: torch.Tensor,
+                                 num_vectors: int, group=None) -> torch.Tensor:
+    parallel.allreduce_accumulator(acc, group)
+    s_cov = acc.finalize(use_mean=False, damp_factor=0.0)
+    return linalg.eigvecs_from_input_covariance(s_cov, weight, num_vectors)
 
-    decompose_config: dict[str, Any] = {}
-    decomposed_submodules: list[str] = []
-    group = parallel.default_group()
 
-    if precomputing_covariance_num_splits is not None and precomputing_covariance_num_splits > 0:
-        u_dict = _precompute_covariance_matrix_decompositions_in_splits(
-            module=module, modules_to_decompose=names,
-            num_splits=precomputing_covariance_num_splits, data_iterator=data_iterator,
-            num_data_steps=num_data_steps, device=device,
-            decompose_in_float64=decompose_in_float64, reduction_factor=reduction_factor,
-            group=group)
+def _get_eigenvectors(acc: linalg.CovarianceAccumulator, num_vectors: Optional[int] = None,
+                      group=None) -> torch.Tensor:
+    """D:155-163 on the accumulated covariance: /steps, damping 0.01*mean(diag), eigenvectors
+    ascending (all, or the last `num_vectors`). With a process group the partial covariances are
+    summed over ranks first."""
+    parallel.allreduce_accumulator(acc, group)
+    cov = acc.finalize(use_mean=False, damp_factor=EIGEN_DAMPEN_FACTOR)
+    _, u = linalg.eigh(cov, k=num_vectors)
+    return u
+
+
+def _update_Eyyt_in_place(acc: linalg.CovarianceAccumulator, y_reshaped: torch.Tensor,
+                          sub: Optional[torch.Tensor] = None) -> None:
+    """D:147-152: Eyyt += y^T y / N for one batch of rows."""
+    acc.update(y_reshaped, sub=sub)
+
+
+def _max_rank_consumed(dim_in: int, dim_out: int, reduction_factor: float) -> int:
+    """Largest rank the descent of D:407-408 can ask for: int(full_rank * reduction_factor)."""
+    full_rank = min(dim_in, dim_out)
+    return max(1, min(full_rank, int(full_rank * reduction_factor)))
+
+
+def _wrap_in_place(root_module: torch.nn.Module, decomposed_submodule_name: str) -> None:
+    """D:281-304."""
+    sub = root_module.get_submodule(decomposed_submodule_name)
+    if isinstance(sub, torch.nn.Linear):
+        wrapped: WrappedDWAINModule = WrappedDWAINLinear(sub, decomposed_submodule_name)
+    elif is_decomposeable_module(sub):
+        wrapped = WrappedDWAINConv2d1x1(sub, decomposed_submodule_name)
     else:
-        logger.info("Skipping precomputing convariance matrices")
-        u_dict = {}
-    utils.relieve_gpu_memory_pressure()
-    pair_state = _wrap.PairState()
+        raise ValueError(f"Cannot decompose {decomposed_submodule_name}={sub}")
+    utils.replace_submodule_in_place(root_module, decomposed_submodule_name, wrapped)
 
-    for i, name in enumerate(reversed(names), start=1):
-        logger.info(f"PROCESSING {name} MODULE {i} OUT OF {n}")
-        with torch.no_grad():
-            logger.info(f"start reserved gpu mem={utils.get_gpu_reserved_memory_gb():.2f} GB")
-            result = _process_module(
-                root_module=module, decomposed_submodule_name=name, data_iterator=data_iterator,
-                loss_fn=loss_fn, metric_iterator=metric_iterator,
-                nsr_final_threshold=nsr_final_threshold, num_data_steps=num_data_steps,
-                num_metric_steps=num_metric_steps, device=device, num_params=num_params,
-                trade_off_factor=trade_off_factor, reduction_factor=reduction_factor,
-                max_accepted_ppl_diff=max_accepted_ppl_diff, min_rank=min_rank,
-                decompose_in_float64=decompose_in_float64,
-                u_matrix=u_dict.pop(name) if len(u_dict) > 0 else None, trace=trace,
-                pair_state=pair_state)
-            logger.info(f"stop reserved gpu mem={utils.get_gpu_reserved_memory_gb():.2f} GB")
-        current_params -= result.get("drop_in_params", 0)
-        logger.info(f"CURRENT PARAMS IN M: {current_params / 1e6}")
-        new_module = result["decomposed_module"]
-        proportion = result["proportion"]
-        if new_module is not None:
-            decomposed_submodules.append(name)
-            utils.replace_submodule_in_place(module, name, new_module)
-            module = finetune_fn(module, device, decomposed_submodules)
-            utils.relieve_gpu_memory_pressure()
-            module_config = utils.get_module_config(new_module)
-            _add_meta_to_module_config(module_config, result)
-            decompose_config[name] = module_config
-            logger.info(f"{name} decomposed with rank {proportion=:.4f}")
-            n_decomposed += 1
-        utils.relieve_gpu_memory_pressure()
 
-    logger.info(f"Decomposed {n_decomposed} out of {n} modules")
-    logger.info(f"Decomposition took {time.perf_counter() - start_time:.1f} seconds")
-    return decompose_config
+def _unwrap_in_place(root_module: torch.nn.Module, decomposed_submodule_name: str) -> None:
+    """D:307-316."""
+    sub = root_module.get_submodule(decomposed_submodule_name)
+    assert isinstance(sub, WrappedDWAINModule)
+    utils.replace_submodule_in_place(root_module, decomposed_submodule_name, sub.get_orig_module())
+
+
+def _get_decomposeable_submodule_names(module: torch.nn.Module,
+                                       blacklisted_module_names: list[str]) -> list[str]:
+    """D:549-559."""
+    res = []
+    for name, mod in module.named_modules():
+        if is_decomposeable_module(mod):
+            if name in blacklisted_module_names:
+                logger.info(f"Skipping blacklisted module {name}")
+            else:
+                res.append(name)
+    return res
+
+
+def _add_meta_to_module_config(module_config: dict[str, Any], module_deco_results: dict[str, Any]) -> None:
+    """D:562-566."""
+    module_config[utils.MODCONFIG_META_KEY] = {
+        k: v for k, v in module_deco_results.items() if k != "decomposed_module"}

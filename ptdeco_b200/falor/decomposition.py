@@ -51,130 +51,89 @@ is_decomposeable_module = _wrap.is_decomposeable_module
 _is_num_params_reduced = _wrap.is_num_params_reduced
 
 
-def _accumulate_Ey_and_Eyyt(acc: linalg.CovarianceAccumulator, wrapper: WrappedFALORModule) -> None:
-    """F:156-162 for one calibration batch. The layer output captured by the wrapper is
-    y + bias; the kernel subtracts the bias while staging, so what is accumulated is exactly the
-    reference's y = x W^T: Eyyt += y^T y / N and (when tracked) Ey += mean(y)."""
-    acc.update(wrapper.get_last_output_rows(), sub=wrapper.get_bias())
-
-
-def _compute_decompositon_of_covariance_matrix(
+def decompose_in_place(
     *,
-    root_module: torch.nn.Module,
-    decomposed_submodule_name: str,
-    data_iterator: collections.abc.Iterator[torch.Tensor],
-    weight: torch.Tensor,
-    num_data_steps: int,
+    module: torch.nn.Module,
     device: torch.device,
+    data_iterator: collections.abc.Iterator[torch.Tensor],
+    blacklisted_module_names: Optional[list[str]] = None,
+    proportion_threshold: float,
+    nsr_final_threshold: float,
+    kl_final_threshold: float,
+    num_data_steps: int,
+    num_metric_steps: int,
     use_float64: bool,
     use_mean: bool,
     use_damping: bool,
-    num_vectors: Optional[int] = None,
-    forward_fn=None,
-) -> torch.Tensor:
-    """F:165-208. Returns eigenvectors in columns, ascending by eigenvalue: all `d` of them like
-    torch.linalg.eigh, or only the last `num_vectors` (what the rank search consumes; slicing
-    `u[:, u.shape[1] - rank:]` works on either).
+    trace: Optional[list] = None,
+) -> dict[str, Any]:
+    """F:424-511. Every target is analysed against the unmodified model; swaps happen afterwards.
+    Returns the decompose_config (insertion order = forward module order)."""
+    start_time = time.perf_counter()
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise nat.NativeError("ptdeco_b200.falor runs on CUDA (sm_100a) only; there is no CPU path")
+    nat.lib()  # fail now, loudly, if the native library is missing
+    results_all: dict[str, dict[str, Any]] = {}
+    decompose_config: dict[str, Any] = {}
+    if blacklisted_module_names is None:
+        blacklisted_module_names = []
 
-    `use_float64`: the reference forms each per-batch product in the model dtype and only *adds*
-    it into an fp64 accumulator (F:160,181-183), which measures 5.6e-8 vs 7.3e-8 against an fp64
-    truth (SURVEY.md 6.1). Here products are exact-bf16 / bf16x3-split with fp32 accumulation and
-    the tridiagonal eigenproblem is solved in fp64 either way, so the flag is accepted and has no
-    further effect. The falor damping quirk is kept: damping reaches `cov` only when
-    use_mean=False (F:196-205)."""
-    root_module.eval()
-    forward_fn = forward_fn or root_module
-    wrapper = root_module.get_submodule(decomposed_submodule_name)
-    assert isinstance(wrapper, WrappedFALORModule)
-    n_out, n_in = weight.shape
-    input_side = linalg.use_input_side(n_in, n_out, num_vectors)
-    d = n_in if input_side else n_out
-    acc = linalg.CovarianceAccumulator(d, device, with_mean=use_mean,
-                                       defer_rows=linalg.default_defer_rows(d, weight.element_size()))
-    wrapper.capture_output = not input_side
-    try:
-        for _ in range(num_data_steps):
-            inputs = next(data_iterator).to(device)
-            _ = forward_fn(inputs)
-            _sync_wrapper_with_recorder(wrapper, forward_fn)
-            if input_side:  # C = W S W^T: accumulate S = E[x x^T] (and E[x]) instead of C
-                acc.update(wrapper.get_last_input())
-            else:
-                _accumulate_Ey_and_Eyyt(acc, wrapper)
-    finally:
-        wrapper.capture_output = False
-        wrapper.output = None
-    logger.info("Using mean for covariance" if use_mean else "Not using mean for covariance")
-    if use_damping:
-        logger.info("Using damping")
-    if input_side:
-        # centring carries over (E[y] = W E[x]); damping is a multiple of I on C and moves no
-        # eigenvector, so it has no input-side counterpart
-        s_cov = acc.finalize(use_mean=use_mean, damp_factor=0.0)
-        return linalg.eigvecs_from_input_covariance(s_cov, weight, num_vectors)
-    damp = EIGEN_DAMPEN_FACTOR if (use_damping and not use_mean) else 0.0
-    cov = acc.finalize(use_mean=use_mean, damp_factor=damp)
-    _, u = linalg.eigh(cov, k=num_vectors)
-    return u
+    names = _get_decomposeable_submodule_names(module)
+    n = len(names)
+    # One CUDA graph of the model forward serves every layer: hooks on the targets remember where
+    # the graph keeps each layer's input / output (see _graphs.py). Eager until the third call.
+    module.eval()
+    recorder = _graphs.ActivationRecorder(module, [nm for nm in names if nm not in blacklisted_module_names])
+    forward_fn = _graphs.GraphedForward(module, recorder=recorder)
+    if not forward_fn.enabled:
+        recorder.close()
+        forward_fn.recorder = None
+    pair_state = _wrap.PairState()
+    for i, name in enumerate(names, start=1):
+        msg_prefix = f"Processing {name}: module {i} of {n}"
+        if name in blacklisted_module_names:
+            logger.info(f"{msg_prefix}, skipped as blacklisted")
+            continue
+        logger.info(msg_prefix)
+        with torch.no_grad():
+            results_all[name] = _process_module(
+                root_module=module, decomposed_submodule_name=name, data_iterator=data_iterator,
+                nsr_final_threshold=nsr_final_threshold, kl_final_threshold=kl_final_threshold,
+                num_data_steps=num_data_steps, num_metric_steps=num_metric_steps, device=device,
+                use_float64=use_float64, use_mean=use_mean, use_damping=use_damping, trace=trace,
+                forward_fn=forward_fn, pair_state=pair_state)
+    recorder.close()
+    del forward_fn
 
+    counter: collections.Counter[str] = collections.Counter()
+    for name in names:
+        msg_prefix = f"Decomposing {name}:"
+        if name in blacklisted_module_names:
+            logger.info(f"{msg_prefix} SKIPPED blacklisted module {name}")
+            continue
+        result = results_all[name]
+        new_module = result["decomposed_module"]
+        proportion = result["proportion"]
+        if new_module is None:
+            logger.info(f"{msg_prefix} SKIPPED {proportion=:.4f} leads to num param increase")
+            continue
+        if proportion < proportion_threshold:
+            old_type = utils.get_type_name(module.get_submodule(name))
+            utils.replace_submodule_in_place(module, name, new_module)
+            module_config = utils.get_module_config(new_module)
+            _add_meta_to_module_config(module_config, result)
+            decompose_config[name] = module_config
+            counter[old_type] += 1
+            logger.info(f"{msg_prefix} finished {proportion=:.3f}")
+        else:
+            logger.info(f"{msg_prefix} SKIPPED, {proportion=:.3f} above {proportion_threshold=:.3f}")
 
-def _sync_wrapper_with_recorder(wrapper: WrappedFALORModule, forward_fn) -> None:
-    """When the forward ran as a CUDA-graph replay the wrapper's Python forward did not execute;
-    its last input / output are the static tensors the recorder saw at capture time."""
-    rec = getattr(forward_fn, "recorder", None)
-    name = getattr(wrapper, "name", None)
-    if rec is not None and name in rec.inputs:
-        wrapper.input = rec.inputs[name]
-        wrapper.output = rec.outputs[name]
-
-
-def _compute_metrics(
-    *,
-    x: torch.Tensor,
-    root_module: torch.nn.Module,
-    decomposed_submodule: torch.nn.Module,
-    orig_weight: torch.Tensor,
-    deco_weight: torch.Tensor,
-    forward_fn=None,
-    pair_state: Optional[_wrap.PairState] = None,
-) -> tuple[torch.Tensor, torch.Tensor]:
-    """F:211-233: two full forwards (decomposed weight, original weight) -- or, once `pair_state`
-    has verified it on this model, one forward of the doubled batch (see _wrap.PairState) -- then
-    NSR over the batch dim and symmetric-max KL of the logits; both returned as 0-dim device
-    tensors (no host sync)."""
-    assert isinstance(decomposed_submodule, WrappedFALORModule)
-    root_module.eval()
-    forward_fn = forward_fn or root_module
-    if pair_state is not None and getattr(forward_fn, "recorder", None) is None:
-        y_deco, y_orig = pair_state.forward_pair(forward_fn, decomposed_submodule, x, orig_weight,
-                                                 deco_weight)
-    else:
-        decomposed_submodule.set_weight(deco_weight)
-        y_deco = forward_fn(x)
-        decomposed_submodule.set_weight(orig_weight)
-        y_orig = forward_fn(x)
-    nsr_final = utils.calc_per_channel_noise_to_signal_ratio(y=y_orig, x=y_deco, non_channel_dim=(0,))
-    kl_final = utils.calc_kl_loss(y_deco, y_orig)
-    return nsr_final, kl_final
-
-
-def _wrap_in_place(root_module: torch.nn.Module, decomposed_submodule_name: str) -> None:
-    """F:236-259."""
-    sub = root_module.get_submodule(decomposed_submodule_name)
-    if isinstance(sub, torch.nn.Linear):
-        wrapped: WrappedFALORModule = WrappedFALORLinear(sub, decomposed_submodule_name)
-    elif is_decomposeable_module(sub):
-        wrapped = WrappedFALORConv2d1x1(sub, decomposed_submodule_name)
-    else:
-        raise ValueError(f"Cannot decompose {decomposed_submodule_name}={sub}")
-    utils.replace_submodule_in_place(root_module, decomposed_submodule_name, wrapped)
-
-
-def _unwrap_in_place(root_module: torch.nn.Module, decomposed_submodule_name: str) -> None:
-    """F:262-270."""
-    sub = root_module.get_submodule(decomposed_submodule_name)
-    assert isinstance(sub, WrappedFALORModule)
-    utils.replace_submodule_in_place(root_module, decomposed_submodule_name, sub.get_orig_module())
+    for type_name, count in counter.items():
+        logger.info(f"Decomposed {count} instances of {type_name}")
+    logger.info(f"Total decomposable modules {n}")
+    logger.info(f"Decomposition took {time.perf_counter() - start_time:.1f} seconds")
+    return decompose_config
 
 
 def _process_module(
@@ -284,6 +243,113 @@ def _process_module(
             "decomposed_module": new_module}
 
 
+def _compute_metrics(
+    *,
+    x: torch.Tensor,
+    root_module: torch.nn.Module,
+    decomposed_submodule: torch.nn.Module,
+    orig_weight: torch.Tensor,
+    deco_weight: torch.Tensor,
+    forward_fn=None,
+    pair_state: Optional[_wrap.PairState] = None,
+) -> tuple[torch.Tensor, torch.Tensor]:
+    """F:211-233: two full forwards (decomposed weight, original weight) -- or, once `pair_state`
+    has verified it on this model, one forward of the doubled batch (see _wrap.PairState) -- then
+    NSR over the batch dim and symmetric-max KL of the logits; both returned as 0-dim device
+    tensors (no host sync)."""
+    assert isinstance(decomposed_submodule, WrappedFALORModule)
+    root_module.eval()
+    forward_fn = forward_fn or root_module
+    if pair_state is not None and getattr(forward_fn, "recorder", None) is None:
+        y_deco, y_orig = pair_state.forward_pair(forward_fn, decomposed_submodule, x, orig_weight,
+                                                 deco_weight)
+    else:
+        decomposed_submodule.set_weight(deco_weight)
+        y_deco = forward_fn(x)
+        decomposed_submodule.set_weight(orig_weight)
+        y_orig = forward_fn(x)
+    nsr_final = utils.calc_per_channel_noise_to_signal_ratio(y=y_orig, x=y_deco, non_channel_dim=(0,))
+    kl_final = utils.calc_kl_loss(y_deco, y_orig)
+    return nsr_final, kl_final
+
+
+def _compute_decompositon_of_covariance_matrix(
+    *,
+    root_module: torch.nn.Module,
+    decomposed_submodule_name: str,
+    data_iterator: collections.abc.Iterator[torch.Tensor],
+    weight: torch.Tensor,
+    num_data_steps: int,
+    device: torch.device,
+    use_float64: bool,
+    use_mean: bool,
+    use_damping: bool,
+    num_vectors: Optional[int] = None,
+    forward_fn=None,
+) -> torch.Tensor:
+    """F:165-208. Returns eigenvectors in columns, ascending by eigenvalue: all `d` of them like
+    torch.linalg.eigh, or only the last `num_vectors` (what the rank search consumes; slicing
+    `u[:, u.shape[1] - rank:]` works on either).
+
+    `use_float64`: the reference forms each per-batch product in the model dtype and only *adds*
+    it into an fp64 accumulator (F:160,181-183), which measures 5.6e-8 vs 7.3e-8 against an fp64
+    truth (SURVEY.md 6.1). Here products are exact-bf16 / bf16x3-split with fp32 accumulation and
+    the tridiagonal eigenproblem is solved in fp64 either way, so the flag is accepted and has no
+    further effect. The falor damping quirk is kept: damping reaches `cov` only when
+    use_mean=False (F:196-205)."""
+    root_module.eval()
+    forward_fn = forward_fn or root_module
+    wrapper = root_module.get_submodule(decomposed_submodule_name)
+    assert isinstance(wrapper, WrappedFALORModule)
+    n_out, n_in = weight.shape
+    input_side = linalg.use_input_side(n_in, n_out, num_vectors)
+    d = n_in if input_side else n_out
+    acc = linalg.CovarianceAccumulator(d, device, with_mean=use_mean,
+                                       defer_rows=linalg.default_defer_rows(d, weight.element_size()))
+    wrapper.capture_output = not input_side
+    try:
+        for _ in range(num_data_steps):
+            inputs = next(data_iterator).to(device)
+            _ = forward_fn(inputs)
+            _sync_wrapper_with_recorder(wrapper, forward_fn)
+            if input_side:  # C = W S W^T: accumulate S = E[x x^T] (and E[x]) instead of C
+                acc.update(wrapper.get_last_input())
+            else:
+                _accumulate_Ey_and_Eyyt(acc, wrapper)
+    finally:
+        wrapper.capture_output = False
+        wrapper.output = None
+    logger.info("Using mean for covariance" if use_mean else "Not using mean for covariance")
+    if use_damping:
+        logger.info("Using damping")
+    if input_side:
+        # centring carries over (E[y] = W E[x]); damping is a multiple of I on C and moves no
+        # eigenvector, so it has no input-side counterpart
+        s_cov = acc.finalize(use_mean=use_mean, damp_factor=0.0)
+        return linalg.eigvecs_from_input_covariance(s_cov, weight, num_vectors)
+    damp = EIGEN_DAMPEN_FACTOR if (use_damping and not use_mean) else 0.0
+    cov = acc.finalize(use_mean=use_mean, damp_factor=damp)
+    _, u = linalg.eigh(cov, k=num_vectors)
+    return u
+
+
+def _accumulate_Ey_and_Eyyt(acc: linalg.CovarianceAccumulator, wrapper: WrappedFALORModule) -> None:
+    """F:156-162 for one calibration batch. The layer output captured by the wrapper is
+    y + bias; the kernel subtracts the bias while staging, so what is accumulated is exactly the
+    reference's y = x W^T: Eyyt += y^T y / N and (when tracked) Ey += mean(y)."""
+    acc.update(wrapper.get_last_output_rows(), sub=wrapper.get_bias())
+
+
+def _sync_wrapper_with_recorder(wrapper: WrappedFALORModule, forward_fn) -> None:
+    """When the forward ran as a CUDA-graph replay the wrapper's Python forward did not execute;
+    its last input / output are the static tensors the recorder saw at capture time."""
+    rec = getattr(forward_fn, "recorder", None)
+    name = getattr(wrapper, "name", None)
+    if rec is not None and name in rec.inputs:
+        wrapper.input = rec.inputs[name]
+        wrapper.output = rec.outputs[name]
+
+
 def _get_decomposeable_submodule_names(module: torch.nn.Module) -> list[str]:
     """F:411-414: forward (named_modules) order."""
     return [name for name, mod in module.named_modules() if is_decomposeable_module(mod)]
@@ -295,86 +361,20 @@ def _add_meta_to_module_config(module_config: dict[str, Any], module_deco_result
         k: v for k, v in module_deco_results.items() if k != "decomposed_module"}
 
 
-def decompose_in_place(
-    *,
-    module: torch.nn.Module,
-    device: torch.device,
-    data_iterator: collections.abc.Iterator[torch.Tensor],
-    blacklisted_module_names: Optional[list[str]] = None,
-    proportion_threshold: float,
-    nsr_final_threshold: float,
-    kl_final_threshold: float,
-    num_data_steps: int,
-    num_metric_steps: int,
-    use_float64: bool,
-    use_mean: bool,
-    use_damping: bool,
-    trace: Optional[list] = None,
-) -> dict[str, Any]:
-    """F:424-511. Every target is analysed against the unmodified model; swaps happen afterwards.
-    Returns the decompose_config (insertion order = forward module order)."""
-    start_time = time.perf_counter()
-    device = torch.device(device)
-    if device.type != "cuda":
-        raise nat.NativeError("ptdeco_b200.falor runs on CUDA (sm_100a) only; there is no CPU path")
-    nat.lib()  # fail now, loudly, if the native library is missing
-    results_all: dict[str, dict[str, Any]] = {}
-    decompose_config: dict[str, Any] = {}
-    if blacklisted_module_names is None:
-        blacklisted_module_names = []
+def _wrap_in_place(root_module: torch.nn.Module, decomposed_submodule_name: str) -> None:
+    """F:236-259."""
+    sub = root_module.get_submodule(decomposed_submodule_name)
+    if isinstance(sub, torch.nn.Linear):
+        wrapped: WrappedFALORModule = WrappedFALORLinear(sub, decomposed_submodule_name)
+    elif is_decomposeable_module(sub):
+        wrapped = WrappedFALORConv2d1x1(sub, decomposed_submodule_name)
+    else:
+        raise ValueError(f"Cannot decompose {decomposed_submodule_name}={sub}")
+    utils.replace_submodule_in_place(root_module, decomposed_submodule_name, wrapped)
 
-    names = _get_decomposeable_submodule_names(module)
-    n = len(names)
-    # One CUDA graph of the model forward serves every layer: hooks on the targets remember where
-    # the graph keeps each layer's input / output (see _graphs.py). Eager until the third call.
-    module.eval()
-    recorder = _graphs.ActivationRecorder(module, [nm for nm in names if nm not in blacklisted_module_names])
-    forward_fn = _graphs.GraphedForward(module, recorder=recorder)
-    if not forward_fn.enabled:
-        recorder.close()
-        forward_fn.recorder = None
-    pair_state = _wrap.PairState()
-    for i, name in enumerate(names, start=1):
-        msg_prefix = f"Processing {name}: module {i} of {n}"
-        if name in blacklisted_module_names:
-            logger.info(f"{msg_prefix}, skipped as blacklisted")
-            continue
-        logger.info(msg_prefix)
-        with torch.no_grad():
-            results_all[name] = _process_module(
-                root_module=module, decomposed_submodule_name=name, data_iterator=data_iterator,
-                nsr_final_threshold=nsr_final_threshold, kl_final_threshold=kl_final_threshold,
-                num_data_steps=num_data_steps, num_metric_steps=num_metric_steps, device=device,
-                use_float64=use_float64, use_mean=use_mean, use_damping=use_damping, trace=trace,
-                forward_fn=forward_fn, pair_state=pair_state)
-    recorder.close()
-    del forward_fn
 
-    counter: collections.Counter[str] = collections.Counter()
-    for name in names:
-        msg_prefix = f"Decomposing {name}:"
-        if name in blacklisted_module_names:
-            logger.info(f"{msg_prefix} SKIPPED blacklisted module {name}")
-            continue
-        result = results_all[name]
-        new_module = result["decomposed_module"]
-        proportion = result["proportion"]
-        if new_module is None:
-            logger.info(f"{msg_prefix} SKIPPED {proportion=:.4f} leads to num param increase")
-            continue
-        if proportion < proportion_threshold:
-            old_type = utils.get_type_name(module.get_submodule(name))
-            utils.replace_submodule_in_place(module, name, new_module)
-            module_config = utils.get_module_config(new_module)
-            _add_meta_to_module_config(module_config, result)
-            decompose_config[name] = module_config
-            counter[old_type] += 1
-            logger.info(f"{msg_prefix} finished {proportion=:.3f}")
-        else:
-            logger.info(f"{msg_prefix} SKIPPED, {proportion=:.3f} above {proportion_threshold=:.3f}")
-
-    for type_name, count in counter.items():
-        logger.info(f"Decomposed {count} instances of {type_name}")
-    logger.info(f"Total decomposable modules {n}")
-    logger.info(f"Decomposition took {time.perf_counter() - start_time:.1f} seconds")
-    return decompose_config
+def _unwrap_in_place(root_module: torch.nn.Module, decomposed_submodule_name: str) -> None:
+    """F:262-270."""
+    sub = root_module.get_submodule(decomposed_submodule_name)
+    assert isinstance(sub, WrappedFALORModule)
+    utils.replace_submodule_in_place(root_module, decomposed_submodule_name, sub.get_orig_module())
