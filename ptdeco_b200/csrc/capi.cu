@@ -197,6 +197,7 @@ int ptdeco_kl_metric(const void* student, const void* teacher, int dtype, long l
 
 void ptdeco_debug_set(int key, long long value) {
   if (key == 100) ptd::eigh_debug_profile(static_cast<int>(value));
+  else if (key == 101) ptd::eigh_debug_sym_min_m(static_cast<int>(value));
   else ptd::gemm_tc_debug_set(key, value);
 }
 long long ptdeco_debug_get(int key) {

@@ -205,6 +205,10 @@ struct PanelArgs {
   float* taus;    // [d]
   float* Tmat;    // [NB][NB] of this panel (pre-zeroed)
   unsigned* bar;  // grid barrier counter (pre-zeroed)
+  int sym;        // 1: symv reads only the lower triangle (see sym_symv)
+  int sym_tile;   // tile edge of the triangle partition (multiple of 4, <= 256)
+  double* pglob;  // [2][ldp] symv result of the current / next column (sym mode; pre-zeroed)
+  long long ldp;
   int prof;       // 1: CTA 0 accumulates per-phase cycle counts into g_phase_cycles
 };
 
@@ -229,8 +233,157 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& epoch) {
   __syncthreads();
 }
 
+// Sum over the 32 lanes of 16 per-lane values with 16 shuffles instead of 80: each stage halves
+// the values a lane carries and the lanes a value still has to visit. Returns, in every lane, the
+// full sum of v[8*b4 + 4*b3 + 2*b2 + b1] (b_k = bit k of the lane index).
+__device__ __forceinline__ float reduce16_packed(const float (&v)[16], int lane) {
+  float a8[8], a4[4], a2[2];
+  const bool u4 = (lane & 16) != 0, u3 = (lane & 8) != 0, u2 = (lane & 4) != 0, u1 = (lane & 2) != 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    a8[j] = (u4 ? v[j + 8] : v[j]) + __shfl_xor_sync(0xffffffffu, u4 ? v[j] : v[j + 8], 16);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    a4[j] = (u3 ? a8[j + 4] : a8[j]) + __shfl_xor_sync(0xffffffffu, u3 ? a8[j] : a8[j + 4], 8);
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+    a2[j] = (u2 ? a4[j + 2] : a4[j]) + __shfl_xor_sync(0xffffffffu, u2 ? a4[j] : a4[j + 2], 4);
+  float a1 = (u1 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, u1 ? a2[0] : a2[1], 2);
+  a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+  return a1;
+}
+
+// Symmetric matrix-vector product from the LOWER triangle only (large d: the trailing matrix no
+// longer fits the L2 and the one-stage symv is HBM-bound, so reading half of it is the lever).
+// The triangle is cut into T x T tiles dealt round-robin to the CTAs (fixed for the whole panel);
+// an element A[r][c], c < r, feeds p[r] += A v[c] (row part) and p[c] += A v[r] (column part).
+// All (tile, 128-column strip, 16-row chunk) items of a CTA are walked by its 16 warps in one
+// flat loop -- every lane keeps 8 independent 16-byte loads in flight, no barrier between tiles --
+// with row dots (packed warp reduction) and column sums (registers) gathered per tile in shared
+// memory, then flushed once with fp64 atomics into the global p (2T atomics per T^2 elements;
+// fp64 keeps the sum independent of arrival order after rounding).
+// Returns this thread's partial of v^T A v.
+constexpr int SYM_MAX_SLOTS = 12;  // tiles per CTA
+__device__ __forceinline__ void sym_tile_of(int t, int T, int m, int L, int& ta, int& tb, int& ca,
+                                            int& cb, bool& diag) {
+  int bi = static_cast<int>((sqrtf(8.f * static_cast<float>(t) + 1.f) - 1.f) * 0.5f);
+  while (bi * (bi + 1) / 2 > t) --bi;
+  while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+  const int bj = t - bi * (bi + 1) / 2;
+  ta = bi * T;
+  tb = min(m, ta + T);
+  ca = bj * T;
+  cb = min(L, ca + T);
+  diag = bi == bj;
+}
+
+__device__ __forceinline__ float sym_symv(const float* __restrict__ Abase, long long ldA, int m, int L,
+                                          int i, const float* vs, int T, double* pcur, float* trow,
+                                          float* tcol, int cta, int G, int tid) {
+  const int warp = tid >> 5, lane = tid & 31;
+  const int kk = (m + T - 1) / T;
+  const int ntiles = kk * (kk + 1) / 2;
+  const int nslots = (ntiles - cta + G - 1) / G;  // tiles cta, cta + G, ...
+  const int nstrip = (T + 127) >> 7, nchunk = (T + 15) >> 4;
+  const int per_tile = nstrip * nchunk;
+  float vav = 0.f;
+  for (int idx = tid; idx < nslots * 256; idx += PANEL_THREADS) {
+    trow[idx] = 0.f;
+    tcol[idx] = 0.f;
+  }
+  __syncthreads();
+  for (int item = warp; item < nslots * per_tile; item += PANEL_WARPS) {
+    const int slot = item / per_tile, rem = item - slot * per_tile;
+    int ta, tb, ca, cb;
+    bool diag;
+    sym_tile_of(cta + slot * G, T, m, L, ta, tb, ca, cb, diag);
+    if (tb <= i + 1 || cb <= i + 1) continue;  // no active row / column in this tile
+    const int sidx = rem % nstrip, ch = rem / nstrip;
+    const int c = ca + (sidx << 7) + 4 * lane;  // first of this lane's four columns
+    const int rbase = ta + (ch << 4);
+    if (rbase >= tb || ca + (sidx << 7) >= cb) continue;          // edge tile: nothing here
+    if (diag && ca + (sidx << 7) > rbase + 15) continue;          // strip entirely above the diagonal
+    const bool cvalid = c < cb;
+    const float4 x = cvalid ? *reinterpret_cast<const float4*>(vs + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 colacc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float rd[16];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float4 a[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = rbase + 8 * h + u;
+        a[u] = (cvalid && r < tb)
+                   ? __ldg(reinterpret_cast<const float4*>(Abase + static_cast<long long>(r) * ldA + c))
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = rbase + 8 * h + u;
+        const float vr = (r < tb) ? vs[r] : 0.f;
+        float4 e = a[u];  // entries with c <= r (diagonal included)
+        float4 f = a[u];  // entries with c <  r
+        if (diag) {
+          e.x = (c <= r) ? e.x : 0.f;
+          e.y = (c + 1 <= r) ? e.y : 0.f;
+          e.z = (c + 2 <= r) ? e.z : 0.f;
+          e.w = (c + 3 <= r) ? e.w : 0.f;
+          f.x = (c < r) ? f.x : 0.f;
+          f.y = (c + 1 < r) ? f.y : 0.f;
+          f.z = (c + 2 < r) ? f.z : 0.f;
+          f.w = (c + 3 < r) ? f.w : 0.f;
+        }
+        const float dot = e.x * x.x + e.y * x.y + e.z * x.z + e.w * x.w;
+        rd[8 * h + u] = dot;
+        colacc.x += f.x * vr;
+        colacc.y += f.y * vr;
+        colacc.z += f.z * vr;
+        colacc.w += f.w * vr;
+        if (diag) {
+          const float off = f.x * x.x + f.y * x.y + f.z * x.z + f.w * x.w;
+          vav += vr * (off + dot);  // 2 * off + (dot - off)
+        } else {
+          vav += 2.f * vr * dot;
+        }
+      }
+    }
+    const float rsum = reduce16_packed(rd, lane);
+    if ((lane & 1) == 0) {
+      const int rl = rbase - ta + (((lane >> 4) & 1) << 3) + (((lane >> 3) & 1) << 2) +
+                     (((lane >> 2) & 1) << 1) + ((lane >> 1) & 1);
+      if (rl < tb - ta && rsum != 0.f) atomicAdd(trow + slot * 256 + rl, rsum);
+    }
+    if (cvalid) {
+      float* tc = tcol + slot * 256 + (c - ca);
+      atomicAdd(tc, colacc.x);
+      atomicAdd(tc + 1, colacc.y);
+      atomicAdd(tc + 2, colacc.z);
+      atomicAdd(tc + 3, colacc.w);
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < nslots * 512; idx += PANEL_THREADS) {
+    const int slot = idx >> 9, within = idx & 511;
+    int ta, tb, ca, cb;
+    bool diag;
+    sym_tile_of(cta + slot * G, T, m, L, ta, tb, ca, cb, diag);
+    if (tb <= i + 1 || cb <= i + 1) continue;
+    if (within < 256) {
+      if (within < tb - ta) {
+        const float sr = trow[slot * 256 + within];
+        if (sr != 0.f) atomicAdd(pcur + ta + within, static_cast<double>(sr));
+      }
+    } else if (within - 256 < cb - ca) {
+      const float sc = tcol[slot * 256 + within - 256];
+      if (sc != 0.f) atomicAdd(pcur + ca + within - 256, static_cast<double>(sc));
+    }
+  }
+  return vav;
+}
+
 // One launch = one panel of up to NB Householder columns (LAPACK latrd, lower variant).
 // Cooperative: all CTAs are co-resident; row slices of the trailing matrix are owned by CTAs.
+template <bool SYM>
 __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const PanelArgs g) {
   extern __shared__ float smf[];
   const int m = g.d - g.j0;
@@ -247,6 +400,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
   float* pseg = Ts + NB * (NB + 1);          // [rows_per_cta][segments] symv partials
   __shared__ double sred[PANEL_WARPS];
   __shared__ double s_scal[4];
+  __shared__ float s_trow[SYM ? SYM_MAX_SLOTS * 256 : 1], s_tcol[SYM ? SYM_MAX_SLOTS * 256 : 1];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x, cta = blockIdx.x;
@@ -340,51 +494,63 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
     for (int r = tid; r < NB; r += PANEL_THREADS) Vt[r * (NB + 1) + i] = (r < L) ? vs[r] : 0.f;
     PTD_PHASE(2)
 
+    if (SYM) {
+      // The other parity buffer of p was last read in P3 of the previous column (before barrier
+      // A) and is next accumulated after the next barrier A: zero it here, tau or not.
+      double* pnext = g.pglob + static_cast<long long>((i + 1) & 1) * g.ldp;
+      for (int c = cta * PANEL_THREADS + tid; c < L; c += G * PANEL_THREADS) pnext[c] = 0.0;
+    }
     if (tau != 0.f) {
-      // symv over the CTA's row block, split into (row, 1024-float segment) items so that every
-      // lane keeps 8 independent 16-byte loads in flight even when the block has few rows
-      const int n4 = L >> 2;
-      const float4* v4 = reinterpret_cast<const float4*>(vs);
       const int rbeg = max(r0, i + 1);
       const int R = max(0, r1 - rbeg);
-      const int seg0 = (i + 1) >> 10;  // segments entirely left of column i+1 multiply zeros
-      const int nseg = ((n4 + 255) >> 8) - seg0;
-      for (int item = warp; item < R * nseg; item += PANEL_WARPS) {
-        const int rr = item / nseg, sg = item - rr * nseg + seg0;
-        const float4* arow =
-            reinterpret_cast<const float4*>(Abase + static_cast<long long>(rbeg + rr) * g.ldA);
-        const int cbase = (sg << 8) + lane;
-        float4 a[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int c4 = cbase + 32 * u;
-          a[u] = (c4 < n4) ? __ldg(arow + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-        for (int u = 0; u < 8; u += 2) {
-          const int c4 = cbase + 32 * u;
-          if (c4 < n4) {
-            const float4 x = v4[c4];
-            s0 += a[u].x * x.x + a[u].y * x.y + a[u].z * x.z + a[u].w * x.w;
+      float vav_sym = 0.f;
+      if (SYM) {
+        double* pcur = g.pglob + static_cast<long long>(i & 1) * g.ldp;
+        vav_sym = sym_symv(Abase, g.ldA, m, L, i, vs, g.sym_tile, pcur, s_trow, s_tcol, cta, G, tid);
+      } else {
+        // symv over the CTA's row block, split into (row, 1024-float segment) items so that every
+        // lane keeps 8 independent 16-byte loads in flight even when the block has few rows
+        const int n4 = L >> 2;
+        const float4* v4 = reinterpret_cast<const float4*>(vs);
+        const int seg0 = (i + 1) >> 10;  // segments entirely left of column i+1 multiply zeros
+        const int nseg = ((n4 + 255) >> 8) - seg0;
+        for (int item = warp; item < R * nseg; item += PANEL_WARPS) {
+          const int rr = item / nseg, sg = item - rr * nseg + seg0;
+          const float4* arow =
+              reinterpret_cast<const float4*>(Abase + static_cast<long long>(rbeg + rr) * g.ldA);
+          const int cbase = (sg << 8) + lane;
+          float4 a[8];
+  #pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int c4 = cbase + 32 * u;
+            a[u] = (c4 < n4) ? __ldg(arow + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          if (c4 + 32 < n4) {
-            const float4 x = v4[c4 + 32];
-            s1 += a[u + 1].x * x.x + a[u + 1].y * x.y + a[u + 1].z * x.z + a[u + 1].w * x.w;
+          float s0 = 0.f, s1 = 0.f;
+  #pragma unroll
+          for (int u = 0; u < 8; u += 2) {
+            const int c4 = cbase + 32 * u;
+            if (c4 < n4) {
+              const float4 x = v4[c4];
+              s0 += a[u].x * x.x + a[u].y * x.y + a[u].z * x.z + a[u].w * x.w;
+            }
+            if (c4 + 32 < n4) {
+              const float4 x = v4[c4 + 32];
+              s1 += a[u + 1].x * x.x + a[u + 1].y * x.y + a[u + 1].z * x.z + a[u + 1].w * x.w;
+            }
           }
+          const float s = warp_sum(s0 + s1);
+          if (lane == 0) pseg[rr * nseg + (sg - seg0)] = s;
         }
-        const float s = warp_sum(s0 + s1);
-        if (lane == 0) pseg[rr * nseg + (sg - seg0)] = s;
+        __syncthreads();
+        for (int rr = tid; rr < R; rr += PANEL_THREADS) {
+          float s = 0.f;
+          for (int sg = 0; sg < nseg; ++sg) s += pseg[rr * nseg + sg];
+          const int r = rbeg + rr;
+          pbuf[r - r0] = s;
+          if (r < NB) g.ptop[r] = s;
+        }
+        __syncthreads();
       }
-      __syncthreads();
-      for (int rr = tid; rr < R; rr += PANEL_THREADS) {
-        float s = 0.f;
-        for (int sg = 0; sg < nseg; ++sg) s += pseg[rr * nseg + sg];
-        const int r = rbeg + rr;
-        pbuf[r - r0] = s;
-        if (r < NB) g.ptop[r] = s;
-      }
-      __syncthreads();
       float aw0 = 0.f, aw1 = 0.f, av0 = 0.f, av1 = 0.f;
       double vp = 0.0;
       for (int r = max(r0, i + 1) + warp; r < r1; r += PANEL_WARPS) {
@@ -397,12 +563,13 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
           aw1 += Wp[r * NB + lane + 32] * vr;
           av1 += Vp[r * NB + lane + 32] * vr;
         }
-        if (lane == 0) vp += static_cast<double>(vr) * pbuf[r - r0];
+        if (lane == 0 && !SYM) vp += static_cast<double>(vr) * pbuf[r - r0];
       }
       red[warp * 2 * NB + lane] = aw0;
       red[warp * 2 * NB + 32 + lane] = aw1;
       red[warp * 2 * NB + NB + lane] = av0;
       red[warp * 2 * NB + NB + 32 + lane] = av1;
+      if (SYM) vp = static_cast<double>(warp_sum(vav_sym));
       if (lane == 0) sred[warp] = vp;
       __syncthreads();
       if (tid < 2 * NB) {
@@ -411,7 +578,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
           for (int w = 0; w < PANEL_WARPS; ++w) s += red[w * 2 * NB + tid];
           atomicAdd(g.gacc + i * GP_STRIDE + tid, static_cast<double>(s));
         }
-      } else if (tid == 2 * NB && R > 0) {
+      } else if (tid == 2 * NB && (R > 0 || SYM)) {
         double s = 0.0;
         for (int w = 0; w < PANEL_WARPS; ++w) s += sred[w];
         atomicAdd(g.gacc + i * GP_STRIDE + 2 * NB, s);
@@ -430,7 +597,17 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
         else s_scal[1] = s;
       } else if (tid >= 256 && tid < 256 + NB) {  // one parallel fetch of the top rows' symv results
         const int r = tid - 256;
-        pts[r] = (r > i && r < m) ? __ldcg(g.ptop + r) : 0.f;
+        if (SYM)
+          pts[r] = (r > i && r < m)
+                       ? static_cast<float>(__ldcg(g.pglob + static_cast<long long>(i & 1) * g.ldp + r))
+                       : 0.f;
+        else
+          pts[r] = (r > i && r < m) ? __ldcg(g.ptop + r) : 0.f;
+      }
+      if (SYM) {  // own rows of A v, summed over all CTAs' tiles
+        const double* pcur = g.pglob + static_cast<long long>(i & 1) * g.ldp;
+        for (int r = max(r0, i + 1) + tid; r < r1; r += PANEL_THREADS)
+          pbuf[r - r0] = static_cast<float>(__ldcg(pcur + r));
       }
       __syncthreads();
       if (warp == 0) {
@@ -949,7 +1126,7 @@ struct Plan {
   float* Aw; long long ldA;
   __nv_bfloat16* Vs; long long ldv;
   float *Vp, *Wp, *colbuf, *ptop, *dvec, *evec, *taus, *Tmats, *X1;
-  double *nacc, *gacc;
+  double *nacc, *gacc, *pglob;
   unsigned* bars;
   __nv_bfloat16 *VW, *WV, *Zs, *Xs;
   TriBufs tb;
@@ -985,6 +1162,7 @@ Plan make_plan(void* ws, int d, int k) {
   p.nacc = cv.take<double>(static_cast<size_t>(p.npanels) * NB);
   p.gacc = cv.take<double>(static_cast<size_t>(p.npanels) * NB * GP_STRIDE);
   p.ptop = cv.take<float>(NB);
+  p.pglob = cv.take<double>(2 * static_cast<size_t>(p.ldA));
   p.dvec = cv.take<float>(D);
   p.evec = cv.take<float>(D);
   p.taus = cv.take<float>(D);
@@ -1022,6 +1200,8 @@ Plan make_plan(void* ws, int d, int k) {
 }  // namespace
 
 static int g_panel_prof = 0;
+static int g_sym_min_m = 6144;  // trailing size from which the symv reads only the lower triangle
+void eigh_debug_sym_min_m(int m) { g_sym_min_m = m; }
 void eigh_debug_profile(int enable) {
   g_panel_prof = enable;
   unsigned long long z[8] = {0};
@@ -1081,12 +1261,15 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
   cudaMemsetAsync(p.Wp, 0, static_cast<size_t>(d) * NB * sizeof(float), st);
   cudaMemsetAsync(p.evec, 0, static_cast<size_t>(d) * sizeof(float), st);
   cudaMemsetAsync(p.taus, 0, static_cast<size_t>(d) * sizeof(float), st);
+  cudaMemsetAsync(p.pglob, 0, 2 * static_cast<size_t>(p.ldA) * sizeof(double), st);
 
   // ---- (1) tridiagonalisation
   static bool panel_attr = false;
   if (!panel_attr) {
-    if (cudaFuncSetAttribute(sytrd_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             220 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(sytrd_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             220 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(sytrd_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             200 * 1024) != cudaSuccess)  // + 24 KB of static tile accumulators
       return -12;
     panel_attr = true;
   }
@@ -1103,6 +1286,8 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
     g.ptop = p.ptop; g.dvec = p.dvec; g.evec = p.evec; g.taus = p.taus;
     g.Tmat = p.Tmats + static_cast<size_t>(pi) * NB * NB;
     g.bar = p.bars + pi;
+    g.pglob = p.pglob;
+    g.ldp = p.ldA;
     g.prof = g_panel_prof;
     const int grid = (m + g.rows_per_cta - 1) / g.rows_per_cta;
     const long long L = p.ldA - j0;
@@ -1110,8 +1295,20 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
     const size_t smem = (static_cast<size_t>(L) + 3 * NB * (NB + 1) + g.rows_per_cta + 3 * NB +
                          PANEL_WARPS * 2 * NB + g.rows_per_cta * nseg_max) * sizeof(float);
     if (smem > 220 * 1024) return -22;  // d beyond what one SM's shared memory can stage
+    // Lower-triangle symv while the trailing matrix is too large for the L2 (full rows otherwise:
+    // L2-resident, and the per-tile atomics would only add latency). Needs its tile accumulators
+    // (24 KB static) next to the dynamic shared memory and at most SYM_MAX_SLOTS tiles per CTA.
+    g.sym = (g_sym_min_m > 0 && m >= g_sym_min_m) ? 1 : 0;
+    g.sym_tile = static_cast<int>(std::min<long long>(256, round_up((m + 32) / 33, 4)));
+    {
+      const long long kk = (m + g.sym_tile - 1) / g.sym_tile;
+      const long long tiles_per_cta = (kk * (kk + 1) / 2 + grid - 1) / grid;
+      if (tiles_per_cta > SYM_MAX_SLOTS || smem > 200 * 1024) g.sym = 0;
+    }
     void* args[] = {&g};
-    if (cudaLaunchCooperativeKernel(reinterpret_cast<void*>(sytrd_panel_kernel), dim3(grid),
+    void* kern = g.sym ? reinterpret_cast<void*>(sytrd_panel_kernel<true>)
+                       : reinterpret_cast<void*>(sytrd_panel_kernel<false>);
+    if (cudaLaunchCooperativeKernel(kern, dim3(grid),
                                     dim3(PANEL_THREADS), args, smem, st) != cudaSuccess)
       return -5;
     {

@@ -27,5 +27,7 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
 // Debug: per-phase cycle counters of the panel kernel (CTA 0), see eigh.cu.
 void eigh_debug_profile(int enable);
 long long eigh_debug_phase_cycles(int k);
+// Debug: trailing-matrix size from which the panel symv reads only the lower triangle (0 = never).
+void eigh_debug_sym_min_m(int m);
 
 }  // namespace ptd

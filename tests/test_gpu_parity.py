@@ -163,6 +163,31 @@ def test_eigh_step_spectrum(dev, d, k):
                 u.cpu().numpy().astype(np.float64), k, cos_ks)
 
 
+@pytest.mark.parametrize("d,k", [(1000, 250), (2050, 1025)])
+def test_eigh_lower_triangle_symv_path(dev, d, k):
+    """The panel kernel's lower-triangle symv (default for trailing sizes >= 6144, where the
+    one-stage reduction is HBM-bound) forced on at test sizes: same eigenvalue / subspace /
+    residual bars as the full-row path, and agreement of the two paths' eigenvalues."""
+    from ptdeco_b200 import _native as nat
+    from ptdeco_b200 import linalg
+    y = cases.step_spectrum_batch(4 * d + 8, d, 5).double()
+    cov = (y.T @ y / y.shape[0])
+    cov = cov + 0.01 * cov.diagonal().mean() * torch.eye(d, dtype=torch.float64)
+    c32 = cov.float()
+    L = nat.lib()
+    try:
+        L.ptdeco_debug_set(101, 128)
+        ev, u = linalg.eigh(c32.to(dev), k=k)
+        L.ptdeco_debug_set(101, 0)
+        ev_full, _ = linalg.eigh(c32.to(dev), k=k)
+    finally:
+        L.ptdeco_debug_set(101, 6144)
+    cos_ks = [kk for kk in (d // 8, d // 4) if kk <= k]
+    _check_eigh(c32.double().numpy(), ev.cpu().numpy().astype(np.float64),
+                u.cpu().numpy().astype(np.float64), k, cos_ks)
+    assert float((ev - ev_full).abs().max() / ev_full.abs().max()) < 2e-6
+
+
 def test_eigh_rank_deficient_with_damping(dev):
     """Covariance of rank d/4 plus damping: a (d - d/4)-fold near-degenerate cluster."""
     from ptdeco_b200 import linalg
