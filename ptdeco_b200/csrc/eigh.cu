@@ -1200,7 +1200,7 @@ Plan make_plan(void* ws, int d, int k) {
 }  // namespace
 
 static int g_panel_prof = 0;
-static int g_sym_min_m = 6144;  // trailing size from which the symv reads only the lower triangle
+static int g_sym_min_m = 5120;  // trailing size from which the symv reads only the lower triangle
 void eigh_debug_sym_min_m(int m) { g_sym_min_m = m; }
 void eigh_debug_profile(int enable) {
   g_panel_prof = enable;

@@ -181,7 +181,7 @@ def test_eigh_lower_triangle_symv_path(dev, d, k):
         L.ptdeco_debug_set(101, 0)
         ev_full, _ = linalg.eigh(c32.to(dev), k=k)
     finally:
-        L.ptdeco_debug_set(101, 6144)
+        L.ptdeco_debug_set(101, 5120)
     cos_ks = [kk for kk in (d // 8, d // 4) if kk <= k]
     _check_eigh(c32.double().numpy(), ev.cpu().numpy().astype(np.float64),
                 u.cpu().numpy().astype(np.float64), k, cos_ks)

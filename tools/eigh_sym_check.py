@@ -51,10 +51,10 @@ def main():
             print(json.dumps({"d": d, "k": k, "mode": name, "eval_err": ev_err, "residual": res, "orth": orth}), flush=True)
     for d, k, reps in ((4096, 4096, 2), (8192, 2048, 1)) + (((14336, 2048, 1),) if big else ()):
         cov = spectrum_cov(d).float().cuda()
-        for name, thr in (("full-row symv", 0), ("lower-triangle symv", 128), ("default (m >= 6144)", 6144)):
+        for name, thr in (("full-row symv", 0), ("lower-triangle symv", 128), ("default (m >= 5120)", 5120)):
             L.ptdeco_debug_set(101, thr)
             print(json.dumps({"d": d, "k": k, "mode": name, "ms": timed(cov, k, reps)}), flush=True)
-    L.ptdeco_debug_set(101, 6144)
+    L.ptdeco_debug_set(101, 5120)
 
 
 if __name__ == "__main__":
