@@ -165,7 +165,7 @@ def test_eigh_step_spectrum(dev, d, k):
 
 @pytest.mark.parametrize("d,k", [(1000, 250), (2050, 1025)])
 def test_eigh_lower_triangle_symv_path(dev, d, k):
-    """The panel kernel's lower-triangle symv (default for trailing sizes >= 6144, where the
+    """The panel kernel's lower-triangle symv (default for trailing sizes >= 5120, where the
     one-stage reduction is HBM-bound) forced on at test sizes: same eigenvalue / subspace /
     residual bars as the full-row path, and agreement of the two paths' eigenvalues."""
     from ptdeco_b200 import _native as nat
