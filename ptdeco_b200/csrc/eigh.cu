@@ -428,18 +428,35 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
   for (int i = 0; i < g.ncols; ++i) {
     const int j = g.j0 + i;
     // ---------------------------------------------------------------- P1: updated column i
+    // 64 rows per pass, 8 threads per row, each thread one contiguous 8-column chunk of the row's
+    // V / W entries (two 16-byte loads per array, all independent: one L2 round trip per pass)
     double nrm = 0.0;
-    for (int r = max(r0, i) + warp; r < r1; r += PANEL_WARPS) {
-      float s = 0.f;
-      for (int c = lane; c < i; c += 32)
-        s += Vp[r * NB + c] * Wt[i * (NB + 1) + c] + Wp[r * NB + c] * Vt[i * (NB + 1) + c];
-      s = warp_sum(s);
-      if (lane == 0) {
-        const float a = Abase[static_cast<long long>(i) * g.ldA + r] - s;
-        g.colbuf[r] = a;
-        if (r >= i + 2) nrm += static_cast<double>(a) * a;
+    {
+      const int sub = tid & 7, c0 = sub * 8;
+      for (int rb = max(r0, i); rb < r1; rb += PANEL_THREADS / 8) {
+        const int r = rb + (tid >> 3);
+        float s = 0.f;
+        if (r < r1 && c0 < i) {
+          const float4* vp = reinterpret_cast<const float4*>(Vp + static_cast<long long>(r) * NB + c0);
+          const float4* wp = reinterpret_cast<const float4*>(Wp + static_cast<long long>(r) * NB + c0);
+          const float4 v0 = vp[0], v1 = vp[1], w0 = wp[0], w1 = wp[1];
+          const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (c0 + e < i) s += vv[e] * Wt[i * (NB + 1) + c0 + e] + ww[e] * Vt[i * (NB + 1) + c0 + e];
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (sub == 0 && r < r1) {
+          const float a = Abase[static_cast<long long>(i) * g.ldA + r] - s;
+          g.colbuf[r] = a;
+          if (r >= i + 2) nrm += static_cast<double>(a) * a;
+        }
       }
     }
+    nrm = warp_sum(nrm);
     if (lane == 0) sred[warp] = nrm;
     __syncthreads();
     if (tid == 0) {
@@ -623,23 +640,40 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
       }
       __syncthreads();
       const float alpha2 = static_cast<float>(s_scal[2]);
-      for (int r = max(r0, i + 1) + warp; r < r1; r += PANEL_WARPS) {
-        float s = 0.f;
-        for (int c = lane; c < i; c += 32) s += Vp[r * NB + c] * gWs[c] + Wp[r * NB + c] * gVs[c];
-        s = warp_sum(s);
-        if (lane == 0) Wp[r * NB + i] = tau * (pbuf[r - r0] - s) + alpha2 * vs[r];
+      {  // own rows: 64 per pass, 8 threads per row (see P1)
+        const int sub = tid & 7, c0 = sub * 8;
+        for (int rb = max(r0, i + 1); rb < r1; rb += PANEL_THREADS / 8) {
+          const int r = rb + (tid >> 3);
+          float s = 0.f;
+          if (r < r1 && c0 < i) {
+            const float4* vp = reinterpret_cast<const float4*>(Vp + static_cast<long long>(r) * NB + c0);
+            const float4* wp = reinterpret_cast<const float4*>(Wp + static_cast<long long>(r) * NB + c0);
+            const float4 v0 = vp[0], v1 = vp[1], w0 = wp[0], w1 = wp[1];
+            const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (c0 + e < i) s += vv[e] * gWs[c0 + e] + ww[e] * gVs[c0 + e];
+          }
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          s += __shfl_xor_sync(0xffffffffu, s, 4);
+          if (sub == 0 && r < r1) Wp[r * NB + i] = tau * (pbuf[r - r0] - s) + alpha2 * vs[r];
+        }
       }
       for (int r = r0 + tid; r < min(r1, i + 1); r += PANEL_THREADS) Wp[r * NB + i] = 0.f;
-      for (int r = warp; r < NB; r += PANEL_WARPS) {  // top block, redundantly in every CTA
-        float w = 0.f;
-        if (r > i && r < m) {
-          float s = 0.f;
-          for (int c = lane; c < i; c += 32)
+      {  // top block, redundantly in every CTA: all NB rows in one pass, 8 threads per row
+        static_assert(PANEL_THREADS == 8 * NB, "one 8-thread group per top-block row");
+        const int r = tid >> 3, sub = tid & 7;
+        const bool live = r > i && r < m;
+        float s = 0.f;
+        if (live)
+          for (int c = sub; c < i; c += 8)
             s += Vt[r * (NB + 1) + c] * gWs[c] + Wt[r * (NB + 1) + c] * gVs[c];
-          s = warp_sum(s);
-          w = tau * (pts[r] - s) + alpha2 * vs[r];
-        }
-        if (lane == 0) Wt[r * (NB + 1) + i] = w;
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (sub == 0) Wt[r * (NB + 1) + i] = live ? tau * (pts[r] - s) + alpha2 * vs[r] : 0.f;
       }
       if (cta == 0 && tid < NB) {  // compact-WY T column: T[0:i,i] = -tau T[0:i,0:i] (V^T v)
         if (tid < i) {
