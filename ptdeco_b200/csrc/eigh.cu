@@ -279,13 +279,12 @@ __device__ __forceinline__ void sym_tile_of(int t, int T, int m, int L, int& ta,
   diag = bi == bj;
 }
 
-__device__ __forceinline__ float sym_symv(const float* __restrict__ Abase, long long ldA, int m, int L,
-                                          int i, const float* vs, int T, double* pcur, float* trow,
-                                          float* tcol, int cta, int G, int tid) {
+__device__ __forceinline__ float sym_symv(const float* __restrict__ Abase, long long ldA, int i,
+                                          const float* vs, int T, double* pcur, float* trow,
+                                          float* tcol, const int* tiles, int nslots, int tid) {
+  // tiles[slot * 4 + {0,1,2,3}] = ta, tb, ca, cb of the CTA's slot-th tile (diagonal iff ta == ca),
+  // decoded once per panel launch
   const int warp = tid >> 5, lane = tid & 31;
-  const int kk = (m + T - 1) / T;
-  const int ntiles = kk * (kk + 1) / 2;
-  const int nslots = (ntiles - cta + G - 1) / G;  // tiles cta, cta + G, ...
   const int nstrip = (T + 127) >> 7, nchunk = (T + 15) >> 4;
   const int per_tile = nstrip * nchunk;
   float vav = 0.f;
@@ -296,9 +295,9 @@ __device__ __forceinline__ float sym_symv(const float* __restrict__ Abase, long 
   __syncthreads();
   for (int item = warp; item < nslots * per_tile; item += PANEL_WARPS) {
     const int slot = item / per_tile, rem = item - slot * per_tile;
-    int ta, tb, ca, cb;
-    bool diag;
-    sym_tile_of(cta + slot * G, T, m, L, ta, tb, ca, cb, diag);
+    const int ta = tiles[slot * 4], tb = tiles[slot * 4 + 1], ca = tiles[slot * 4 + 2],
+              cb = tiles[slot * 4 + 3];
+    const bool diag = ta == ca;
     if (tb <= i + 1 || cb <= i + 1) continue;  // no active row / column in this tile
     const int sidx = rem % nstrip, ch = rem / nstrip;
     const int c = ca + (sidx << 7) + 4 * lane;  // first of this lane's four columns
@@ -366,9 +365,8 @@ __device__ __forceinline__ float sym_symv(const float* __restrict__ Abase, long 
   __syncthreads();
   for (int idx = tid; idx < nslots * 512; idx += PANEL_THREADS) {
     const int slot = idx >> 9, within = idx & 511;
-    int ta, tb, ca, cb;
-    bool diag;
-    sym_tile_of(cta + slot * G, T, m, L, ta, tb, ca, cb, diag);
+    const int ta = tiles[slot * 4], tb = tiles[slot * 4 + 1], ca = tiles[slot * 4 + 2],
+              cb = tiles[slot * 4 + 3];
     if (tb <= i + 1 || cb <= i + 1) continue;
     if (within < 256) {
       if (within < tb - ta) {
@@ -403,6 +401,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
   __shared__ double sred[PANEL_WARPS];
   __shared__ double s_scal[4];
   __shared__ float s_trow[SYM ? SYM_MAX_SLOTS * 256 : 1], s_tcol[SYM ? SYM_MAX_SLOTS * 256 : 1];
+  __shared__ int s_tiles[SYM ? SYM_MAX_SLOTS * 4 : 1];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x, cta = blockIdx.x;
@@ -413,6 +412,22 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
   float* Vp = g.Vp + static_cast<long long>(g.j0) * NB;
   float* Wp = g.Wp + static_cast<long long>(g.j0) * NB;
 
+  int sym_nslots = 0;
+  if (SYM) {  // this CTA's tiles of the lower-triangle partition: fixed for the whole panel
+    const int T = g.sym_tile;
+    const int kk = (m + T - 1) / T;
+    const int ntiles = kk * (kk + 1) / 2;
+    sym_nslots = (ntiles > cta) ? (ntiles - cta + G - 1) / G : 0;
+    if (tid < sym_nslots) {
+      int ta, tb, ca, cb;
+      bool diag;
+      sym_tile_of(cta + tid * G, T, m, L, ta, tb, ca, cb, diag);
+      s_tiles[tid * 4] = ta;
+      s_tiles[tid * 4 + 1] = tb;
+      s_tiles[tid * 4 + 2] = ca;
+      s_tiles[tid * 4 + 3] = cb;
+    }
+  }
   for (int idx = tid; idx < 2 * NB * (NB + 1); idx += PANEL_THREADS) Vt[idx] = 0.f;
   for (int idx = tid; idx < NB * (NB + 1); idx += PANEL_THREADS) Ts[idx] = 0.f;
   __syncthreads();
@@ -525,7 +540,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
       float vav_sym = 0.f;
       if (SYM) {
         double* pcur = g.pglob + static_cast<long long>(i & 1) * g.ldp;
-        vav_sym = sym_symv(Abase, g.ldA, m, L, i, vs, g.sym_tile, pcur, s_trow, s_tcol, cta, G, tid);
+        vav_sym = sym_symv(Abase, g.ldA, i, vs, g.sym_tile, pcur, s_trow, s_tcol, s_tiles, sym_nslots, tid);
       } else {
         // symv over the CTA's row block, split into (row, 1024-float segment) items so that every
         // lane keeps 8 independent 16-byte loads in flight even when the block has few rows
