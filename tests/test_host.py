@@ -277,3 +277,56 @@ def test_capi_argument_errors_return_codes_without_touching_the_gpu():
     assert L.ptdeco_kl_metric(None, p, 0, 4, 4, p, None) == EINVAL
     for code in (EINVAL, ENOMEM, -5, -34, -38, -1003):
         assert len(L.ptdeco_strerror(code)) > 3
+
+
+def test_lowrank_workspace_covers_the_decode_kernel():
+    """Size query only (no GPU): for bf16 batches of up to 128 tokens the workspace must hold the
+    decode kernel's control words, the fp32 partial sums and the bf16 intermediate
+    (4096 + 6 * round_up(n, 16) * round_up(k, 128) bytes), for larger batches the two-GEMM path's
+    intermediate."""
+    from ptdeco_b200 import _native as nat
+    L = nat.lib()
+    for n, in_f, k, out_f in ((1, 4096, 512, 4096), (16, 8192, 3584, 28672), (128, 4096, 1000, 4096)):
+        npad, ldh = -(-n // 16) * 16, -(-k // 128) * 128
+        assert L.ptdeco_lowrank_workspace_bytes(nat.BF16, n, in_f, k, out_f) >= 4096 + 6 * npad * ldh
+    assert L.ptdeco_lowrank_workspace_bytes(nat.BF16, 8192, 4096, 512, 4096) >= 2 * 8192 * 512
+    assert L.ptdeco_lowrank_workspace_bytes(nat.F32, 64, 256, 32, 256) >= 3 * 2 * 64 * 32
+
+
+def test_pair_state_host_logic():
+    """_wrap.PairState on the CPU: batch doubling of tensors and dict batches, refusal of batches it
+    cannot double, and the reference's two-forward path (weights restored) when pairing is off."""
+    from ptdeco_b200 import _wrap
+    import ptdeco_b200.falor.decomposition as F
+    x = torch.arange(12.0).reshape(3, 4)
+    doubled, b = _wrap.PairState._double(x)
+    assert b == 3 and tuple(doubled.shape) == (6, 4) and torch.equal(doubled[:3], doubled[3:])
+    batch = {"input_ids": torch.ones(2, 5, dtype=torch.long), "mask": torch.ones(2, 5), "tag": "keep"}
+    doubled, b = _wrap.PairState._double(batch)
+    assert b == 2 and tuple(doubled["input_ids"].shape) == (4, 5) and doubled["tag"] == "keep"
+    assert _wrap.PairState._double({"a": torch.ones(2, 3), "b": torch.ones(3, 3)}) == (None, 0)
+    assert _wrap.PairState._double({"a": torch.ones(2, 3), "s": torch.tensor(1.0)}) == (None, 0)
+    assert _wrap.PairState._double([x]) == (None, 0)
+
+    net = torch.nn.Sequential(torch.nn.Linear(4, 6), torch.nn.ReLU(), torch.nn.Linear(6, 2)).eval()
+    F._wrap_in_place(net, "0")
+    wrapper = net.get_submodule("0")
+    w = wrapper.get_weight_copy()
+    st = _wrap.PairState()
+    with torch.no_grad():
+        y_deco, y_orig = st.forward_pair(net, wrapper, x, w, 0.5 * w)  # CPU tensors: no probing
+        assert st.mode == "off" and st.paired_forwards == 0
+        assert torch.equal(wrapper.get_weight_copy(), w) and wrapper.pair_weight is None
+        assert torch.allclose(y_orig, net(x)) and not torch.allclose(y_deco, y_orig)
+        # the wrapper's paired forward itself: first half through the pair weight
+        wrapper.pair_weight = 0.5 * w
+        yy = net(torch.cat([x, x], 0))
+        wrapper.pair_weight = None
+        assert torch.allclose(yy[:3], y_deco, atol=1e-6) and torch.allclose(yy[3:], y_orig, atol=1e-6)
+
+
+def test_memory_pressure_gate_without_cuda_is_a_no_op():
+    from ptdeco_b200 import utils
+    if not torch.cuda.is_available():
+        assert utils.relieve_gpu_memory_pressure() is False
+    assert "relieve_gpu_memory_pressure" in utils.__all__ and "free_gpu_reserved_memory" in utils.__all__
