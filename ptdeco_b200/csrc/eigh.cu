@@ -858,11 +858,12 @@ __device__ __forceinline__ int sturm_count(const double* __restrict__ D,
   return cnt;
 }
 
-// LPE lanes per eigenvalue: (LPE+1)-way multisection on the Sturm count, log2(LPE+1) bits per pass.
+// LPE lanes per eigenvalue: (LPE+1)-way multisection on the Sturm count, log2(LPE+1) bits per pass
+// (16 lanes: 8 + 7 passes instead of 10 + 9 with 8 lanes; measured 1-3 % of the eigensolve).
 // 8 lanes cost 2.5x the arithmetic of plain bisection (32 lanes: 6.4x) and still give the FP64 pipe
 // 8 d independent recurrences to overlap.
 // first = 1: start from the Gershgorin interval of the block; else continue from lamA/lamB.
-constexpr int LPE = 8;
+constexpr int LPE = 16;
 __global__ void bisect_kernel(TriBufs b, int d, int count, const int* __restrict__ sel, int first,
                               int passes) {
   const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1391,12 +1392,12 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
   {
     const int tpb = 128, per_block = tpb / LPE;
     // all eigenvalues to ~2^-31 of the block norm (enough for ordering and the fp32 output) ...
-    bisect_kernel<<<(d + per_block - 1) / per_block, tpb, 0, st>>>(p.tb, d, d, nullptr, 1, 10);
+    bisect_kernel<<<(d + per_block - 1) / per_block, tpb, 0, st>>>(p.tb, d, d, nullptr, 1, LPE == 16 ? 8 : 10);
     PTD_CHECK_LAUNCH();
     rank_kernel<<<(d + 255) / 256, 256, 0, st>>>(p.tb, d, k, evals);
     PTD_CHECK_LAUNCH();
     // ... then the k wanted ones to full fp64 precision
-    bisect_kernel<<<(k + per_block - 1) / per_block, tpb, 0, st>>>(p.tb, d, k, p.tb.sel, 0, 9);
+    bisect_kernel<<<(k + per_block - 1) / per_block, tpb, 0, st>>>(p.tb, d, k, p.tb.sel, 0, LPE == 16 ? 7 : 9);
     PTD_CHECK_LAUNCH();
   }
   eigvec_kernel<<<(k + 31) / 32, 32, 0, st>>>(p.tb, d, k);
