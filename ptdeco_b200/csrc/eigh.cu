@@ -952,97 +952,144 @@ __device__ __forceinline__ double guard_piv(double x, double pivmin) {
   return fabs(x) < pivmin ? (x < 0.0 ? -pivmin : pivmin) : x;
 }
 
-// One thread per wanted eigenvector: twisted factorisation of T_block - lambda I
-// (forward L D+ L^T, backward U D- U^T, twist at argmin |gamma|), un-normalised z into Dp.
-__global__ void eigvec_kernel(TriBufs b, int d, int k) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= k) return;
-  const int t = b.sel[c];
-  const int lo = b.blo[t], hi = b.bhi[t];
-  const double lam = 0.5 * (b.lamA[t] + b.lamB[t]);
-  b.clam[c] = lam;
-  b.clo[c] = lo;
-  b.chi[c] = hi;
+// Twisted factorisation of T_block - lambda I for 32 wanted eigenvectors per block (lane = vector):
+// forward L D+ L^T and backward U D- U^T are independent recurrences (one fp64 division per row
+// each), so warp 0 runs the forward one while warp 1 runs the backward one; both then scan half of
+// the rows for the twist index argmin |gamma|, and the two halves of z (below / above the twist)
+// are again swept concurrently. Un-normalised z goes into Dp.
+__global__ void __launch_bounds__(64) eigvec_kernel(TriBufs b, int d, int k) {
+  __shared__ double s_best[2][32];
+  __shared__ int s_r[2][32];
+  __shared__ double s_nn[2][32];
+  const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;  // role 0: forward / lower, 1: backward / upper
+  const int c = blockIdx.x * 32 + lane;
+  const bool act = c < k;
+  const int t = act ? b.sel[c] : 0;
+  const int lo = act ? b.blo[t] : 0, hi = act ? b.bhi[t] : 0;
+  const double lam = act ? 0.5 * (b.lamA[t] + b.lamB[t]) : 0.0;
   const long long K = k;
-  if (lo == hi) {
-    b.Dp[lo * K + c] = 1.0;
-    b.znorm[c] = 1.0;
-    b.cbn[c] = fabs(lam);
-    return;
-  }
+  const bool single = lo == hi;
   double e2max = 0.0, bn = 0.0;
-  for (int i = lo; i <= hi; ++i) {
-    const double er = i < hi ? fabs(b.E[i]) : 0.0;
-    const double el = i > lo ? fabs(b.E[i - 1]) : 0.0;
-    e2max = fmax(e2max, er * er);
-    bn = fmax(bn, fabs(b.D[i]) + el + er);
+  if (act && !single) {
+    for (int i = lo; i <= hi; ++i) {
+      const double er = i < hi ? fabs(b.E[i]) : 0.0;
+      const double el = i > lo ? fabs(b.E[i - 1]) : 0.0;
+      e2max = fmax(e2max, er * er);
+      bn = fmax(bn, fabs(b.D[i]) + el + er);
+    }
   }
-  b.cbn[c] = bn;
   const double pivmin = fmax(DBL_MIN * fmax(1.0, e2max), 1e-300);
-  double dp = b.D[lo] - lam;
-  b.Dp[lo * K + c] = dp;
-  for (int i = lo; i < hi; ++i) {
-    const double e = b.E[i];
-    const double l = e / guard_piv(dp, pivmin);
-    dp = (b.D[i + 1] - lam) - l * e;
-    b.Dp[(i + 1) * K + c] = dp;
+  if (act && role == 0) {
+    b.clam[c] = lam;
+    b.clo[c] = lo;
+    b.chi[c] = hi;
+    b.cbn[c] = single ? fabs(lam) : bn;
+    if (single) {
+      b.Dp[lo * K + c] = 1.0;
+      b.znorm[c] = 1.0;
+    }
   }
-  // The remaining passes read D+ / D- back from global memory; the loads do not depend on the
-  // recurrence, so they are issued eight at a time ahead of the dependent chain.
-  double dm = b.D[hi] - lam;
-  b.Dm[hi * K + c] = dm;
-  double best = fabs(dp);  // gamma at hi = Dp[hi]
-  int r = hi;
-  for (int i0 = hi - 1; i0 >= lo; i0 -= 8) {
-    double dpv[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) dpv[u] = (i0 - u >= lo) ? b.Dp[(i0 - u) * K + c] : 0.0;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int i = i0 - u;
-      if (i >= lo) {
+  const bool work = act && !single;
+  // ---- phase A: the two pivot recurrences
+  if (work) {
+    if (role == 0) {
+      double dp = b.D[lo] - lam;
+      b.Dp[lo * K + c] = dp;
+      for (int i = lo; i < hi; ++i) {
+        const double e = b.E[i];
+        const double l = e / guard_piv(dp, pivmin);
+        dp = (b.D[i + 1] - lam) - l * e;
+        b.Dp[(i + 1) * K + c] = dp;
+      }
+    } else {
+      double dm = b.D[hi] - lam;
+      b.Dm[hi * K + c] = dm;
+      for (int i = hi - 1; i >= lo; --i) {
         const double e = b.E[i];
         const double uu = e / guard_piv(dm, pivmin);
-        const double dl = b.D[i] - lam;
-        dm = dl - uu * e;
+        dm = (b.D[i] - lam) - uu * e;
         b.Dm[i * K + c] = dm;
-        const double gam = fabs(dpv[u] + dm - dl);
-        if (gam < best) { best = gam; r = i; }
       }
     }
   }
-  double zz = 1.0, nn = 1.0;
-  for (int i0 = r - 1; i0 >= lo; i0 -= 8) {
-    double dpv[8];
+  __threadfence_block();
+  __syncthreads();
+  // ---- phase B: twist index = argmin |D+ + D- - (D - lambda)|, ties to the larger row
+  {
+    double best = DBL_MAX;
+    int r = hi;
+    if (work) {
+      const int mid = lo + (hi - lo) / 2;
+      const int i_hi = role == 0 ? mid : hi, i_lo = role == 0 ? lo : mid + 1;
+      for (int i0 = i_hi; i0 >= i_lo; i0 -= 8) {
+        double dpv[8], dmv[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) dpv[u] = (i0 - u >= lo) ? b.Dp[(i0 - u) * K + c] : 1.0;
+        for (int u = 0; u < 8; ++u) {
+          const bool ok = i0 - u >= i_lo;
+          dpv[u] = ok ? b.Dp[(i0 - u) * K + c] : 0.0;
+          dmv[u] = ok ? b.Dm[(i0 - u) * K + c] : 0.0;
+        }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int i = i0 - u;
-      if (i >= lo) {
-        zz = -(b.E[i] / guard_piv(dpv[u], pivmin)) * zz;
-        b.Dp[i * K + c] = zz;
-        nn += zz * zz;
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 - u;
+          if (i >= i_lo) {
+            const double gam = fabs(dpv[u] + dmv[u] - (b.D[i] - lam));
+            if (gam < best) { best = gam; r = i; }
+          }
+        }
+      }
+    }
+    s_best[role][lane] = best;
+    s_r[role][lane] = r;
+  }
+  __syncthreads();
+  int r = hi;
+  if (work) {  // the upper half wins ties (larger row), like a single downward scan
+    r = (s_best[1][lane] <= s_best[0][lane]) ? s_r[1][lane] : s_r[0][lane];
+    if (s_best[0][lane] == DBL_MAX && s_best[1][lane] == DBL_MAX) r = hi;
+  }
+  // ---- phase C: the two halves of z
+  double nn = 0.0;
+  if (work) {
+    double zz = 1.0;
+    if (role == 0) {
+      for (int i0 = r - 1; i0 >= lo; i0 -= 8) {
+        double dpv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) dpv[u] = (i0 - u >= lo) ? b.Dp[(i0 - u) * K + c] : 1.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 - u;
+          if (i >= lo) {
+            zz = -(b.E[i] / guard_piv(dpv[u], pivmin)) * zz;
+            b.Dp[i * K + c] = zz;
+            nn += zz * zz;
+          }
+        }
+      }
+    } else {
+      for (int i0 = r; i0 < hi; i0 += 8) {
+        double dmv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) dmv[u] = (i0 + u < hi) ? b.Dm[(i0 + u + 1) * K + c] : 1.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u;
+          if (i < hi) {
+            zz = -(b.E[i] / guard_piv(dmv[u], pivmin)) * zz;
+            b.Dp[(i + 1) * K + c] = zz;
+            nn += zz * zz;
+          }
+        }
       }
     }
   }
-  zz = 1.0;
-  for (int i0 = r; i0 < hi; i0 += 8) {
-    double dmv[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) dmv[u] = (i0 + u < hi) ? b.Dm[(i0 + u + 1) * K + c] : 1.0;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int i = i0 + u;
-      if (i < hi) {
-        zz = -(b.E[i] / guard_piv(dmv[u], pivmin)) * zz;
-        b.Dp[(i + 1) * K + c] = zz;
-        nn += zz * zz;
-      }
-    }
+  s_nn[role][lane] = nn;
+  __syncthreads();
+  if (work && role == 0) {
+    b.Dp[r * K + c] = 1.0;
+    b.znorm[c] = sqrt(1.0 + s_nn[0][lane] + s_nn[1][lane]);
   }
-  b.Dp[r * K + c] = 1.0;
-  b.znorm[c] = sqrt(nn);
 }
 
 __device__ __forceinline__ bool same_cluster(const TriBufs& b, int c1, int c2) {
@@ -1400,7 +1447,7 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
     bisect_kernel<<<(k + per_block - 1) / per_block, tpb, 0, st>>>(p.tb, d, k, p.tb.sel, 0, LPE == 16 ? 7 : 9);
     PTD_CHECK_LAUNCH();
   }
-  eigvec_kernel<<<(k + 31) / 32, 32, 0, st>>>(p.tb, d, k);
+  eigvec_kernel<<<(k + 31) / 32, 64, 0, st>>>(p.tb, d, k);
   PTD_CHECK_LAUNCH();
   cluster_fix_kernel<<<k, 256, 0, st>>>(p.tb, k);
   PTD_CHECK_LAUNCH();
