@@ -188,6 +188,7 @@ def workload_config(n_gpus: int) -> dict:
     return {"workload": "BASELINE configs[2]: dwain calibration, Llama-3-8B-shape decoder (random init, bf16), "
                         "2048-token synthetic sequences, all 224 target Linears",
             "tokens_per_step_per_gpu": SEQ, "global_tokens_per_step": SEQ * n_gpus,
+            "tokens_per_syrk_launch": "up to 16384 (8 steps staged), see DESIGN.md",
             "parallelism": f"dp{n_gpus} (tokens sharded, d x d fp32 reduction at the end)",
             "l2": "inputs (176 MB) + accumulators (59 GB) exceed the 126 MB L2; no explicit flush"}
 
@@ -235,7 +236,13 @@ def main() -> None:
     g = torch.Generator(device=dev).manual_seed(1314159 + rank)
     acts = {name: torch.randn(SEQ, d, generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
             for name, d in LAYER_DIMS}
-    accs = [[linalg.CovarianceAccumulator(d, dev, defer_rows=linalg.default_defer_rows(d, 2))
+    # staging depth: the library default (up to 16384 tokens = 8 steps per launch), shortened to a
+    # divisor of the step count when there is one >= 4, so that the timed region ends on a full
+    # launch instead of a short remainder (a short launch pays the same accumulator traffic)
+    per = max(c for c in range(1, 9) if args.steps % c == 0)
+    if per < 4:
+        per = 8
+    accs = [[linalg.CovarianceAccumulator(d, dev, defer_rows=min(linalg.default_defer_rows(d, 2), per * SEQ))
              for _, d in LAYER_DIMS] for _ in range(n_layers)]
 
     def syrk_step():
