@@ -188,6 +188,24 @@ __global__ void copy_sym_kernel(const float* __restrict__ A, long long lda, int 
   }
 }
 
+// In place: A[i][j] = A[j][i] for j > i over an m x m block (the lower triangle is authoritative).
+// Run once when the panels switch from the lower-triangle symv back to full rows.
+__global__ void mirror_lower_kernel(float* __restrict__ A, long long lda, int m) {
+  __shared__ float tile[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj < bi) return;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int yy = ty; yy < 32; yy += 8) {
+    const int i = bj * 32 + yy, j = bi * 32 + tx;  // source tile (bj, bi): on or below the diagonal
+    tile[yy][tx] = (i < m && j < m) ? A[static_cast<long long>(i) * lda + j] : 0.f;
+  }
+  __syncthreads();
+  for (int yy = ty; yy < 32; yy += 8) {
+    const int i = bi * 32 + yy, j = bj * 32 + tx;
+    if (i < m && j < m && j > i) A[static_cast<long long>(i) * lda + j] = tile[tx][yy];
+  }
+}
+
 // ============================================================================ sytrd panel
 struct PanelArgs {
   float* A;
@@ -465,7 +483,10 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         s += __shfl_xor_sync(0xffffffffu, s, 4);
         if (sub == 0 && r < r1) {
-          const float a = Abase[static_cast<long long>(i) * g.ldA + r] - s;
+          // column i of the trailing matrix: from row i of the (mirrored) upper triangle, or, when
+          // only the lower triangle is kept current (SYM panels), from column i itself
+          const float a = (SYM ? Abase[static_cast<long long>(r) * g.ldA + i]
+                               : Abase[static_cast<long long>(i) * g.ldA + r]) - s;
           g.colbuf[r] = a;
           if (r >= i + 2) nrm += static_cast<double>(a) * a;
         }
@@ -1373,12 +1394,34 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
     panel_attr = true;
   }
   const int sms = max_grid();
+  struct PanelShape { int rows_per_cta, grid, sym, sym_tile; size_t smem; };
+  // Lower-triangle symv while the trailing matrix is too large for the L2 (full rows otherwise:
+  // L2-resident, and the per-tile atomics would only add latency). Needs its tile accumulators
+  // (24 KB static) next to the dynamic shared memory and at most SYM_MAX_SLOTS tiles per CTA.
+  auto shape_of = [&](int pi) {
+    PanelShape ps;
+    const int j0 = pi * NB;
+    const int m = d - j0;
+    ps.rows_per_cta = std::max(PANEL_WARPS, (m + sms - 1) / sms);
+    ps.grid = (m + ps.rows_per_cta - 1) / ps.rows_per_cta;
+    const long long L = p.ldA - j0;
+    const size_t nseg_max = static_cast<size_t>((L / 4 + 255) / 256);
+    ps.smem = (static_cast<size_t>(L) + 3 * NB * (NB + 1) + ps.rows_per_cta + 3 * NB +
+               PANEL_WARPS * 2 * NB + ps.rows_per_cta * nseg_max) * sizeof(float);
+    ps.sym = (g_sym_min_m > 0 && m >= g_sym_min_m) ? 1 : 0;
+    ps.sym_tile = static_cast<int>(std::min<long long>(256, round_up((m + 32) / 33, 4)));
+    const long long kk = (m + ps.sym_tile - 1) / ps.sym_tile;
+    const long long tiles_per_cta = (kk * (kk + 1) / 2 + ps.grid - 1) / ps.grid;
+    if (tiles_per_cta > SYM_MAX_SLOTS || ps.smem > 200 * 1024) ps.sym = 0;
+    return ps;
+  };
   for (int pi = 0; pi < p.npanels; ++pi) {
     const int j0 = pi * NB;
     const int m = d - j0;
+    const PanelShape ps = shape_of(pi);
     PanelArgs g;
     g.A = p.Aw; g.ldA = p.ldA; g.d = d; g.j0 = j0; g.ncols = std::min(NB, m);
-    g.rows_per_cta = std::max(PANEL_WARPS, (m + sms - 1) / sms);
+    g.rows_per_cta = ps.rows_per_cta;
     g.Vp = p.Vp; g.Wp = p.Wp; g.colbuf = p.colbuf;
     g.nacc = p.nacc + static_cast<size_t>(pi) * NB;
     g.gacc = p.gacc + static_cast<size_t>(pi) * NB * GP_STRIDE;
@@ -1388,22 +1431,11 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
     g.pglob = p.pglob;
     g.ldp = p.ldA;
     g.prof = g_panel_prof;
-    const int grid = (m + g.rows_per_cta - 1) / g.rows_per_cta;
-    const long long L = p.ldA - j0;
-    const size_t nseg_max = static_cast<size_t>((L / 4 + 255) / 256);
-    const size_t smem = (static_cast<size_t>(L) + 3 * NB * (NB + 1) + g.rows_per_cta + 3 * NB +
-                         PANEL_WARPS * 2 * NB + g.rows_per_cta * nseg_max) * sizeof(float);
+    const int grid = ps.grid;
+    const size_t smem = ps.smem;
     if (smem > 220 * 1024) return -22;  // d beyond what one SM's shared memory can stage
-    // Lower-triangle symv while the trailing matrix is too large for the L2 (full rows otherwise:
-    // L2-resident, and the per-tile atomics would only add latency). Needs its tile accumulators
-    // (24 KB static) next to the dynamic shared memory and at most SYM_MAX_SLOTS tiles per CTA.
-    g.sym = (g_sym_min_m > 0 && m >= g_sym_min_m) ? 1 : 0;
-    g.sym_tile = static_cast<int>(std::min<long long>(256, round_up((m + 32) / 33, 4)));
-    {
-      const long long kk = (m + g.sym_tile - 1) / g.sym_tile;
-      const long long tiles_per_cta = (kk * (kk + 1) / 2 + grid - 1) / grid;
-      if (tiles_per_cta > SYM_MAX_SLOTS || smem > 200 * 1024) g.sym = 0;
-    }
+    g.sym = ps.sym;
+    g.sym_tile = ps.sym_tile;
     void* args[] = {&g};
     void* kern = g.sym ? reinterpret_cast<void*>(sytrd_panel_kernel<true>)
                        : reinterpret_cast<void*>(sytrd_panel_kernel<false>);
@@ -1428,8 +1460,18 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
       ep.C = p.Aw + static_cast<long long>(j0 + NB) * p.ldA + (j0 + NB);
       ep.ldc = p.ldA;
       ep.accumulate = 1;
+      // While the following panel reads only the lower triangle, only that half is updated
+      // (V W^T + W V^T is symmetric); when the panels switch back to full rows the block is
+      // mirrored once.
+      const int next_sym = (pi + 1 < p.npanels) ? shape_of(pi + 1).sym : 0;
+      ep.lower_only = next_sym;
       const int rc = gemm_tc(a, b, mt, mt, 2 * NB, -1, ep, st);
       if (rc) return rc;
+      if (g.sym && !next_sym) {
+        dim3 mgrid(static_cast<unsigned>((mt + 31) / 32), static_cast<unsigned>((mt + 31) / 32));
+        mirror_lower_kernel<<<mgrid, dim3(32, 8), 0, st>>>(ep.C, p.ldA, mt);
+        PTD_CHECK_LAUNCH();
+      }
     }
   }
 
