@@ -1,5 +1,6 @@
 """CPU tests of the host logic: config schema, wrappers, rank arithmetic, the C-ABI surface, the
 no-CPU-fallback rule, and the world_size-2 gloo path of ptdeco_b200.parallel."""
+import collections
 import ctypes
 import json
 import os
@@ -330,3 +331,63 @@ def test_memory_pressure_gate_without_cuda_is_a_no_op():
     if not torch.cuda.is_available():
         assert utils.relieve_gpu_memory_pressure() is False
     assert "relieve_gpu_memory_pressure" in utils.__all__ and "free_gpu_reserved_memory" in utils.__all__
+
+
+def test_artifact_round_trip_like_the_reference_readme(tmp_path):
+    """The reference's save / load recipe (README.md:56-105): decompose_config.json +
+    decompose_state_dict.pt written from a decomposed model, then a FRESH original model is
+    rebuilt, the config applied, the state dict loaded strictly -- and the fused fast-path modules
+    can be swapped in on either side without changing config or state-dict keys."""
+    import ptdeco_b200 as ptdeco
+    from ptdeco_b200 import modules
+
+    def build():
+        torch.manual_seed(11)
+        return torch.nn.Sequential(collections.OrderedDict(
+            stem=torch.nn.Conv2d(3, 8, 1), act=torch.nn.ReLU(), pool=torch.nn.AdaptiveAvgPool2d(1),
+            flat=torch.nn.Flatten(), fc1=torch.nn.Linear(8, 12), act2=torch.nn.ReLU(),
+            head=torch.nn.Linear(12, 5)))
+
+    # a decomposed model: two targets replaced by the two-factor modules the wrappers build
+    import ptdeco_b200.falor.decomposition as F
+    model = build().eval()
+    decompose_config = {}
+    for name, k in (("stem", 2), ("fc1", 3)):
+        F._wrap_in_place(model, name)
+        wrapper = model.get_submodule(name)
+        w = wrapper.get_weight_copy()
+        out_f, in_f = w.shape
+        q = torch.linalg.qr(torch.randn(out_f, out_f, generator=torch.Generator().manual_seed(k)))[0]
+        uk = q[:, :k].contiguous()
+        new = wrapper.get_decomposed_module(u=uk.T @ w, v=uk)
+        F._unwrap_in_place(model, name)
+        ptdeco.utils.replace_submodule_in_place(model, name, new)
+        cfg = ptdeco.utils.get_module_config(new)
+        cfg[ptdeco.utils.MODCONFIG_META_KEY] = {"proportion": k / min(in_f, out_f), "nsr_final": 0.0, "kl_final": 0.0}
+        decompose_config[name] = cfg
+    x = torch.randn(4, 3, 6, 6, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        y = model(x)
+    with open(tmp_path / "decompose_config.json", "wt") as f:
+        json.dump(decompose_config, f)
+    torch.save(model.state_dict(), tmp_path / "decompose_state_dict.pt")
+
+    # loading side, exactly the README's steps
+    fresh = build().eval()
+    with open(tmp_path / "decompose_config.json", "rt") as f:
+        loaded_cfg = json.load(f)
+    ptdeco.utils.apply_decompose_config_in_place(fresh, loaded_cfg)
+    fresh.load_state_dict(torch.load(tmp_path / "decompose_state_dict.pt"), strict=True)
+    assert modules.fuse_decomposed_modules_in_place(fresh) == 2
+    assert list(fresh.state_dict().keys()) == list(model.state_dict().keys())
+    assert ptdeco.utils.get_module_config(fresh.get_submodule("fc1")) == {
+        k: v for k, v in loaded_cfg["fc1"].items() if k != ptdeco.utils.MODCONFIG_META_KEY}
+    with torch.no_grad():
+        torch.testing.assert_close(fresh(x), y)
+    # and a checkpoint written from the fused model loads into plain reference-style modules
+    torch.save(fresh.state_dict(), tmp_path / "fused_state_dict.pt")
+    plain = build().eval()
+    ptdeco.utils.apply_decompose_config_in_place(plain, loaded_cfg)
+    plain.load_state_dict(torch.load(tmp_path / "fused_state_dict.pt"), strict=True)
+    with torch.no_grad():
+        torch.testing.assert_close(plain(x), y)
