@@ -70,9 +70,11 @@ int ptdeco_gemm(const void* A, int a_dtype, int a_mn_major, long long lda, const
  * D:425): A[d][lda] fp32 symmetric (lower triangle authoritative, torch's UPLO='L'), not modified.
  * evals[d] receives ALL eigenvalues ascending; U[d][ldu] receives in column c the eigenvector of
  * eigenvalue number d-k+c, i.e. the k largest in ascending order (k = d gives torch's full `u`).
- * d <= 96: one-CTA fp64 Jacobi. d > 96: blocked Householder tridiagonalisation (cooperative panel
- * kernel + tcgen05 trailing update), fp64 multisection + twisted-factorisation eigenvectors,
- * tcgen05 compact-WY back-transformation of the k wanted vectors. */
+ * d <= 32: one-CTA fp64 Jacobi. d > 32: Householder tridiagonalisation -- while the trailing block
+ * exceeds the chip's shared memory (d > ~2560) a cooperative blocked panel kernel with tcgen05
+ * trailing updates, then ONE cooperative launch that keeps the trailing block resident in the
+ * shared memory of all SMs (one grid-wide exchange per column) --, fp64 multisection +
+ * twisted-factorisation eigenvectors, tcgen05 compact-WY back-transformation of the k wanted vectors. */
 size_t ptdeco_eigh_workspace_bytes(int d, int k);
 int ptdeco_eigh(const float* A, int d, long long lda, int k, float* evals, float* U, long long ldu,
                 void* workspace, size_t workspace_bytes, void* stream);

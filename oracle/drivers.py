@@ -45,7 +45,7 @@ class _Tap(torch.nn.Module):
         x = self.last
         if isinstance(self.inner, torch.nn.Conv2d):
             x = x.permute(0, 2, 3, 1)
-        return x.reshape(-1, self.weight2d().shape[1]).detach().numpy()
+        return x.reshape(-1, self.weight2d().shape[1]).detach().float().numpy()  # bf16 -> exact fp32
 
     def weight2d(self) -> torch.Tensor:
         w = self.inner.weight.detach()
@@ -197,14 +197,18 @@ def falor_decompose_in_place(*, module, data_iterator, blacklisted_module_names=
 
 # ------------------------------------------------------------------------------------ dwain
 def dwain_eigenvectors(root, name: str, it, weight: np.ndarray, num_data_steps: int,
-                       decompose_in_float64: bool, return_cov: bool = False):
-    """D:211-244 with the target already tapped."""
+                       decompose_in_float64: bool, return_cov: bool = False, bf16: bool = False):
+    """D:211-244 with the target already tapped. bf16: the model's dtype is bfloat16, so
+    y = x W^T is a bf16 GEMM and every per-step product is rounded to bf16 (D:152, D:239-240)."""
     root.eval()
     tap = root.get_submodule(name)
     acc = np.float64 if decompose_in_float64 else np.float32
     Eyyt = np.zeros((weight.shape[0], weight.shape[0]), dtype=acc)
     for _ in range(num_data_steps):
         root(next(it))
+        if bf16:
+            P.update_Eyyt_in_place_bf16(Eyyt, P.bf16_round(tap.rows() @ weight.T))
+            continue
         P.update_Eyyt_in_place(Eyyt, tap.rows() @ weight.T)
     cov = Eyyt / num_data_steps
     u = P.dwain_get_eigenvectors(cov)
@@ -222,7 +226,10 @@ class _CovLinear(torch.nn.Module):
 
     def forward(self, x):
         y = x @ self.lin.weight.T
-        P.update_Eyyt_in_place(self.Eyyt, y.reshape(-1, self.lin.out_features).detach().numpy())
+        if y.dtype == torch.bfloat16:
+            P.update_Eyyt_in_place_bf16(self.Eyyt, y.reshape(-1, self.lin.out_features).detach().float().numpy())
+        else:
+            P.update_Eyyt_in_place(self.Eyyt, y.reshape(-1, self.lin.out_features).detach().numpy())
         if self.lin.bias is not None:
             y = y + self.lin.bias
         self.steps += 1
@@ -250,7 +257,9 @@ def dwain_precompute(module, names, num_splits, num_data_steps, it, f64) -> dict
         for n in sub:
             c = module.get_submodule(n)
             u = P.dwain_get_eigenvectors(c.Eyyt / c.steps)
-            out[n] = u.astype(_np_dtype(saved[n].weight.dtype))
+            # D:208: cast to the weight dtype (bf16 values kept in a float32 array)
+            out[n] = (P.bf16_round(u) if saved[n].weight.dtype == torch.bfloat16
+                      else u.astype(_np_dtype(saved[n].weight.dtype)))
         for n in sub:
             parent, key = _parent_and_key(module, n)
             setattr(parent, key, saved[n])
@@ -270,14 +279,23 @@ def dwain_process(root, name, it, loss_fn, nsr_thr, num_data_steps, num_metric_s
     tap = _Tap(orig)
     setattr(parent, key, tap)
     w_t = tap.weight2d().clone()
-    w = w_t.numpy()
+    bf16 = w_t.dtype == torch.bfloat16
+    w = w_t.float().numpy()
     d_out, d_in = w.shape
     full_rank = min(d_in, d_out)
     if full_rank == 1:
         setattr(parent, key, orig)
         return {"proportion": 1.0, "nsr_final": 0.0, "ppl_final": 0.0, "decomposed_module": None}
     if u_matrix is None:
-        u_matrix = dwain_eigenvectors(root, name, it, w, num_data_steps, f64)
+        u_matrix = dwain_eigenvectors(root, name, it, w, num_data_steps, f64, bf16=bf16)
+
+    def factors(rank):
+        if bf16:
+            return P.factors_bf16(w, P.top_k(u_matrix, rank))
+        return P.factors(w, P.top_k(u_matrix, rank).astype(w.dtype))
+
+    def as_weight(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(w_t.dtype)
     rank_best = rank_new = full_rank
     nsr_best = ppl_best = 0.0
     tried = False
@@ -288,13 +306,12 @@ def dwain_process(root, name, it, loss_fn, nsr_thr, num_data_steps, num_metric_s
         ppl_thr = drop / num_params * trade_off
         if drop == 0:
             continue
-        uk = P.top_k(u_matrix, rank_new).astype(w.dtype)
-        _, _, deco = P.factors(w, uk)
+        _, _, deco = factors(rank_new)
         tried = True
         nsr_new = ppl_new = diff_new = 0.0
         for _ in range(num_metric_steps):
             d = next(metric_it)
-            tap.put_weight(torch.from_numpy(np.ascontiguousarray(deco)))
+            tap.put_weight(as_weight(deco))
             y_deco = root(d)
             tap.put_weight(w_t)
             y_orig = root(d)
@@ -314,10 +331,8 @@ def dwain_process(root, name, it, loss_fn, nsr_thr, num_data_steps, num_metric_s
             rank_best, nsr_best, ppl_best = rank_new, nsr_new, ppl_new
     proportion = rank_best / full_rank
     if tried and rank_best != full_rank and P.is_num_params_reduced(proportion, d_in, d_out):
-        uk = P.top_k(u_matrix, rank_best).astype(w.dtype)
-        U, V, _ = P.factors(w, uk)
-        new = build_two_factor(orig, torch.from_numpy(np.ascontiguousarray(U)).T,
-                               torch.from_numpy(np.ascontiguousarray(V)).T)
+        U, V, _ = factors(rank_best)
+        new = build_two_factor(orig, as_weight(U).T, as_weight(V).T)
         drop = P.get_params_for_proportion(1.0, d_in, d_out) - P.get_params_for_proportion(
             proportion, d_in, d_out)
         # on success the tap is overwritten by the caller's swap (D:779)

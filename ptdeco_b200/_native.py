@@ -62,6 +62,13 @@ SIGNATURES = {
 }
 
 
+# ptdeco_debug_set keys of the low-rank forward's runtime switches <- environment variables
+LOWRANK_KNOBS = {200: "PTDECO_B200_FORCE_DECODE", 201: "PTDECO_B200_NO_DECODE",
+                 202: "PTDECO_B200_NO_FUSED", 203: "PTDECO_B200_NO_PERSISTENT",
+                 204: "PTDECO_B200_NO_TMA_STORE", 205: "PTDECO_B200_FUSED_ROT",
+                 206: "PTDECO_B200_FUSED_STAGES"}
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -78,6 +85,12 @@ def lib() -> ctypes.CDLL:
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
+        # Runtime switches of the forward kernels are read from the environment ONCE, here; the
+        # kernels' host code never calls getenv (tests flip them through ptdeco_debug_set).
+        for key, name in LOWRANK_KNOBS.items():
+            if os.environ.get(name) is not None:
+                v = os.environ[name]
+                handle.ptdeco_debug_set(key, int(v) if v.lstrip("-").isdigit() else 1)
         if os.environ.get("PTDECO_B200_DETERMINISTIC", "0") == "1":
             # Reproducible mode: no split-K, so every output element is accumulated by exactly one
             # CTA in a fixed order (the default splits short-and-wide reductions over CTAs and

@@ -13,6 +13,19 @@ from typing import Any, Optional
 
 import torch
 
+from . import linalg
+
+
+class StopForward(Exception):
+    """Raised by a wrapper in capture-only mode once it has seen its input (and produced its
+    output): the calibration forward of F:189 / D:237 discards the model output, so the layers
+    AFTER the target need not run. Caught by `calibration_forward`."""
+
+
+class PairLayoutError(RuntimeError):
+    """A paired rank trial reached the wrapper with a leading dimension that is not the doubled
+    batch (seq-first layouts, reshapes that fold the batch): pairing is not valid for this layer."""
+
 
 class WrappedModule(torch.nn.Module):
     """Method table of the reference's WrappedFALORModule / WrappedDWAINModule (F:29-48, D:19-38)."""
@@ -22,9 +35,11 @@ class WrappedModule(torch.nn.Module):
         self.input = torch.zeros(size=(0,))
         self.output: Optional[torch.Tensor] = None
         self.capture_output = False
-        # paired rank trial (see PairState): when set, the first half of the batch goes through
-        # this [out, in] weight and the second half through the layer's own
-        self.pair_weight: Optional[torch.Tensor] = None
+        self.capture_only = False  # raise StopForward after capturing (calibration forwards)
+        # rank trial (see set_trial): rows go through the two-factor op W2 (W1 x) instead of a
+        # materialised W2 W1 copied into the layer (F:347-348 / D:427-429 + set_weight)
+        self.trial_factors: Optional[tuple[torch.Tensor, torch.Tensor]] = None
+        self.trial_pair_batch = 0  # b > 0: batch is [2b, ...], first half decomposed, second original
 
     def get_weight_copy(self) -> torch.Tensor:
         raise NotImplementedError()
@@ -49,6 +64,46 @@ class WrappedModule(torch.nn.Module):
         """Last layer output as [N, out] rows (bias still included)."""
         raise NotImplementedError()
 
+    def output_covers_input_positions(self) -> bool:
+        """Whether the layer output has one row per INPUT position, i.e. the captured output can
+        stand in for the reference's y = x W^T over all input rows (F:125-126,159; D:115-116,239).
+        False for strided / padded 1x1 convs: there the covariance is formed from the input."""
+        return True
+
+    def set_trial(self, w1: torch.Tensor, w2: torch.Tensor, pair_batch: int = 0) -> None:
+        """Evaluate the layer as W2 (W1 x) + b (w1 [k, in], w2 [out, k]) until clear_trial():
+        every row, or with pair_batch = b only the first b entries of a [2b, ...] batch."""
+        dt = self.get_orig_module().weight.dtype
+        dt = dt if dt in (torch.float32, torch.bfloat16) else torch.float32
+        self.trial_factors = (w1.to(dt).contiguous(), w2.to(dt).contiguous())
+        self.trial_pair_batch = int(pair_batch)
+
+    def clear_trial(self) -> None:
+        self.trial_factors = None
+        self.trial_pair_batch = 0
+
+    def _orig_forward(self, x: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError()
+
+    def _factored_forward(self, x: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError()
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        self.input = x
+        if self.trial_factors is not None:
+            b = self.trial_pair_batch
+            if b == 0:
+                return self._factored_forward(x)
+            if x.dim() < 1 or x.shape[0] != 2 * b:
+                raise PairLayoutError(f"leading dim {tuple(x.shape)[:1]} is not the doubled batch {2 * b}")
+            return torch.cat([self._factored_forward(x[:b]), self._orig_forward(x[b:])], 0)
+        y = self._orig_forward(x)
+        if self.capture_output:
+            self.output = y
+        if self.capture_only:
+            raise StopForward()
+        return y
+
 
 class WrappedLinear(WrappedModule):
     def __init__(self, lin_orig: torch.nn.Module, name: Optional[str] = None):
@@ -57,17 +112,14 @@ class WrappedLinear(WrappedModule):
         self.lin_orig = lin_orig
         self.name = name
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        self.input = x
-        if self.pair_weight is not None:
-            b = x.shape[0] // 2
-            bias = self.lin_orig.bias
-            return torch.cat([torch.nn.functional.linear(x[:b], self.pair_weight, bias),
-                              torch.nn.functional.linear(x[b:], self.lin_orig.weight, bias)], 0)
-        y = self.lin_orig(x)
-        if self.capture_output:
-            self.output = y
-        return y
+    def _orig_forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.lin_orig(x)
+
+    def _factored_forward(self, x: torch.Tensor) -> torch.Tensor:
+        w1, w2 = self.trial_factors
+        rows = x.reshape(-1, self.lin_orig.in_features)
+        y = linalg.lowrank_forward(rows, w1, w2, self.lin_orig.bias)
+        return y.to(x.dtype).reshape(*x.shape[:-1], self.lin_orig.out_features)
 
     def get_weight_copy(self) -> torch.Tensor:
         return self.lin_orig.weight.detach().clone()
@@ -106,18 +158,32 @@ class WrappedConv2d1x1(WrappedModule):
                 and conv_orig.kernel_size[1] == 1 and conv_orig.groups == 1)
         self.conv_orig = conv_orig
         self.name = name
+        if not self.output_covers_input_positions():
+            logging.getLogger("ptdeco.utils.common").warning(
+                f"{name}: 1x1 conv with stride={conv_orig.stride} padding={conv_orig.padding}: like the "
+                "reference (F:125-126,136-147), the covariance uses ALL input positions and the "
+                "decomposed module is rebuilt WITHOUT stride / padding (its output shape changes); "
+                "blacklist such layers unless that is intended")
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        self.input = x
-        if self.pair_weight is not None:
-            b = x.shape[0] // 2
-            conv = self.conv_orig
-            return torch.cat([conv._conv_forward(x[:b], self.pair_weight[:, :, None, None], conv.bias),
-                              conv._conv_forward(x[b:], conv.weight, conv.bias)], 0)
-        y = self.conv_orig(x)
-        if self.capture_output:
-            self.output = y
-        return y
+    def output_covers_input_positions(self) -> bool:
+        c = self.conv_orig
+        return tuple(c.stride) == (1, 1) and c.padding in ((0, 0), 0, "valid")
+
+    def _orig_forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.conv_orig(x)
+
+    def _factored_forward(self, x: torch.Tensor) -> torch.Tensor:
+        w1, w2 = self.trial_factors
+        conv = self.conv_orig
+        if not self.output_covers_input_positions():
+            # strided / padded target: keep the layer's own geometry for the trial, as the
+            # reference does by copying the effective weight into the original conv (F:211-233)
+            h = conv._conv_forward(x, w1[:, :, None, None].to(x.dtype), None)
+            return torch.nn.functional.conv2d(h, w2[:, :, None, None].to(x.dtype), conv.bias)
+        n, c, hh, ww = x.shape
+        rows = x.permute(0, 2, 3, 1).reshape(-1, c)
+        y = linalg.lowrank_forward(rows, w1, w2, conv.bias)
+        return y.to(x.dtype).reshape(n, hh, ww, conv.out_channels).permute(0, 3, 1, 2)
 
     def get_weight_copy(self) -> torch.Tensor:
         return self.conv_orig.weight.detach().data[..., 0, 0].clone()
@@ -149,6 +215,22 @@ class WrappedConv2d1x1(WrappedModule):
         return torch.nn.Sequential(conv_1, conv_2)
 
 
+def calibration_forward(forward_fn, inputs: Any, wrapper: WrappedModule) -> None:
+    """One calibration forward of the user model (F:189 / D:237), stopped right after the wrapped
+    target produced its activation: the reference discards the model output of these calls, so the
+    rest of the network is dead work. PTDECO_B200_EARLY_EXIT=0 runs the whole forward."""
+    if os.environ.get("PTDECO_B200_EARLY_EXIT", "1") == "0":
+        forward_fn(inputs)
+        return
+    wrapper.capture_only = True
+    try:
+        forward_fn(inputs)
+    except StopForward:
+        pass
+    finally:
+        wrapper.capture_only = False
+
+
 def is_decomposeable_module(module: torch.nn.Module) -> bool:
     """F:402-408 / D:540-546: any nn.Linear (subclasses included) or a 1x1, groups=1 Conv2d."""
     return isinstance(module, torch.nn.Linear) or (
@@ -169,20 +251,39 @@ class PairState:
     forwards of the same batch, one with the decomposed weight copied into the layer and one with
     the original (F:211-233, D:247-278). The library owns the wrapped layer, so both variants can
     share ONE forward of the batch concatenated with itself: the wrapper sends the first half
-    through the decomposed weight and the second half through the original. Same arithmetic per
+    through the two-factor op and the second half through the original layer. Same arithmetic per
     sample for any model that treats batch elements independently in eval mode; half the kernel
     launches (small models are launch-bound) and better-filled GEMMs.
 
-    Safety: the first trial batch of a decompose call is evaluated BOTH ways; pairing is kept only
-    if the two agree (relative Frobenius error of the logits within the dtype's rounding noise)
-    and the paired forward is measurably faster, so a model with a batch-dependent forward, an
-    unusual batch layout, or a forward that already fills the GPU (an LLM at 2048 tokens: measured
-    slower paired) keeps the reference's two-forward path. PTDECO_B200_PAIRED_TRIALS=0 disables it."""
+    Safety: for EVERY layer the first trial batch is evaluated both ways and pairing is used for
+    the rest of that layer's search only if the two agree (relative Frobenius error of the logits
+    within the dtype's rounding noise); the wrapper additionally checks that the tensor it receives
+    still has the doubled batch as its leading dimension (PairLayoutError otherwise). A model with
+    a batch-dependent forward or an unusual batch layout keeps the reference's two-forward path.
 
-    def __init__(self) -> None:
-        self.mode = "off" if os.environ.get("PTDECO_B200_PAIRED_TRIALS", "1") == "0" else "unknown"
+    Whether pairing is attempted at all is a fixed policy, never a timing measurement:
+    PTDECO_B200_PAIRED_TRIALS=1 / 0 forces it on / off; the default ("auto") pairs models of at
+    most 100 M parameters (launch-bound forwards) and leaves larger ones -- whose forward already
+    fills the GPU: an 8B decoder at 2048 tokens measured slower paired -- on two forwards."""
+
+    AUTO_MAX_PARAMS = 100_000_000
+
+    def __init__(self, root_module: Optional[torch.nn.Module] = None) -> None:
+        env = os.environ.get("PTDECO_B200_PAIRED_TRIALS", "auto")
+        if env == "0":
+            self.enabled = False
+        elif env == "1":
+            self.enabled = True
+        else:
+            n = sum(p.numel() for p in root_module.parameters()) if root_module is not None else 0
+            self.enabled = root_module is not None and n <= self.AUTO_MAX_PARAMS
+        self.mode = "unverified" if self.enabled else "off"  # state for the CURRENT layer
         self.paired_forwards = 0
-        self.probe: Optional[dict] = None  # what the verification measured
+        self.probe: Optional[dict] = None  # what the last verification measured
+
+    def begin_layer(self) -> None:
+        """Every layer re-verifies: its input layout can differ from the previous layer's."""
+        self.mode = "unverified" if self.enabled else "off"
 
     @staticmethod
     def _double(inputs: Any) -> tuple[Optional[Any], int]:
@@ -199,62 +300,50 @@ class PairState:
         return None, 0
 
     def _paired(self, forward_fn, wrapper: WrappedModule, inputs: Any,
-                deco_weight: torch.Tensor) -> Optional[tuple[torch.Tensor, torch.Tensor]]:
+                factors: tuple[torch.Tensor, torch.Tensor]) -> Optional[tuple[torch.Tensor, torch.Tensor]]:
         doubled, b = self._double(inputs)
         if doubled is None:
             return None
-        wrapper.pair_weight = deco_weight
+        wrapper.set_trial(factors[0], factors[1], pair_batch=b)
         try:
             yy = forward_fn(doubled)
+        except PairLayoutError:
+            return None
         finally:
-            wrapper.pair_weight = None
+            wrapper.clear_trial()
         if not isinstance(yy, torch.Tensor) or yy.dim() < 1 or yy.shape[0] != 2 * b:
             return None
         self.paired_forwards += 1
         return yy[:b], yy[b:]
 
-    def forward_pair(self, forward_fn, wrapper: WrappedModule, inputs: Any, orig_weight: torch.Tensor,
-                     deco_weight: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
-        """(y_deco, y_orig) of one trial batch. Leaves the original weight in the layer."""
+    def forward_pair(self, forward_fn, wrapper: WrappedModule, inputs: Any,
+                     factors: tuple[torch.Tensor, torch.Tensor]) -> tuple[torch.Tensor, torch.Tensor]:
+        """(y_deco, y_orig) of one trial batch; `factors` = (W1 [k, in], W2 [out, k]). The layer's
+        own weight is never touched."""
         if self.mode == "on":
-            out = self._paired(forward_fn, wrapper, inputs, deco_weight)
+            out = self._paired(forward_fn, wrapper, inputs, factors)
             if out is not None:
                 return out
             self.mode = "off"
-        probing = self.mode == "unknown" and deco_weight.is_cuda
-        if probing:
-            torch.cuda.synchronize(deco_weight.device)
-            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-            e[0].record()
-        wrapper.set_weight(deco_weight)
-        y_deco = forward_fn(inputs)
-        wrapper.set_weight(orig_weight)
+        wrapper.set_trial(factors[0], factors[1])
+        try:
+            y_deco = forward_fn(inputs)
+        finally:
+            wrapper.clear_trial()
         y_orig = forward_fn(inputs)
-        if probing:
-            # First trial batch of the call: evaluate it the paired way too (once to warm the
-            # allocator up for the doubled shapes, once timed). Pairing is kept only if the results
-            # agree AND the paired forward is faster -- it halves kernel launches, which pays for
-            # launch-bound models and not for ones whose forward already fills the GPU.
-            e[1].record()
+        if self.mode == "unverified":
+            # first trial batch of this layer: evaluate it the paired way too and compare
             self.mode = "off"
-            out = self._paired(forward_fn, wrapper, inputs, deco_weight)
+            out = self._paired(forward_fn, wrapper, inputs, factors)
             if out is not None and isinstance(y_orig, torch.Tensor) and out[0].shape == y_deco.shape:
-                e[2].record()
-                out = self._paired(forward_fn, wrapper, inputs, deco_weight)
-                e[3].record()
                 tol = 1e-4 if y_orig.dtype in (torch.float32, torch.float64) else 3e-2
                 ref = torch.linalg.vector_norm(y_orig.float()).clamp_min(1e-30)
                 err = max(float(torch.linalg.vector_norm(out[0].float() - y_deco.float()) / ref),
                           float(torch.linalg.vector_norm(out[1].float() - y_orig.float()) / ref))
-                self.probe = {"rel_err": err, "two_forwards_ms": e[0].elapsed_time(e[1]),
-                              "paired_ms": e[2].elapsed_time(e[3])}
-                # NaN fails the comparisons and keeps pairing off
-                if err <= tol and self.probe["paired_ms"] < 0.9 * self.probe["two_forwards_ms"]:
+                self.probe = {"rel_err": err, "layer": getattr(wrapper, "name", None)}
+                if err <= tol:  # NaN fails the comparison and keeps pairing off
                     self.mode = "on"
-                logging.getLogger("ptdeco.utils.common").info(
-                    f"paired rank trials {self.mode}: rel_err={err:.2e} "
-                    f"two_forwards={self.probe['two_forwards_ms']:.2f} ms paired={self.probe['paired_ms']:.2f} ms")
+                logging.getLogger("ptdeco.utils.common").debug(
+                    f"paired rank trials {self.mode} for {self.probe['layer']}: rel_err={err:.2e}")
             self.paired_forwards = 0
-        elif self.mode == "unknown":
-            self.mode = "off"
         return y_deco, y_orig

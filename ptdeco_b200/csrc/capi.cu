@@ -198,10 +198,15 @@ int ptdeco_kl_metric(const void* student, const void* teacher, int dtype, long l
 void ptdeco_debug_set(int key, long long value) {
   if (key == 100) ptd::eigh_debug_profile(static_cast<int>(value));
   else if (key == 101) ptd::eigh_debug_sym_min_m(static_cast<int>(value));
+  else if (key == 102) ptd::eigh_debug_resident(static_cast<int>(value), 0, -1);
+  else if (key == 103) ptd::eigh_debug_resident(1, static_cast<int>(value), -1);
+  else if (key == 104) ptd::eigh_debug_resident(1, 0, static_cast<int>(value));
+  else if (key == 105) ptd::eigh_debug_bisect_narrow(static_cast<int>(value));
+  else if (key >= 200 && key < 208) ptd::lowrank_debug_set(key - 200, value);
   else ptd::gemm_tc_debug_set(key, value);
 }
 long long ptdeco_debug_get(int key) {
-  if (key >= 100 && key < 108) return ptd::eigh_debug_phase_cycles(key - 100);
+  if (key >= 100 && key < 116) return ptd::eigh_debug_phase_cycles(key - 100);
   return ptd::gemm_tc_last_launch_info(key);
 }
 

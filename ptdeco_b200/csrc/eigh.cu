@@ -18,7 +18,11 @@ namespace ptd {
 
 namespace {
 
-constexpr int JACOBI_MAX = 96;
+constexpr int JACOBI_MAX = 96;      // largest d the one-CTA Jacobi kernel can hold
+constexpr int JACOBI_DEFAULT = 32;  // largest d it is USED for: beyond, the resident path is faster
+                                    // (B200: d = 96 0.72 vs 4.85 ms; at d = 32 0.28 vs 0.40 ms, but
+                                    // the fp64 Jacobi's 1e-8 orthogonality is what keeps the
+                                    // reference's full-rank reconstruction test under its 1e-6)
 constexpr int NB = 64;  // Householder panel width
 constexpr int PANEL_THREADS = 512;
 constexpr int PANEL_WARPS = PANEL_THREADS / 32;
@@ -231,7 +235,7 @@ struct PanelArgs {
 };
 
 // P1 | barrier A | reflector + v | symv + dots | barrier B | P3   (cycles of CTA 0, summed over columns)
-__device__ unsigned long long g_phase_cycles[8];
+__device__ unsigned long long g_phase_cycles[16];
 
 // Grid barrier of the cooperative panel kernel: release-arrive on one counter, acquire-poll.
 // (Measured alternatives, both slower: per-CTA release flags written by the last arriver, and a
@@ -769,6 +773,426 @@ __global__ void panel_split_kernel(const float* __restrict__ Vp, const float* __
   }
 }
 
+// ============================================================================ resident sytd2
+// Tridiagonalisation of a trailing block that FITS THE CHIP'S SHARED MEMORY (m0 <= ~2560 on 148
+// SMs): rows are dealt cyclically to the CTAs of one cooperative launch and stay in shared memory
+// for the whole reduction, so a Householder column costs no trip over the matrix through L2/HBM.
+// The unblocked recurrence (LAPACK sytd2) is restructured so that ONE grid-wide exchange per
+// column suffices (the blocked panel kernel needs two):
+//   * the rank-2 update of column i-1 (v_{i-1}, w_{i-1}) is applied on the fly while the symv of
+//     column i streams over the rows (one read-modify-write pass over shared memory),
+//   * every CTA then publishes its rows of p = A v_i, and the owner of row i+1 publishes that row;
+//     one release-arrive on the column's own counter, ONE thread per CTA polls it (measured on a
+//     B200, tools/micro/exchange_bench.cu: 1.9-2.0 us per round whatever m; self-validating tagged
+//     packets polled by every thread cost 5-6.6 us -- 75k pollers swamp the L2),
+//   * every CTA reads p and the row back through L2 and REDUNDANTLY computes w_i, column i+1 and
+//     the next reflector with identical arithmetic, so all CTAs agree bit for bit without a
+//     second exchange.
+// The exchange buffers are double-buffered by column parity: a CTA can publish column i+1 only
+// after passing the barrier of column i, i.e. after every CTA finished reading column i-1.
+constexpr int RES_THREADS = 512;
+constexpr int RES_WARPS = RES_THREADS / 32;
+constexpr int RES_MAX_NLOC = 32;   // local rows per CTA
+constexpr int RES_SLOTS = 2;       // 4-column chunks per thread: covers row lengths up to 4096
+constexpr int RES_MAX_L = 4 * RES_THREADS * RES_SLOTS;
+
+struct ResArgs {
+  const float* A;       // working copy (both triangles valid); the block starts at (j0, j0)
+  long long ldA;
+  int j0, m0, L, nloc;  // L = m0 rounded up to 4; nloc = ceil(m0 / grid)
+  float* VT;            // [m0][ldvt]: row i = reflector of column j0 + i (local row index), pre-zeroed
+  long long ldvt;
+  float* dvec;          // [d]
+  float* evec;          // [d]
+  float* taus;          // [d]
+  float* xP;            // [2][L] exchanged symv results
+  float* xR;            // [2][L] exchanged row
+  unsigned* ctr;        // [m0] arrival counter of every column (pre-zeroed)
+  int prof;
+};
+
+// Sum over the CTA; every thread gets the same value (identical order in every CTA): fp32 inside
+// a warp (<= 8 terms per lane, 5 shuffles), fp64 across the 16 warps.
+__device__ __forceinline__ double res_block_sum(float v, float* buf, int warp, int lane) {
+  v = warp_sum(v);
+  if (lane == 0) buf[warp] = v;
+  __syncthreads();
+  double s = 0.0;
+#pragma unroll
+  for (int w = 0; w < RES_WARPS; ++w) s += static_cast<double>(buf[w]);
+  return s;
+}
+
+// Sums over the 32 lanes of 8 per-lane values with 9 shuffles instead of 40 (see reduce16_packed):
+// every lane returns the full sum of v[4*b4 + 2*b3 + b2] (b_k = bit k of the lane index).
+__device__ __forceinline__ float reduce8_packed(const float (&v)[8], int lane) {
+  float a4[4], a2[2];
+  const bool u4 = (lane & 16) != 0, u3 = (lane & 8) != 0, u2 = (lane & 4) != 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    a4[j] = (u4 ? v[j + 4] : v[j]) + __shfl_xor_sync(0xffffffffu, u4 ? v[j] : v[j + 4], 16);
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+    a2[j] = (u3 ? a4[j + 2] : a4[j]) + __shfl_xor_sync(0xffffffffu, u3 ? a4[j] : a4[j + 2], 8);
+  float a1 = (u2 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, u2 ? a2[0] : a2[1], 4);
+  a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+  a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+  return a1;
+}
+
+// Reflector of column n from the full column a (this thread's chunks): d_n = a[n], alpha = a[n+1],
+// x = a[n+2:]. Writes v (1 at n+1, zeros up to n) into vnext, returns tau. Uniform over the CTA.
+struct ResReflector { float tau, beta, dn; };
+
+__global__ void __launch_bounds__(RES_THREADS, 1) sytd2_resident_kernel(const ResArgs g) {
+  extern __shared__ float smf[];
+  const int L = g.L, m0 = g.m0;
+  const int G = gridDim.x, cta = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* As = smf;                                        // [nloc][L]
+  float* vb = As + static_cast<size_t>(g.nloc) * L;       // [3][L] rotating v_{i-1}, v_i, v_{i+1}
+  float* wprev = vb + 3 * L;                              // [L]
+  float2* rowvw = reinterpret_cast<float2*>(wprev + L);   // [RES_MAX_NLOC] (v_{i-1}[r], w_{i-1}[r]) of own rows
+  float* red = reinterpret_cast<float*>(rowvw + RES_MAX_NLOC);  // [RES_WARPS][RES_MAX_NLOC]
+  __shared__ float sred[2][RES_WARPS];
+  __shared__ float s_b[4];
+  const int nrows = (m0 > cta) ? (m0 - cta + G - 1) / G : 0;  // rows cta, cta + G, ...
+  const int nq = L >> 2;
+
+  const bool prof = g.prof && cta == 0 && tid == 0;
+  long long tp = prof ? clock64() : 0;
+#define RES_PHASE(k)                                             \
+  if (prof) {                                                    \
+    const long long tn = clock64();                              \
+    atomicAdd(&g_phase_cycles[k], (unsigned long long)(tn - tp)); \
+    tp = tn;                                                     \
+  }
+
+  // ---- own rows into shared memory
+  for (int lr = 0; lr < nrows; ++lr) {
+    const float* src = g.A + static_cast<long long>(g.j0 + cta + lr * G) * g.ldA + g.j0;
+    for (int q = tid; q < nq; q += RES_THREADS) {
+      const int c = q << 2;
+      float4 x;
+      if (c + 3 < m0) {
+        x = __ldg(reinterpret_cast<const float4*>(src + c));
+      } else {
+        x.x = (c < m0) ? src[c] : 0.f;
+        x.y = (c + 1 < m0) ? src[c + 1] : 0.f;
+        x.z = (c + 2 < m0) ? src[c + 2] : 0.f;
+        x.w = 0.f;
+      }
+      *reinterpret_cast<float4*>(As + static_cast<size_t>(lr) * L + c) = x;
+    }
+  }
+  for (int c = tid; c < 3 * L + L; c += RES_THREADS) vb[c] = 0.f;  // v buffers and wprev
+  __syncthreads();
+
+  // Reflector of column n from this thread's elements a[s][e] of the full column (chunk base
+  // columns cb[s]); publishes d / e / tau / v through CTA (n mod G). Returns tau.
+  auto make_reflector = [&](const float (&a)[RES_SLOTS][4], const int (&cb)[RES_SLOTS],
+                            const bool (&live)[RES_SLOTS], int n, float* vnext, int redbuf) -> float {
+    float part = 0.f;
+#pragma unroll
+    for (int s = 0; s < RES_SLOTS; ++s)
+      if (live[s]) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = cb[s] + e;
+          if (c == n) s_b[1] = a[s][e];
+          if (c == n + 1) s_b[2] = a[s][e];
+          if (c >= n + 2 && c < m0) part += a[s][e] * a[s][e];
+        }
+      }
+    const float xnorm2 = static_cast<float>(res_block_sum(part, sred[redbuf], warp, lane));
+    const float dn = s_b[1];
+    float tau = 0.f, beta = 0.f, scale = 0.f;
+    if (n + 1 < m0) {
+      // working-precision reflector (LAPACK slarfg); 512 threads doing this in fp64 would cost
+      // more than the whole symv pass
+      const float alpha = s_b[2];
+      beta = alpha;
+      if (xnorm2 > 0.f) {
+        beta = -copysignf(sqrtf(alpha * alpha + xnorm2), alpha);
+        tau = (beta - alpha) / beta;
+        scale = 1.f / (alpha - beta);
+      }
+    }
+    const bool writer = cta == (n % G);
+#pragma unroll
+    for (int s = 0; s < RES_SLOTS; ++s)
+      if (live[s]) {
+        float4 v;
+        float* vv = reinterpret_cast<float*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = cb[s] + e;
+          vv[e] = (c >= n + 2 && c < m0) ? a[s][e] * scale : ((c == n + 1 && c < m0) ? 1.f : 0.f);
+        }
+        *reinterpret_cast<float4*>(vnext + cb[s]) = v;
+        if (writer && n + 1 < m0)
+          *reinterpret_cast<float4*>(g.VT + static_cast<long long>(n) * g.ldvt + cb[s]) = v;
+      }
+    if (writer && tid == 0) {
+      g.dvec[g.j0 + n] = dn;
+      if (n + 1 < m0) {
+        g.evec[g.j0 + n] = beta;
+        g.taus[g.j0 + n] = tau;
+      }
+    }
+    return tau;
+  };
+
+  int cur = 0;  // vb[cur] = v_i, vb[(cur+2)%3] = v_{i-1}, vb[(cur+1)%3] receives v_{i+1}
+  float tau;
+  {  // ---- reflector of column 0 straight from the global copy (row j0 == column j0)
+    float a[RES_SLOTS][4];
+    int cb[RES_SLOTS];
+    bool live[RES_SLOTS];
+    const float* src = g.A + static_cast<long long>(g.j0) * g.ldA + g.j0;
+#pragma unroll
+    for (int s = 0; s < RES_SLOTS; ++s) {
+      const int q = tid + s * RES_THREADS;
+      live[s] = q < nq;
+      cb[s] = q << 2;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) a[s][e] = (live[s] && cb[s] + e < m0) ? src[cb[s] + e] : 0.f;
+    }
+    tau = make_reflector(a, cb, live, 0, vb + cur * L, 0);
+  }
+  __syncthreads();
+  RES_PHASE(0)
+
+  for (int i = 0; i + 1 < m0; ++i) {
+    const int q0 = (i + 1) >> 2;
+    float* vcur = vb + cur * L;
+    const float* vprev = vb + ((cur + 2) % 3) * L;
+    float* vnext = vb + ((cur + 1) % 3) * L;
+    const int lr0 = (i + 1 > cta) ? (i + 1 - cta + G - 1) / G : 0;  // first local row >= i + 1
+    float* P = g.xP + static_cast<size_t>(i & 1) * L;
+    float* R = g.xR + static_cast<size_t>(i & 1) * L;
+
+    if (tid < nrows) {
+      const int r = cta + tid * G;
+      rowvw[tid] = make_float2(vprev[r], wprev[r]);
+    }
+    float4 v4[RES_SLOTS], vp4[RES_SLOTS], wp4[RES_SLOTS];
+    int cb[RES_SLOTS];
+    bool live[RES_SLOTS];
+#pragma unroll
+    for (int s = 0; s < RES_SLOTS; ++s) {
+      const int q = q0 + tid + s * RES_THREADS;
+      live[s] = q < nq;
+      cb[s] = q << 2;
+      if (live[s]) {
+        v4[s] = *reinterpret_cast<const float4*>(vcur + cb[s]);
+        vp4[s] = *reinterpret_cast<const float4*>(vprev + cb[s]);
+        wp4[s] = *reinterpret_cast<const float4*>(wprev + cb[s]);
+      } else {
+        v4[s] = vp4[s] = wp4[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    __syncthreads();
+    RES_PHASE(1)
+
+    // ---- fused pass: pending rank-2 update of column i-1, then the symv row dots against v_i
+    const bool own_next = lr0 < nrows && cta + lr0 * G == i + 1;  // this CTA holds row i+1
+    for (int lr8 = lr0; lr8 < nrows; lr8 += 8) {
+      float part[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int lr = lr8 + u;
+        part[u] = 0.f;
+        if (lr < nrows) {
+          const float2 rw = rowvw[lr];
+          float* arow = As + static_cast<size_t>(lr) * L;
+#pragma unroll
+          for (int s = 0; s < RES_SLOTS; ++s)
+            if (live[s]) {
+              float4 a4 = *reinterpret_cast<float4*>(arow + cb[s]);
+              a4.x -= rw.x * wp4[s].x + rw.y * vp4[s].x;
+              a4.y -= rw.x * wp4[s].y + rw.y * vp4[s].y;
+              a4.z -= rw.x * wp4[s].z + rw.y * vp4[s].z;
+              a4.w -= rw.x * wp4[s].w + rw.y * vp4[s].w;
+              *reinterpret_cast<float4*>(arow + cb[s]) = a4;
+              part[u] += a4.x * v4[s].x + a4.y * v4[s].y + a4.z * v4[s].z + a4.w * v4[s].w;
+              if (own_next && lr == lr0)  // row i+1 (updated through column i-1) for everybody
+                __stcg(reinterpret_cast<float4*>(R + cb[s]), a4);
+            }
+        }
+      }
+      const float rsum = reduce8_packed(part, lane);
+      if ((lane & 3) == 0) {
+        const int lr = lr8 + (((lane >> 4) & 1) << 2) + (((lane >> 3) & 1) << 1) + ((lane >> 2) & 1);
+        if (lr < nrows) red[warp * RES_MAX_NLOC + lr] = rsum;
+      }
+    }
+    RES_PHASE(2)
+    __syncthreads();
+    if (warp == 0) {  // nrows <= 32: lane = local row
+      if (lane >= lr0 && lane < nrows) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < RES_WARPS; ++w) s += red[w * RES_MAX_NLOC + lane];
+        __stcg(P + cta + lane * G, s);
+      }
+      __syncwarp();
+      if (lane == 0) {  // arrive (release: the row stores above were ordered by the barrier) and wait
+        unsigned* c = g.ctr + i;
+        RES_PHASE(3)
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(c) : "memory");
+        RES_PHASE(4)
+        unsigned v, polls = 0;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+          if (++polls > (1u << 26)) __trap();  // never hang the box on a lost CTA
+        } while (v < static_cast<unsigned>(G));
+        RES_PHASE(5)
+      }
+    }
+    __syncthreads();
+
+    // ---- gather: p (all live rows) and row i+1, for this thread's columns (through L2)
+    float pr[RES_SLOTS][4], ar[RES_SLOTS][4];
+#pragma unroll
+    for (int s = 0; s < RES_SLOTS; ++s) {
+      float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f), r4 = p4;
+      if (live[s]) {
+        p4 = __ldcg(reinterpret_cast<const float4*>(P + cb[s]));
+        r4 = __ldcg(reinterpret_cast<const float4*>(R + cb[s]));
+      }
+      const float* pp = reinterpret_cast<const float*>(&p4);
+      const float* rr = reinterpret_cast<const float*>(&r4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = cb[s] + e;
+        const bool in = live[s] && c >= i + 1 && c < m0;  // the rest is stale / padding
+        pr[s][e] = in ? pp[e] : 0.f;
+        ar[s][e] = in ? rr[e] : 0.f;
+      }
+    }
+
+    // ---- w_i = tau p - (tau^2/2)(p^T v) v ; column i+1 = row i+1 - w_i - w_i[i+1] v_i
+    float part = 0.f;
+#pragma unroll
+    for (int s = 0; s < RES_SLOTS; ++s) {
+      const float* vv = reinterpret_cast<const float*>(&v4[s]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        part += pr[s][e] * vv[e];
+        if (live[s] && cb[s] + e == i + 1) s_b[0] = pr[s][e];
+      }
+    }
+    RES_PHASE(6)
+    const float pv = static_cast<float>(res_block_sum(part, sred[0], warp, lane));
+    RES_PHASE(7)
+    const float alpha = -0.5f * tau * tau * pv;
+    const float w1 = tau * s_b[0] + alpha;  // v_i[i+1] = 1
+    float a[RES_SLOTS][4];
+#pragma unroll
+    for (int s = 0; s < RES_SLOTS; ++s) {
+      const float* vv = reinterpret_cast<const float*>(&v4[s]);
+      float4 w4;
+      float* ww = reinterpret_cast<float*>(&w4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = cb[s] + e;
+        const bool in = live[s] && c >= i + 1 && c < m0;
+        ww[e] = in ? tau * pr[s][e] + alpha * vv[e] : 0.f;
+        a[s][e] = in ? ar[s][e] - ww[e] - w1 * vv[e] : 0.f;
+      }
+      if (live[s]) *reinterpret_cast<float4*>(wprev + cb[s]) = w4;
+    }
+    tau = make_reflector(a, cb, live, i + 1, vnext, 1);
+    cur = (cur + 1) % 3;
+    RES_PHASE(8)
+    __syncthreads();
+    RES_PHASE(9)
+  }
+#undef RES_PHASE
+}
+
+// Compact-WY factor of one panel of reflectors stored as ROWS of VT (the resident kernel's
+// layout): T[a][b] = -tau_b * sum_{c=a}^{b-1} T[a][c] (v_c . v_b), T[b][b] = tau_b (LAPACK larft,
+// forward / columnwise; the panel kernel builds the same T on the fly). One CTA per panel.
+__global__ void __launch_bounds__(256) larft_rows_kernel(const float* __restrict__ VT, long long ldvt,
+                                                         int m0, int L, const float* __restrict__ taus,
+                                                         float* __restrict__ Tmats) {
+  __shared__ float tile[NB][NB + 1];  // staging of VT columns, then T
+  __shared__ float Gs[NB][NB + 1];
+  float (*Ts)[NB + 1] = tile;
+  const int i0 = blockIdx.x * NB;
+  const int nc = min(NB, m0 - i0);
+  const int tid = threadIdx.x;
+  const int ta = (tid >> 4) << 2, tb = (tid & 15) << 2;
+  float acc[4][4];
+#pragma unroll
+  for (int x = 0; x < 4; ++x)
+#pragma unroll
+    for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+  for (int c0 = (i0 / NB) * NB; c0 < L; c0 += NB) {  // reflector i0 + a is zero up to column i0 + a
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+      const int a = idx / NB, c = idx % NB;
+      tile[a][c] = (a < nc && c0 + c < L) ? VT[static_cast<long long>(i0 + a) * ldvt + c0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int c = 0; c < NB; ++c) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) { av[x] = tile[ta + x][c]; bv[x] = tile[tb + x][c]; }
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] += av[x] * bv[y];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int x = 0; x < 4; ++x)
+#pragma unroll
+    for (int y = 0; y < 4; ++y) { Gs[ta + x][tb + y] = acc[x][y]; Ts[ta + x][tb + y] = 0.f; }
+  __syncthreads();
+  for (int b = 0; b < nc; ++b) {
+    const float tau = taus[i0 + b];
+    if (tid < b) {
+      float s = 0.f;
+      for (int c = tid; c < b; ++c) s += Ts[tid][c] * Gs[c][b];
+      Ts[tid][b] = -tau * s;
+    } else if (tid == b) {
+      Ts[b][b] = tau;
+    }
+    __syncthreads();
+  }
+  float* T = Tmats + static_cast<size_t>(blockIdx.x) * NB * NB;
+  for (int idx = tid; idx < NB * NB; idx += 256) T[idx] = Ts[idx / NB][idx % NB];
+}
+
+// Vs[seg][(j0 + c)][(j0 + i)] = split(VT[i][c]): the reflectors as the bf16x3 COLUMNS the
+// back-transformation reads (same layout panel_split_kernel produces).
+__global__ void vt_split_kernel(const float* __restrict__ VT, long long ldvt, int m0, int j0,
+                                __nv_bfloat16* __restrict__ Vs, long long ldv, long long vs_seg) {
+  __shared__ float tile[32][33];
+  const int bi = blockIdx.y * 32, bc = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int yy = ty; yy < 32; yy += 8) {
+    const int i = bi + yy, c = bc + tx;
+    tile[yy][tx] = (i < m0 && c < m0) ? VT[static_cast<long long>(i) * ldvt + c] : 0.f;
+  }
+  __syncthreads();
+  for (int yy = ty; yy < 32; yy += 8) {
+    const int c = bc + yy, i = bi + tx;
+    if (c < m0 && i < m0) {
+      __nv_bfloat16 h, mm, l;
+      split3(tile[tx][yy], h, mm, l);
+      const long long o = static_cast<long long>(j0 + c) * ldv + j0 + i;
+      Vs[o] = h;
+      Vs[vs_seg + o] = mm;
+      Vs[2 * vs_seg + o] = l;
+    }
+  }
+}
+
 // ============================================================================ tridiagonal stage
 struct TriBufs {
   double* D;     // [d]
@@ -884,7 +1308,10 @@ __device__ __forceinline__ int sturm_count(const double* __restrict__ D,
 // 8 lanes cost 2.5x the arithmetic of plain bisection (32 lanes: 6.4x) and still give the FP64 pipe
 // 8 d independent recurrences to overlap.
 // first = 1: start from the Gershgorin interval of the block; else continue from lamA/lamB.
-constexpr int LPE = 16;
+// Small d: 16 lanes (the chain of d dependent divisions per pass is the cost, so few passes);
+// d >= 1536: 4 lanes (the fp64 pipe is the cost: 5-way multisection needs 96 Sturm counts per
+// eigenvalue for the two launches below against 240 with 17-way).
+template <int LPE>
 __global__ void bisect_kernel(TriBufs b, int d, int count, const int* __restrict__ sel, int first,
                               int passes) {
   const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1013,23 +1440,48 @@ __global__ void __launch_bounds__(64) eigvec_kernel(TriBufs b, int d, int k) {
   const bool work = act && !single;
   // ---- phase A: the two pivot recurrences
   if (work) {
+    // D / E are fetched eight rows ahead through the read-only path: the recurrence is one
+    // dependent fp64 division per row, and a load issued inside it would add its latency to every
+    // row (the stores to Dp / Dm keep the compiler from hoisting plain loads)
     if (role == 0) {
-      double dp = b.D[lo] - lam;
+      double dp = __ldg(b.D + lo) - lam;
       b.Dp[lo * K + c] = dp;
-      for (int i = lo; i < hi; ++i) {
-        const double e = b.E[i];
-        const double l = e / guard_piv(dp, pivmin);
-        dp = (b.D[i + 1] - lam) - l * e;
-        b.Dp[(i + 1) * K + c] = dp;
+      for (int i0 = lo; i0 < hi; i0 += 8) {
+        double ev[8], dv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const bool ok = i0 + u < hi;
+          ev[u] = ok ? __ldg(b.E + i0 + u) : 0.0;
+          dv[u] = ok ? __ldg(b.D + i0 + u + 1) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (i0 + u < hi) {
+            const double l = ev[u] / guard_piv(dp, pivmin);
+            dp = (dv[u] - lam) - l * ev[u];
+            b.Dp[(i0 + u + 1) * K + c] = dp;
+          }
+        }
       }
     } else {
-      double dm = b.D[hi] - lam;
+      double dm = __ldg(b.D + hi) - lam;
       b.Dm[hi * K + c] = dm;
-      for (int i = hi - 1; i >= lo; --i) {
-        const double e = b.E[i];
-        const double uu = e / guard_piv(dm, pivmin);
-        dm = (b.D[i] - lam) - uu * e;
-        b.Dm[i * K + c] = dm;
+      for (int i0 = hi - 1; i0 >= lo; i0 -= 8) {
+        double ev[8], dv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const bool ok = i0 - u >= lo;
+          ev[u] = ok ? __ldg(b.E + i0 - u) : 0.0;
+          dv[u] = ok ? __ldg(b.D + i0 - u) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (i0 - u >= lo) {
+            const double uu = ev[u] / guard_piv(dm, pivmin);
+            dm = (dv[u] - lam) - uu * ev[u];
+            b.Dm[(i0 - u) * K + c] = dm;
+          }
+        }
       }
     }
   }
@@ -1054,7 +1506,7 @@ __global__ void __launch_bounds__(64) eigvec_kernel(TriBufs b, int d, int k) {
         for (int u = 0; u < 8; ++u) {
           const int i = i0 - u;
           if (i >= i_lo) {
-            const double gam = fabs(dpv[u] + dmv[u] - (b.D[i] - lam));
+            const double gam = fabs(dpv[u] + dmv[u] - (__ldg(b.D + i) - lam));
             if (gam < best) { best = gam; r = i; }
           }
         }
@@ -1078,11 +1530,14 @@ __global__ void __launch_bounds__(64) eigvec_kernel(TriBufs b, int d, int k) {
         double dpv[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) dpv[u] = (i0 - u >= lo) ? b.Dp[(i0 - u) * K + c] : 1.0;
+        double ev[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) ev[u] = (i0 - u >= lo) ? __ldg(b.E + i0 - u) : 0.0;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int i = i0 - u;
           if (i >= lo) {
-            zz = -(b.E[i] / guard_piv(dpv[u], pivmin)) * zz;
+            zz = -(ev[u] / guard_piv(dpv[u], pivmin)) * zz;
             b.Dp[i * K + c] = zz;
             nn += zz * zz;
           }
@@ -1093,11 +1548,14 @@ __global__ void __launch_bounds__(64) eigvec_kernel(TriBufs b, int d, int k) {
         double dmv[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) dmv[u] = (i0 + u < hi) ? b.Dm[(i0 + u + 1) * K + c] : 1.0;
+        double ev[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) ev[u] = (i0 + u < hi) ? __ldg(b.E + i0 + u) : 0.0;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int i = i0 + u;
           if (i < hi) {
-            zz = -(b.E[i] / guard_piv(dmv[u], pivmin)) * zz;
+            zz = -(ev[u] / guard_piv(dmv[u], pivmin)) * zz;
             b.Dp[(i + 1) * K + c] = zz;
             nn += zz * zz;
           }
@@ -1251,18 +1709,48 @@ struct Plan {
   __nv_bfloat16 *VW, *WV, *Zs, *Xs;
   TriBufs tb;
   int kp, npanels;
+  float* VT; long long ldvt; int res_cap;  // resident stage: reflector rows, exchange buffers, counters
+  float* xbuf; unsigned* rctr;
   size_t bytes;
 };
 
-int max_grid() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+// Where the resident kernel takes over: the first panel boundary j0 from which the trailing block
+// fits the shared memory of one cooperative grid (j0 = 0: the whole matrix).
+struct ResShape { int valid, j0, m0, L, G, nloc; size_t smem; };
+constexpr size_t RES_SMEM_LIMIT = 227 * 1024 - 512;  // opt-in maximum minus the kernel's static part
+size_t res_smem_bytes(int nloc, int L) {
+  return (static_cast<size_t>(nloc) * L + 4 * static_cast<size_t>(L) + 2 * RES_MAX_NLOC +
+          RES_WARPS * RES_MAX_NLOC) * sizeof(float);
+}
+ResShape resident_shape(int d, int sms, int rows_target) {
+  ResShape rs{};
+  for (int j0 = 0; j0 < d; j0 += NB) {
+    const int m0 = d - j0;
+    const int L = static_cast<int>(round_up(m0, 4));
+    if (L > RES_MAX_L) continue;
+    int G = std::min(sms, std::max(1, (m0 + rows_target - 1) / rows_target));
+    int nloc = (m0 + G - 1) / G;
+    if (nloc > RES_MAX_NLOC) {
+      G = (m0 + RES_MAX_NLOC - 1) / RES_MAX_NLOC;
+      if (G > sms) continue;
+      nloc = (m0 + G - 1) / G;
+    }
+    const size_t smem = res_smem_bytes(nloc, L);
+    if (smem > RES_SMEM_LIMIT) continue;
+    rs = ResShape{1, j0, m0, L, G, nloc, smem};
+    return rs;
   }
-  return n;
+  return rs;
+}
+
+int max_grid() { return device_sm_count(); }
+
+// cudaFuncSetAttribute is per device: remember which devices were configured.
+bool* attr_flag(int which) {
+  static bool done[4][64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return &done[which][dev & 63];
 }
 
 Plan make_plan(void* ws, int d, int k) {
@@ -1305,6 +1793,11 @@ Plan make_plan(void* ws, int d, int k) {
   p.tb.cbn = cv.take<double>(K);
   p.tb.clo = cv.take<int>(K);
   p.tb.chi = cv.take<int>(K);
+  p.res_cap = static_cast<int>(std::min<long long>(d, RES_MAX_L));
+  p.ldvt = round_up(p.res_cap, 4);
+  p.VT = cv.take<float>(static_cast<size_t>(p.res_cap) * p.ldvt);
+  p.xbuf = cv.take<float>(4 * static_cast<size_t>(p.ldvt));
+  p.rctr = cv.take<unsigned>(static_cast<size_t>(p.res_cap));
   p.Zs = cv.take<__nv_bfloat16>(3 * D * p.kp);
   p.X1 = cv.take<float>(static_cast<size_t>(NB) * p.kp);
   p.Xs = cv.take<__nv_bfloat16>(3 * static_cast<size_t>(NB) * p.kp);
@@ -1320,21 +1813,35 @@ Plan make_plan(void* ws, int d, int k) {
 }  // namespace
 
 static int g_panel_prof = 0;
+static int g_res_enable = 1;  // 0: blocked panel kernel all the way (round-1 path)
+static int g_res_rows = 4;    // target rows per CTA of the resident kernel (grid = m0 / rows, <= SMs)
+static int g_jacobi_max = JACOBI_DEFAULT;
+// From this d on the multisection would use 4 lanes per eigenvalue instead of 16. Measured on a
+// B200 (d = 2048 / 4096): 4 lanes are 1.5-2 ms SLOWER -- the stage is bound by the chain of d
+// dependent fp64 divisions per pass, not by the fp64 pipe, so fewer, wider passes win. Kept as a
+// knob (ptdeco_debug_set key 105).
+static int g_bisect_narrow_d = 1 << 30;
+void eigh_debug_resident(int enable, int rows_target, int jacobi_max) {
+  g_res_enable = enable;
+  if (rows_target > 0) g_res_rows = rows_target;
+  if (jacobi_max >= 0) g_jacobi_max = std::min(jacobi_max, JACOBI_MAX);
+}
+void eigh_debug_bisect_narrow(int d) { g_bisect_narrow_d = d > 0 ? d : (1 << 30); }
 static int g_sym_min_m = 5120;  // trailing size from which the symv reads only the lower triangle
 void eigh_debug_sym_min_m(int m) { g_sym_min_m = m; }
 void eigh_debug_profile(int enable) {
   g_panel_prof = enable;
-  unsigned long long z[8] = {0};
+  unsigned long long z[16] = {0};
   cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z));
 }
 long long eigh_debug_phase_cycles(int k) {
-  unsigned long long v[8];
+  unsigned long long v[16];
   cudaMemcpyFromSymbol(v, g_phase_cycles, sizeof(v));
-  return (k >= 0 && k < 8) ? static_cast<long long>(v[k]) : 0;
+  return (k >= 0 && k < 16) ? static_cast<long long>(v[k]) : 0;
 }
 
 size_t eigh_workspace_bytes(int d, int k) {
-  if (d <= JACOBI_MAX) return 256;
+  if (d <= g_jacobi_max) return 256;
   return make_plan(nullptr, d, k).bytes;
 }
 
@@ -1348,16 +1855,16 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
     PTD_CHECK_LAUNCH();
     return 0;
   }
-  if (d <= JACOBI_MAX) {
+  if (d <= g_jacobi_max) {
     const int n = d + (d & 1);
     const size_t smem = (2 * static_cast<size_t>(d) * (d + 1) + n) * sizeof(double) +
                         (static_cast<size_t>(n) + d) * sizeof(int) + 64;
-    static bool attr = false;
-    if (!attr) {
+    bool* attr = attr_flag(0);
+    if (!*attr) {
       if (cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                200 * 1024) != cudaSuccess)
         return -12;
-      attr = true;
+      *attr = true;
     }
     jacobi_kernel<<<1, 512, smem, st>>>(A, lda, d, k, evals, U, ldu);
     PTD_CHECK_LAUNCH();
@@ -1384,16 +1891,20 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
   cudaMemsetAsync(p.pglob, 0, 2 * static_cast<size_t>(p.ldA) * sizeof(double), st);
 
   // ---- (1) tridiagonalisation
-  static bool panel_attr = false;
-  if (!panel_attr) {
+  bool* panel_attr = attr_flag(1);
+  if (!*panel_attr) {
     if (cudaFuncSetAttribute(sytrd_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              220 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(sytrd_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             200 * 1024) != cudaSuccess)  // + 24 KB of static tile accumulators
+                             200 * 1024) != cudaSuccess ||  // + 24 KB of static tile accumulators
+        cudaFuncSetAttribute(sytd2_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(RES_SMEM_LIMIT)) != cudaSuccess)
       return -12;
-    panel_attr = true;
+    *panel_attr = true;
   }
   const int sms = max_grid();
+  const ResShape rs = g_res_enable ? resident_shape(d, sms, g_res_rows) : ResShape{};
+  const int blocked_panels = rs.valid ? rs.j0 / NB : p.npanels;
   struct PanelShape { int rows_per_cta, grid, sym, sym_tile; size_t smem; };
   // Lower-triangle symv while the trailing matrix is too large for the L2 (full rows otherwise:
   // L2-resident, and the per-tile atomics would only add latency). Needs its tile accumulators
@@ -1415,7 +1926,7 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
     if (tiles_per_cta > SYM_MAX_SLOTS || ps.smem > 200 * 1024) ps.sym = 0;
     return ps;
   };
-  for (int pi = 0; pi < p.npanels; ++pi) {
+  for (int pi = 0; pi < blocked_panels; ++pi) {
     const int j0 = pi * NB;
     const int m = d - j0;
     const PanelShape ps = shape_of(pi);
@@ -1475,18 +1986,46 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
     }
   }
 
+  if (rs.valid) {
+    // The rest of the reduction in ONE launch with the trailing block resident in shared memory.
+    cudaMemsetAsync(p.VT, 0, static_cast<size_t>(rs.m0) * p.ldvt * sizeof(float), st);
+    cudaMemsetAsync(p.rctr, 0, static_cast<size_t>(rs.m0) * sizeof(unsigned), st);
+    ResArgs g;
+    g.A = p.Aw; g.ldA = p.ldA; g.j0 = rs.j0; g.m0 = rs.m0; g.L = rs.L; g.nloc = rs.nloc;
+    g.VT = p.VT; g.ldvt = p.ldvt;
+    g.dvec = p.dvec; g.evec = p.evec; g.taus = p.taus;
+    g.xP = p.xbuf; g.xR = p.xbuf + 2 * static_cast<size_t>(rs.L); g.ctr = p.rctr;
+    g.prof = g_panel_prof;
+    void* args[] = {&g};
+    if (cudaLaunchCooperativeKernel(reinterpret_cast<void*>(sytd2_resident_kernel), dim3(rs.G),
+                                    dim3(RES_THREADS), args, rs.smem, st) != cudaSuccess)
+      return -5;
+    const int rpanels = (rs.m0 + NB - 1) / NB;
+    larft_rows_kernel<<<rpanels, 256, 0, st>>>(p.VT, p.ldvt, rs.m0, rs.L, p.taus + rs.j0,
+                                               p.Tmats + static_cast<size_t>(rs.j0 / NB) * NB * NB);
+    PTD_CHECK_LAUNCH();
+    dim3 sgrid(static_cast<unsigned>((rs.m0 + 31) / 32), static_cast<unsigned>((rs.m0 + 31) / 32));
+    vt_split_kernel<<<sgrid, dim3(32, 8), 0, st>>>(p.VT, p.ldvt, rs.m0, rs.j0, p.Vs, p.ldv,
+                                                   static_cast<long long>(d) * p.ldv);
+    PTD_CHECK_LAUNCH();
+  }
+
   // ---- (2) tridiagonal eigenproblem in fp64
   tri_prep_kernel<<<1, 1024, 0, st>>>(p.dvec, p.evec, d, p.tb);
   PTD_CHECK_LAUNCH();
   {
-    const int tpb = 128, per_block = tpb / LPE;
-    // all eigenvalues to ~2^-31 of the block norm (enough for ordering and the fp32 output) ...
-    bisect_kernel<<<(d + per_block - 1) / per_block, tpb, 0, st>>>(p.tb, d, d, nullptr, 1, LPE == 16 ? 8 : 10);
+    // all eigenvalues to ~2^-31 of the block norm (enough for ordering and the fp32 output), then
+    // the k wanted ones to full fp64 precision (the pass loop stops at convergence)
+    const int tpb = 128;
+    const bool wide = d < g_bisect_narrow_d;
+    const int pb = tpb / (wide ? 16 : 4);
+    if (wide) bisect_kernel<16><<<(d + pb - 1) / pb, tpb, 0, st>>>(p.tb, d, d, nullptr, 1, 8);
+    else bisect_kernel<4><<<(d + pb - 1) / pb, tpb, 0, st>>>(p.tb, d, d, nullptr, 1, 14);
     PTD_CHECK_LAUNCH();
     rank_kernel<<<(d + 255) / 256, 256, 0, st>>>(p.tb, d, k, evals);
     PTD_CHECK_LAUNCH();
-    // ... then the k wanted ones to full fp64 precision
-    bisect_kernel<<<(k + per_block - 1) / per_block, tpb, 0, st>>>(p.tb, d, k, p.tb.sel, 0, LPE == 16 ? 7 : 9);
+    if (wide) bisect_kernel<16><<<(k + pb - 1) / pb, tpb, 0, st>>>(p.tb, d, k, p.tb.sel, 0, 7);
+    else bisect_kernel<4><<<(k + pb - 1) / pb, tpb, 0, st>>>(p.tb, d, k, p.tb.sel, 0, 11);
     PTD_CHECK_LAUNCH();
   }
   eigvec_kernel<<<(k + 31) / 32, 64, 0, st>>>(p.tb, d, k);

@@ -683,15 +683,23 @@ int make_map(CUtensorMap* map, const GemmOperand& op, long long inner, long long
 long long g_dbg[16] = {0};
 long long g_info[16] = {0};
 
+// Per-device caches: the SM count and "cudaFuncSetAttribute done" flags (a function attribute
+// belongs to the device that was current when it was set).
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& slot = n[dev & 63];
+  if (slot == 0) {
+    cudaDeviceGetAttribute(&slot, cudaDevAttrMultiProcessorCount, dev);
+    if (slot <= 0) slot = 148;
   }
-  return n;
+  return slot;
+}
+bool& attr_flag(bool (&flags)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return flags[dev & 63];
 }
 
 template <bool A_MN, bool B_MN, int TILE_N>
@@ -699,7 +707,8 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const KArgs& g, int gri
            cudaStream_t stream) {
   using C_ = Cfg<TILE_N>;
   auto kern = gemm_tc_kernel<A_MN, B_MN, TILE_N>;
-  static bool attr_done = false;
+  static bool attr_flags[64] = {};
+  bool& attr_done = attr_flag(attr_flags);
   if (!attr_done) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES) !=
         cudaSuccess)
@@ -714,7 +723,8 @@ template <bool A_MN, bool B_MN>
 int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const KArgs& g, int npairs_grid,
             cudaStream_t stream) {
   auto kern = gemm_tc2_kernel<A_MN, B_MN>;
-  static bool attr_done = false;
+  static bool attr_flags[64] = {};
+  bool& attr_done = attr_flag(attr_flags);
   if (!attr_done) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES) !=
         cudaSuccess)

@@ -27,6 +27,20 @@
 namespace ptd {
 
 namespace {
+
+// Runtime knobs (set through ptdeco_debug_set keys 200..206; the Python loader maps the
+// PTDECO_B200_* environment variables onto them ONCE at load time -- nothing on the forward path
+// reads the environment): 0 force the decode kernel, 1 no decode kernel, 2 no fused kernel,
+// 3 no persistent kernel, 4 no TMA store, 5 tile rotation (-1 = default), 6 pipeline stages.
+long long g_knob[8] = {0, 0, 0, 0, 0, -1, 0, 0};
+
+// cudaFuncSetAttribute is per device: remember which devices were configured.
+bool* lr_attr_flag(int which) {
+  static bool done[3][64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return &done[which][dev & 63];
+}
 inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -944,7 +958,7 @@ size_t decode_workspace_bytes(long long n, int k) {
 bool decode_eligible(const void* X, long long ldx, const void* W1, long long ldw1, const void* W2,
                      long long ldw2, int is_bf16, long long n, int in_f, int k, int out_f) {
   const bool big = static_cast<long long>(k) * (in_f + out_f) >= (1ll << 20) ||
-                   std::getenv("PTDECO_B200_FORCE_DECODE") != nullptr;
+                   g_knob[0] != 0;
   return is_bf16 && big && n <= 128 && k >= 16 && aligned16(X) && aligned16(W1) && aligned16(W2) &&
          (ldx % 8) == 0 && (ldw1 % 8) == 0 && (ldw2 % 8) == 0 &&
          (round_up(k, 128) / 128) <= (D_CTRL_BYTES / 4 - 16);
@@ -987,7 +1001,7 @@ int launch_decode(const void* X, long long ldx, const void* W1, long long ldw1, 
   if ((rc = make_tma_2d_bf16(&tw2, W2, k, out_f, ldw2, D_TILE))) return rc;
   if ((rc = make_tma_2d_bf16(&th, g.Hb, g.ldh, g.npad, g.ldh, g.npad))) return rc;
   constexpr int D_SMEM = D_STAGES * 32768 + 1024 + 256;
-  static bool attr = false;
+  bool& attr = *lr_attr_flag(0);
   if (!attr) {
     if (cudaFuncSetAttribute(lowrank_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              D_SMEM) != cudaSuccess)
@@ -1045,8 +1059,8 @@ int launch_fused(const void* X, long long ldx, const void* W1, long long ldw1, c
   CUtensorMap tx, tw1, tw2, ty;
   int rc;
   const bool persistent = g.kp <= 128 && row_tiles >= sms && aligned16(Y) && (ldy % 8) == 0 &&
-                          std::getenv("PTDECO_B200_NO_PERSISTENT") == nullptr;
-  g.tma_store = (aligned16(Y) && (ldy % 8) == 0 && std::getenv("PTDECO_B200_NO_TMA_STORE") == nullptr) ? 1 : 0;
+                          g_knob[3] == 0;
+  g.tma_store = (aligned16(Y) && (ldy % 8) == 0 && g_knob[4] == 0) ? 1 : 0;
   if (g.tma_store) {
     if ((rc = make_tma_2d_bf16(&ty, Y, out_f, n, ldy, 32))) return rc;
   } else {
@@ -1061,14 +1075,11 @@ int launch_fused(const void* X, long long ldx, const void* W1, long long ldw1, c
     g.stages = 3; g.slot_bytes = 49152; g.w2_off = F_XBYTES; g.stg_separate = 0;
   }
   g.rotate = 1;
-  if (const char* e = std::getenv("PTDECO_B200_FUSED_ROT")) g.rotate = atoi(e);
-  if (const char* e = std::getenv("PTDECO_B200_FUSED_STAGES")) {  // experiment knob
-    const int v = atoi(e);
-    if (v >= 2 && v <= g.stages) g.stages = v;
-  }
+  if (g_knob[5] >= 0) g.rotate = static_cast<int>(g_knob[5]);
+  if (g_knob[6] >= 2 && g_knob[6] <= g.stages) g.stages = static_cast<int>(g_knob[6]);  // experiment knob
   const int F_SMEM = g.stages * g.slot_bytes + (g.kp / F_BK) * F_HBLOCK +
                      (g.stg_separate ? F_STG_BYTES : 4 * 4096) + 1024 + 256;
-  static bool attr = false;
+  bool& attr = *lr_attr_flag(1);
   if (!attr) {
     if (cudaFuncSetAttribute(lowrank_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              227 * 1024) != cudaSuccess)
@@ -1076,7 +1087,7 @@ int launch_fused(const void* X, long long ldx, const void* W1, long long ldw1, c
     attr = true;
   }
   if (persistent) {
-    static bool pattr = false;
+    bool& pattr = *lr_attr_flag(2);
     if (!pattr) {
       if (cudaFuncSetAttribute(lowrank_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                227 * 1024) != cudaSuccess)
@@ -1095,6 +1106,10 @@ int launch_fused(const void* X, long long ldx, const void* W1, long long ldw1, c
 }
 
 }  // namespace
+
+void lowrank_debug_set(int key, long long value) {
+  if (key >= 0 && key < 8) g_knob[key] = value;
+}
 
 size_t lowrank_workspace_bytes(int is_bf16, long long n, int in_f, int k, int out_f) {
   Carve cv{nullptr};
@@ -1118,9 +1133,9 @@ int lowrank_forward(const void* X, long long ldx, const void* W1, long long ldw1
   if (ldx < in_f || ldw1 < in_f || ldw2 < k || ldy < out_f) return -22;
   if (decode_eligible(X, ldx, W1, ldw1, W2, ldw2, is_bf16, n, in_f, k, out_f) && ws != nullptr &&
       ws_bytes >= decode_workspace_bytes(n, k) + 256 && (reinterpret_cast<uintptr_t>(Y) & 1) == 0 &&
-      std::getenv("PTDECO_B200_NO_DECODE") == nullptr)
+      g_knob[1] == 0)
     return launch_decode(X, ldx, W1, ldw1, W2, ldw2, bias, Y, ldy, n, in_f, k, out_f, ws, st);
-  if (fused_eligible(X, ldx, W1, ldw1, W2, ldw2, is_bf16, k) && std::getenv("PTDECO_B200_NO_FUSED") == nullptr)
+  if (fused_eligible(X, ldx, W1, ldw1, W2, ldw2, is_bf16, k) && g_knob[2] == 0)
     return launch_fused(X, ldx, W1, ldw1, W2, ldw2, bias, Y, ldy, n, in_f, k, out_f, st);
   if (ws == nullptr || ws_bytes < lowrank_workspace_bytes(is_bf16, n, in_f, k, out_f)) return -12;
   uint8_t* base = static_cast<uint8_t*>(ws);

@@ -13,4 +13,7 @@ int lowrank_forward(const void* X, long long ldx, const void* W1, long long ldw1
                     long long n, int in_f, int k, int out_f, void* ws, size_t ws_bytes,
                     cudaStream_t st);
 
+// Runtime knobs 0..6 (see lowrank.cu); reached through ptdeco_debug_set keys 200..206.
+void lowrank_debug_set(int key, long long value);
+
 }  // namespace ptd

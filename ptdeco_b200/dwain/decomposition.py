@@ -106,7 +106,7 @@ def decompose_in_place(
         logger.info("Skipping precomputing convariance matrices")
         u_dict = {}
     utils.relieve_gpu_memory_pressure()
-    pair_state = _wrap.PairState()
+    pair_state = _wrap.PairState(module)
 
     for i, name in enumerate(reversed(names), start=1):
         logger.info(f"PROCESSING {name} MODULE {i} OUT OF {n}")
@@ -199,6 +199,9 @@ def _process_module(
             num_vectors=_max_rank_consumed(dim_in, dim_out, reduction_factor))
         logger.info(f"Computed u_matrix, {u_matrix.dtype=}")
 
+    if pair_state is not None:
+        pair_state.begin_layer()
+
     def factors(rank: int) -> tuple[torch.Tensor, torch.Tensor]:
         """uk [out, k] and W1 = uk^T W [k, in], both in the weight dtype like D:423-428."""
         uk = u_matrix[:, u_matrix.shape[1] - rank:].to(orig_dtype).to(device)
@@ -232,15 +235,14 @@ def _process_module(
         batches = [next(metric_iterator) for _ in range(num_metric_steps)]
         if t % world != my_rank:
             continue
+        # no K5 GEMM (D:429) and no weight copy: the wrapper runs the two-factor op for the trial
         uk, w1 = factors(rank_t)
-        deco_weight = linalg.deco_weight(uk, w1).to(orig_dtype)
         acc = torch.zeros(3, dtype=torch.float64, device=orig_device)
         for batch in batches:
             input_dict = utils.to_device(batch, device)
             nsr_sample, ppl_deco_sample, ppl_orig_sample = _compute_metrics(
                 input_dict=input_dict, root_module=root_module, decomposed_submodule=wrapper,
-                orig_weight=orig_weight, deco_weight=deco_weight, loss_fn=loss_fn,
-                pair_state=pair_state)
+                factors=(w1, uk), loss_fn=loss_fn, pair_state=pair_state)
             ppl_diff_sample = (ppl_deco_sample - ppl_orig_sample) / ppl_orig_sample
             acc += torch.stack([ppl_diff_sample.double(), nsr_sample.double(),
                                 ppl_deco_sample.double()])
@@ -277,7 +279,6 @@ def _process_module(
                     f"{rank_best=} {nsr_best=:.6f} {ppl_deco_best=:.6f}")
         logger.info(f"{indent}---")
 
-    wrapper.set_weight(orig_weight)
     decompose_decision = False
     proportion = 1.0
     if tried:
@@ -309,23 +310,25 @@ def _compute_metrics(
     input_dict: dict[str, torch.Tensor],
     root_module: torch.nn.Module,
     decomposed_submodule: torch.nn.Module,
-    orig_weight: torch.Tensor,
-    deco_weight: torch.Tensor,
+    factors: tuple[torch.Tensor, torch.Tensor],
     loss_fn: collections.abc.Callable[[dict[str, torch.Tensor], torch.Tensor], torch.Tensor],
     pair_state: Optional[_wrap.PairState] = None,
 ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """D:247-278. With a verified `pair_state` the two forwards share one pass over the doubled
-    batch (see _wrap.PairState); the losses are still taken per variant on the original batch."""
+    """D:247-278 with the layer evaluated through the trial factors (W1 [k, in], uk [out, k])
+    instead of a copied-in effective weight. With a `pair_state` that verified this layer the two
+    forwards share one pass over the doubled batch (see _wrap.PairState); the losses are still
+    taken per variant on the original batch."""
     assert isinstance(input_dict, dict)
     assert isinstance(decomposed_submodule, WrappedDWAINModule)
     root_module.eval()
     if pair_state is not None:
-        y_deco, y_orig = pair_state.forward_pair(root_module, decomposed_submodule, input_dict,
-                                                 orig_weight, deco_weight)
+        y_deco, y_orig = pair_state.forward_pair(root_module, decomposed_submodule, input_dict, factors)
     else:
-        decomposed_submodule.set_weight(deco_weight)
-        y_deco = root_module(input_dict)
-        decomposed_submodule.set_weight(orig_weight)
+        decomposed_submodule.set_trial(*factors)
+        try:
+            y_deco = root_module(input_dict)
+        finally:
+            decomposed_submodule.clear_trial()
         y_orig = root_module(input_dict)
     loss_deco = loss_fn(input_dict, y_deco)
     loss_orig = loss_fn(input_dict, y_orig)
@@ -503,15 +506,20 @@ def _compute_covariance_matrix_decomposition(
     d = weight.shape[1] if input_side else weight.shape[0]
     acc = linalg.CovarianceAccumulator(
         d, device, defer_rows=linalg.default_defer_rows(d, weight.element_size()))
-    wrapper.capture_output = not input_side
+    # the hooked layer output stands in for y = x W^T only when it has one row per input position
+    from_output = not input_side and wrapper.output_covers_input_positions()
+    wrapper.capture_output = from_output
     try:
         for _ in range(num_data_steps):
             inputs = utils.to_device(next(data_iterator), device)
-            _ = root_module(inputs)
+            # D:237 discards the model output: the forward stops right after the target layer
+            _wrap.calibration_forward(root_module, inputs, wrapper)
             if input_side:
                 _update_Eyyt_in_place(acc, wrapper.get_last_input())
-            else:
+            elif from_output:
                 _update_Eyyt_in_place(acc, wrapper.get_last_output_rows(), sub=wrapper.get_bias())
+            else:  # strided / padded 1x1 conv: the reference's y = x W^T over ALL input positions (D:239)
+                _update_Eyyt_in_place(acc, linalg.linear_nt(wrapper.get_last_input(), weight))
     finally:
         wrapper.capture_output = False
         wrapper.output = None

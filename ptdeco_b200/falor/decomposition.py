@@ -26,7 +26,7 @@ from typing import Any, Optional
 import torch
 
 from .. import _native as nat
-from .. import _graphs, _wrap, linalg, utils
+from .. import _wrap, linalg, utils
 
 EIGEN_DAMPEN_FACTOR = 0.01  # F:22
 
@@ -81,15 +81,8 @@ def decompose_in_place(
 
     names = _get_decomposeable_submodule_names(module)
     n = len(names)
-    # One CUDA graph of the model forward serves every layer: hooks on the targets remember where
-    # the graph keeps each layer's input / output (see _graphs.py). Eager until the third call.
     module.eval()
-    recorder = _graphs.ActivationRecorder(module, [nm for nm in names if nm not in blacklisted_module_names])
-    forward_fn = _graphs.GraphedForward(module, recorder=recorder)
-    if not forward_fn.enabled:
-        recorder.close()
-        forward_fn.recorder = None
-    pair_state = _wrap.PairState()
+    pair_state = _wrap.PairState(module)
     for i, name in enumerate(names, start=1):
         msg_prefix = f"Processing {name}: module {i} of {n}"
         if name in blacklisted_module_names:
@@ -102,9 +95,7 @@ def decompose_in_place(
                 nsr_final_threshold=nsr_final_threshold, kl_final_threshold=kl_final_threshold,
                 num_data_steps=num_data_steps, num_metric_steps=num_metric_steps, device=device,
                 use_float64=use_float64, use_mean=use_mean, use_damping=use_damping, trace=trace,
-                forward_fn=forward_fn, pair_state=pair_state)
-    recorder.close()
-    del forward_fn
+                pair_state=pair_state)
 
     counter: collections.Counter[str] = collections.Counter()
     for name in names:
@@ -150,11 +141,14 @@ def _process_module(
     use_mean: bool,
     use_damping: bool,
     trace: Optional[list] = None,
-    forward_fn=None,
     pair_state: Optional[_wrap.PairState] = None,
 ) -> dict[str, Any]:
     """F:284-399: covariance -> eigenvectors -> bisection on the rank. `trace` (not in the
-    reference) collects one record per trial for the parity harness."""
+    reference) collects one record per trial for the parity harness.
+
+    A trial does not materialise the effective weight uk uk^T W (K5, F:348) nor copy it into the
+    layer (F:222,226): the wrapper evaluates the layer as the two-factor op uk (W1 x) + b on the
+    fused low-rank kernel (ptdeco_lowrank_forward), which is the same linear map."""
     decomposed_type = utils.get_type_name(root_module.get_submodule(decomposed_submodule_name))
     _wrap_in_place(root_module, decomposed_submodule_name)
     wrapper = root_module.get_submodule(decomposed_submodule_name)
@@ -178,12 +172,13 @@ def _process_module(
     # full_rank and the width halves, so any rank up to full_rank - 1 can be requested (F:340-375).
     k_max = max(1, full_rank - 1)
     root_module.eval()
-    forward_fn = forward_fn or root_module
+    if pair_state is not None:
+        pair_state.begin_layer()
     u = _compute_decompositon_of_covariance_matrix(
         root_module=root_module, decomposed_submodule_name=decomposed_submodule_name,
         data_iterator=data_iterator, weight=orig_weight, num_data_steps=num_data_steps,
         device=device, use_float64=use_float64, use_mean=use_mean, use_damping=use_damping,
-        num_vectors=k_max, forward_fn=forward_fn)
+        num_vectors=k_max)
 
     w32 = orig_weight if orig_weight.dtype == torch.float32 else orig_weight.float()
     w1 = uk = None
@@ -196,7 +191,6 @@ def _process_module(
         rank_new = rank_best - rank_width
         uk = u[:, u.shape[1] - rank_new:]  # [out, k], fp32 (F:346)
         w1 = linalg.factor_w1(w32, uk)  # = U^T, [k, in] (F:347)
-        deco_weight = linalg.deco_weight(uk, w1).to(orig_weight.dtype)  # (U V)^T (F:348)
 
         nsr_acc = torch.zeros((), dtype=torch.float64, device=orig_device)
         kl_acc = torch.zeros((), dtype=torch.float64, device=orig_device)
@@ -204,8 +198,7 @@ def _process_module(
             x = next(data_iterator).to(device)
             nsr_sample, kl_sample = _compute_metrics(
                 x=x, root_module=root_module, decomposed_submodule=wrapper,
-                orig_weight=orig_weight, deco_weight=deco_weight, forward_fn=forward_fn,
-                pair_state=pair_state)
+                factors=(w1, uk), pair_state=pair_state)
             nsr_acc += nsr_sample.double()
             kl_acc += kl_sample.double()
         nsr_new, kl_new = (torch.stack([nsr_acc, kl_acc]) / num_metric_steps).tolist()  # one sync
@@ -222,7 +215,6 @@ def _process_module(
         rank_width //= 2
         i += 1
     assert w1 is not None and uk is not None
-    wrapper.set_weight(orig_weight)
 
     proportion = rank_best / full_rank
     logger.info(f"{msg_prefix} iter=FINAL rank={rank_best} {proportion=:.4f} nsr={nsr_best:.6f} "
@@ -233,7 +225,9 @@ def _process_module(
         # rank (F:346-348 run inside the loop, F:383-386 after it), while `proportion` reports
         # rank_best (F:379).
         new_module = wrapper.get_decomposed_module(u=w1, v=uk)
-        new_module.to(orig_device)
+        # F:387 leaves the fp32 factors as they are; in a non-fp32 model that module would raise a
+        # dtype mismatch at its first forward, so the factors follow the layer's dtype here
+        new_module.to(device=orig_device, dtype=orig_weight.dtype)
     else:
         logger.info(f"{msg_prefix} {proportion=:.4f} leads to num param increase, not decomposing")
         new_module = None
@@ -248,26 +242,24 @@ def _compute_metrics(
     x: torch.Tensor,
     root_module: torch.nn.Module,
     decomposed_submodule: torch.nn.Module,
-    orig_weight: torch.Tensor,
-    deco_weight: torch.Tensor,
-    forward_fn=None,
+    factors: tuple[torch.Tensor, torch.Tensor],
     pair_state: Optional[_wrap.PairState] = None,
 ) -> tuple[torch.Tensor, torch.Tensor]:
-    """F:211-233: two full forwards (decomposed weight, original weight) -- or, once `pair_state`
-    has verified it on this model, one forward of the doubled batch (see _wrap.PairState) -- then
-    NSR over the batch dim and symmetric-max KL of the logits; both returned as 0-dim device
-    tensors (no host sync)."""
+    """F:211-233: two full forwards (layer evaluated through the trial factors W1 [k, in],
+    W2 = uk [out, k], then the original layer) -- or, once `pair_state` has verified it on this
+    layer, one forward of the doubled batch (see _wrap.PairState) -- then NSR over the batch dim and
+    symmetric-max KL of the logits; both returned as 0-dim device tensors (no host sync)."""
     assert isinstance(decomposed_submodule, WrappedFALORModule)
     root_module.eval()
-    forward_fn = forward_fn or root_module
-    if pair_state is not None and getattr(forward_fn, "recorder", None) is None:
-        y_deco, y_orig = pair_state.forward_pair(forward_fn, decomposed_submodule, x, orig_weight,
-                                                 deco_weight)
+    if pair_state is not None:
+        y_deco, y_orig = pair_state.forward_pair(root_module, decomposed_submodule, x, factors)
     else:
-        decomposed_submodule.set_weight(deco_weight)
-        y_deco = forward_fn(x)
-        decomposed_submodule.set_weight(orig_weight)
-        y_orig = forward_fn(x)
+        decomposed_submodule.set_trial(*factors)
+        try:
+            y_deco = root_module(x)
+        finally:
+            decomposed_submodule.clear_trial()
+        y_orig = root_module(x)
     nsr_final = utils.calc_per_channel_noise_to_signal_ratio(y=y_orig, x=y_deco, non_channel_dim=(0,))
     kl_final = utils.calc_kl_loss(y_deco, y_orig)
     return nsr_final, kl_final
@@ -285,7 +277,6 @@ def _compute_decompositon_of_covariance_matrix(
     use_mean: bool,
     use_damping: bool,
     num_vectors: Optional[int] = None,
-    forward_fn=None,
 ) -> torch.Tensor:
     """F:165-208. Returns eigenvectors in columns, ascending by eigenvalue: all `d` of them like
     torch.linalg.eigh, or only the last `num_vectors` (what the rank search consumes; slicing
@@ -298,7 +289,6 @@ def _compute_decompositon_of_covariance_matrix(
     further effect. The falor damping quirk is kept: damping reaches `cov` only when
     use_mean=False (F:196-205)."""
     root_module.eval()
-    forward_fn = forward_fn or root_module
     wrapper = root_module.get_submodule(decomposed_submodule_name)
     assert isinstance(wrapper, WrappedFALORModule)
     n_out, n_in = weight.shape
@@ -306,16 +296,20 @@ def _compute_decompositon_of_covariance_matrix(
     d = n_in if input_side else n_out
     acc = linalg.CovarianceAccumulator(d, device, with_mean=use_mean,
                                        defer_rows=linalg.default_defer_rows(d, weight.element_size()))
-    wrapper.capture_output = not input_side
+    # the hooked layer output stands in for y = x W^T only when it has one row per input position
+    from_output = not input_side and wrapper.output_covers_input_positions()
+    wrapper.capture_output = from_output
     try:
         for _ in range(num_data_steps):
             inputs = next(data_iterator).to(device)
-            _ = forward_fn(inputs)
-            _sync_wrapper_with_recorder(wrapper, forward_fn)
+            # F:189 discards the model output: the forward stops right after the target layer
+            _wrap.calibration_forward(root_module, inputs, wrapper)
             if input_side:  # C = W S W^T: accumulate S = E[x x^T] (and E[x]) instead of C
                 acc.update(wrapper.get_last_input())
-            else:
+            elif from_output:
                 _accumulate_Ey_and_Eyyt(acc, wrapper)
+            else:  # strided / padded 1x1 conv: the reference's y = x W^T over ALL input positions (F:159)
+                acc.update(linalg.linear_nt(wrapper.get_last_input(), weight))
     finally:
         wrapper.capture_output = False
         wrapper.output = None
@@ -338,16 +332,6 @@ def _accumulate_Ey_and_Eyyt(acc: linalg.CovarianceAccumulator, wrapper: WrappedF
     y + bias; the kernel subtracts the bias while staging, so what is accumulated is exactly the
     reference's y = x W^T: Eyyt += y^T y / N and (when tracked) Ey += mean(y)."""
     acc.update(wrapper.get_last_output_rows(), sub=wrapper.get_bias())
-
-
-def _sync_wrapper_with_recorder(wrapper: WrappedFALORModule, forward_fn) -> None:
-    """When the forward ran as a CUDA-graph replay the wrapper's Python forward did not execute;
-    its last input / output are the static tensors the recorder saw at capture time."""
-    rec = getattr(forward_fn, "recorder", None)
-    name = getattr(wrapper, "name", None)
-    if rec is not None and name in rec.inputs:
-        wrapper.input = rec.inputs[name]
-        wrapper.output = rec.outputs[name]
 
 
 def _get_decomposeable_submodule_names(module: torch.nn.Module) -> list[str]:

@@ -58,19 +58,59 @@ def allreduce_accumulator(acc, group) -> None:
     acc.steps = int(steps.item())
 
 
-def reduce_accumulator_to(acc, owner: int, group) -> None:
-    """Sum the partial covariance onto `owner` only (half the traffic of an all-reduce); the step
-    count is summed everywhere so every rank agrees on it."""
+TRIANGLE_BANDS = 8  # row bands of the packed lower-triangle exchange: 1/2 + 1/(2*8) = 56 % of d^2
+
+
+def _bands(d: int) -> list[tuple[int, int]]:
+    step = max(1, -(-d // TRIANGLE_BANDS))
+    return [(r0, min(d, r0 + step)) for r0 in range(0, d, step)]
+
+
+def start_reduce_lower(acc, owner: int, group, total_steps: Optional[int] = None) -> list:
+    """Asynchronously sum the LOWER TRIANGLE of the partial covariance onto `owner` (the SYRK kernel
+    leaves the strict upper triangle unspecified until finalize, include/ptdeco_b200.h, so sending
+    it would move garbage): the triangle goes in row bands C[r0:r1, :r1] staged contiguously.
+    Returns the handles `finish_reduce_lower` consumes. Nothing blocks the host: the caller can
+    keep enqueueing eigensolves of earlier layers while NCCL moves this one. `total_steps` (the
+    calibration's step count, known to every rank) avoids a host-synchronising count exchange."""
+    if group is None:
+        return []
+    _flush(acc)
+    dst = dist.get_global_rank(group, owner)
+    me = dist.get_rank(group)
+    handles = []
+    d = acc.C.shape[0]
+    for r0, r1 in _bands(d):
+        buf = acc.C[r0:r1, :r1].contiguous()
+        work = dist.reduce(buf, dst=dst, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        handles.append((work, buf, r0, r1))
+    if getattr(acc, "colsum", None) is not None:
+        handles.append((dist.reduce(acc.colsum, dst=dst, op=dist.ReduceOp.SUM, group=group,
+                                    async_op=True), None, 0, 0))
+    if total_steps is not None:
+        acc.steps = int(total_steps)
+    else:
+        steps = torch.tensor([acc.steps], dtype=torch.int64, device=acc.C.device)
+        dist.all_reduce(steps, op=dist.ReduceOp.SUM, group=group)
+        acc.steps = int(steps.item())
+    acc._reduce_owner = (me == owner)
+    return handles
+
+
+def finish_reduce_lower(acc, handles: list) -> None:
+    """Wait (stream-side) for `start_reduce_lower` and, on the owner, put the summed bands back."""
+    for work, buf, r0, r1 in handles:
+        work.wait()
+        if buf is not None and getattr(acc, "_reduce_owner", False):
+            acc.C[r0:r1, :r1].copy_(buf)
+
+
+def reduce_accumulator_to(acc, owner: int, group, total_steps: Optional[int] = None) -> None:
+    """Sum the partial covariance onto `owner` only: lower triangle, half the bytes of a full
+    d x d reduce and a quarter of an all-reduce."""
     if group is None:
         return
-    _flush(acc)
-    steps = torch.tensor([acc.steps], dtype=torch.int64, device=acc.C.device)
-    dst = dist.get_global_rank(group, owner)
-    dist.reduce(acc.C, dst=dst, op=dist.ReduceOp.SUM, group=group)
-    if getattr(acc, "colsum", None) is not None:
-        dist.reduce(acc.colsum, dst=dst, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(steps, op=dist.ReduceOp.SUM, group=group)
-    acc.steps = int(steps.item())
+    finish_reduce_lower(acc, start_reduce_lower(acc, owner, group, total_steps))
 
 
 def owner_computes(layer_index: int, group, compute: Callable[[], torch.Tensor], acc,
@@ -89,6 +129,65 @@ def owner_computes(layer_index: int, group, compute: Callable[[], torch.Tensor],
         out = torch.empty(shape, dtype=dtype, device=acc.C.device)
     dist.broadcast(out, src=dist.get_global_rank(group, owner), group=group)
     return out
+
+
+def owners_compute_pipelined(jobs: list, group, total_steps: Optional[int] = None,
+                             dtype: torch.dtype = torch.float32) -> list[torch.Tensor]:
+    """All layers of a calibration split at once: jobs[i] = (acc, compute, shape). Every reduction
+    is enqueued up front (NCCL runs them back to back on its own stream), then each rank walks the
+    layers in order: the owner waits for ITS layer's reduction only, runs the eigensolve on the
+    compute stream and hands the result to an asynchronous broadcast, so layer i's reduction and
+    the other ranks' eigensolves overlap with this rank's. Returns the [d, k] results in job order
+    on every rank; the caller must not read them before `torch.cuda.current_stream()` reaches the
+    point where this function returned (all broadcasts are waited stream-side at the end)."""
+    if group is None:
+        return [compute() for _, compute, _ in jobs]
+    rank, world = rank_and_world(group)
+    pending = [start_reduce_lower(acc, owner_of(i, world), group, total_steps)
+               for i, (acc, _, _) in enumerate(jobs)]
+    outs, works = [], []
+    for i, (acc, compute, shape) in enumerate(jobs):
+        owner = owner_of(i, world)
+        if rank == owner:
+            finish_reduce_lower(acc, pending[i])
+            out = compute().contiguous()
+            assert tuple(out.shape) == tuple(shape), (out.shape, shape)
+        else:
+            out = torch.empty(shape, dtype=dtype, device=acc.C.device)
+        works.append(dist.broadcast(out, src=dist.get_global_rank(group, owner), group=group,
+                                    async_op=True))
+        outs.append(out)
+    for i, (acc, _, _) in enumerate(jobs):  # non-owners: their share of the reductions
+        if rank != owner_of(i, world):
+            finish_reduce_lower(acc, pending[i])
+    for w in works:
+        w.wait()
+    return outs
+
+
+def check_identical_batches(batch, group) -> None:
+    """The sharded paths assume every rank draws the SAME batches from its iterators (each rank
+    skips the ones that are not its share). A cheap guard: compare a checksum of one batch across
+    ranks and fail loudly on rank-sharded loaders instead of silently calibrating on 1/world of
+    the data with diverging replicas."""
+    if group is None:
+        return
+    tensors = [batch] if isinstance(batch, torch.Tensor) else [
+        v for _, v in sorted(batch.items()) if isinstance(v, torch.Tensor)] if isinstance(batch, dict) else []
+    if not tensors:
+        return
+    dev = tensors[0].device
+    sig = torch.stack([t.double().sum().to(dev) + t.numel() for t in tensors]).sum().reshape(1)
+    world = dist.get_world_size(group)
+    if sig.device.type == "cpu" and dist.get_backend(group) == "nccl":
+        sig = sig.cuda()
+    gathered = [torch.empty_like(sig) for _ in range(world)]
+    dist.all_gather(gathered, sig, group=group)
+    vals = [float(g.item()) for g in gathered]
+    if any(v != vals[0] for v in vals):
+        raise RuntimeError(
+            "ptdeco_b200 multi-GPU decomposition needs identical data / metric iterators on every "
+            f"rank (batch checksums differ across ranks: {vals}); do not shard the loaders by rank")
 
 
 def mean_over_ranks(t: torch.Tensor, group) -> torch.Tensor:

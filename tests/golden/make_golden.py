@@ -11,6 +11,8 @@ The reference cannot travel to the GPU box, so its outputs are committed here as
   metrics.npz                            NSR / KL values on seeded logits (U/l:10-63)
   cov_eig_d192.npz                       _update_Eyyt_in_place + _get_eigenvectors on step-spectrum
                                          activations (D:147-163)
+  eig_ref_d768.npz, eig_ref_d2048.npz    the same at d = 768 / 2048: eigenvalues + top-k eigenvector
+                                         blocks (fp16) of the reference's torch.linalg.eigh
   falor_*.json / dwain_*.json            decompose_config + per-trial trace of decompose_in_place
 Everything is seeded; re-running reproduces the files bit for bit on the same torch build
 (torch 2.11.0+cu128, CPU/MKL).
@@ -128,6 +130,25 @@ def make_cov() -> None:
     print("cov_eig_d192: lambda max/min", evals.max().item(), evals.min().item())
 
 
+def make_eig_ref() -> None:
+    """Reference-held K3 fixtures at the sizes of VERDICT r1 weak #3: covariance through the
+    reference's _update_Eyyt_in_place, eigenvectors through its _get_eigenvectors (D:147-163).
+    Only the eigenvalues and the top-k blocks at the designed spectral steps are kept (fp16)."""
+    for d, n, steps, kmax in ((768, 1024, 4, 384), (2048, 2048, 4, 512)):
+        Eyyt = torch.zeros((d, d), dtype=torch.float32)
+        for i in range(steps):
+            RD._update_Eyyt_in_place(Eyyt, cases.step_spectrum_batch(n, d, i))
+        cov = Eyyt / steps
+        with EighTap() as tap:
+            u = RD._get_eigenvectors(cov.clone())
+        evals = torch.linalg.eigvalsh(tap.inputs[0].double())
+        ks = [k for k in (d // 8, d // 4, d // 2) if k <= kmax]
+        np.savez_compressed(os.path.join(HERE, f"eig_ref_d{d}.npz"), evals=evals.numpy(),
+                            u_top=u[:, d - kmax:].numpy().astype(np.float16), ks=np.array(ks),
+                            n=np.int64(n), steps=np.int64(steps))
+        print(f"eig_ref_d{d}: lambda max/min {evals.max().item():.4g} {evals.min().item():.4g}, ks {ks}")
+
+
 class _Trace(logging.Handler):
     """Collects the per-trial log lines of the reference (F:371-373, D:470-486)."""
 
@@ -237,14 +258,16 @@ def make_dwain(which=None) -> None:
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["prim", "metrics", "cov", "falor", "dwain"]
-    sel = [w for w in what if w not in ("prim", "metrics", "cov", "falor", "dwain")]
+    what = sys.argv[1:] or ["prim", "metrics", "cov", "eig", "falor", "dwain"]
+    sel = [w for w in what if w not in ("prim", "metrics", "cov", "eig", "falor", "dwain")]
     if "prim" in what:
         make_prim()
     if "metrics" in what:
         make_metrics()
     if "cov" in what:
         make_cov()
+    if "eig" in what:
+        make_eig_ref()
     if "falor" in what:
         make_falor(sel or None)
     if "dwain" in what:

@@ -148,6 +148,32 @@ def test_eigh_golden_d192(dev, golden_dir):
     _check_eigh(g["damped"].astype(np.float64), ev, u, 192)
 
 
+@pytest.mark.parametrize("d", [768, 2048])
+def test_eigh_matches_reference_fixture(dev, golden_dir, d):
+    """K3 against the REFERENCE's output at d = 768 / 2048: tests/golden/make_golden.py ran
+    _update_Eyyt_in_place + _get_eigenvectors (D:147-163, torch.linalg.eigh on CPU) on seeded
+    step-spectrum activations and committed the eigenvalues and the top-k eigenvector blocks
+    (fp16 to keep the fixture small). The covariance is regenerated here from the same seeds."""
+    from ptdeco_b200 import linalg
+    g = np.load(os.path.join(golden_dir, f"eig_ref_d{d}.npz"))
+    steps, n = int(g["steps"]), int(g["n"])
+    acc = linalg.CovarianceAccumulator(d, dev)
+    for i in range(steps):
+        acc.update(cases.step_spectrum_batch(n, d, i).to(dev))
+    cov = acc.finalize(use_mean=False, damp_factor=P.EIGEN_DAMPEN_FACTOR)
+    kmax = int(g["u_top"].shape[1])
+    ev, u = linalg.eigh(cov, k=kmax)
+    ev = ev.double().cpu().numpy()
+    assert np.abs(ev - g["evals"]).max() / g["evals"].max() < EVAL_TOL
+    u = u.double().cpu().numpy()
+    u_ref = g["u_top"].astype(np.float64)
+    for k in [int(x) for x in g["ks"]]:
+        # the fp16 block is re-orthonormalised: its rounding (5e-4 per entry) tilts the SPAN by
+        # ~1e-7 only, but would enter the cosines at first order through the lost orthonormality
+        q, _ = np.linalg.qr(u_ref[:, kmax - k:])
+        assert P.min_principal_cosine(q, u[:, kmax - k:]) >= COS_TOL, k
+
+
 @pytest.mark.parametrize("d,k", [(1, 1), (2, 2), (3, 2), (10, 10), (32, 32), (33, 7), (96, 96), (97, 97),
                                  (128, 128), (130, 65), (200, 50), (576, 288), (768, 384), (1000, 125)])
 def test_eigh_step_spectrum(dev, d, k):
@@ -176,16 +202,47 @@ def test_eigh_lower_triangle_symv_path(dev, d, k):
     c32 = cov.float()
     L = nat.lib()
     try:
+        L.ptdeco_debug_set(102, 0)  # blocked panel kernel all the way (these sizes are otherwise resident)
         L.ptdeco_debug_set(101, 128)
         ev, u = linalg.eigh(c32.to(dev), k=k)
         L.ptdeco_debug_set(101, 0)
         ev_full, _ = linalg.eigh(c32.to(dev), k=k)
     finally:
         L.ptdeco_debug_set(101, 5120)
+        L.ptdeco_debug_set(102, 1)
     cos_ks = [kk for kk in (d // 8, d // 4) if kk <= k]
     _check_eigh(c32.double().numpy(), ev.cpu().numpy().astype(np.float64),
                 u.cpu().numpy().astype(np.float64), k, cos_ks)
     assert float((ev - ev_full).abs().max() / ev_full.abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("d,k,rows", [(64, 64, 4), (130, 130, 2), (500, 125, 4), (1000, 1000, 8),
+                                      (2050, 300, 4), (2700, 340, 4)])
+def test_eigh_resident_matches_blocked(dev, d, k, rows):
+    """The shared-memory-resident tridiagonalisation (one packet exchange per Householder column;
+    whole matrix for d <= ~2560, the tail of the reduction beyond) against the blocked panel
+    kernel: same bars, eigenvalues of the two paths equal to fp32 rounding. d = 2700 runs blocked
+    panels first and hands the trailing block over at a panel boundary."""
+    from ptdeco_b200 import _native as nat
+    from ptdeco_b200 import linalg
+    y = cases.step_spectrum_batch(4 * d + 8, d, 7).double()
+    cov = (y.T @ y / y.shape[0])
+    cov = cov + 0.01 * cov.diagonal().mean() * torch.eye(d, dtype=torch.float64)
+    c32 = cov.float()
+    L = nat.lib()
+    try:
+        L.ptdeco_debug_set(104, 0)     # no Jacobi: the general path also at d <= 96
+        L.ptdeco_debug_set(103, rows)  # resident on, rows-per-CTA target
+        ev, u = linalg.eigh(c32.to(dev), k=k)
+        L.ptdeco_debug_set(102, 0)
+        ev_blocked, _ = linalg.eigh(c32.to(dev), k=k)
+    finally:
+        L.ptdeco_debug_set(103, 4)
+        L.ptdeco_debug_set(104, 32)
+    cos_ks = [kk for kk in (d // 8, d // 4) if 1 <= kk <= k]
+    _check_eigh(c32.double().numpy(), ev.cpu().numpy().astype(np.float64),
+                u.cpu().numpy().astype(np.float64), k, cos_ks)
+    assert float((ev - ev_blocked).abs().max() / ev_blocked.abs().max()) < 2e-6
 
 
 def test_eigh_rank_deficient_with_damping(dev):
@@ -305,7 +362,7 @@ def test_lowrank_forward(dev, dtype, tol, n, in_f, k, out_f):
     (1, 256, 32, 256, False), (5, 320, 96, 1000, True), (16, 4096, 512, 4096, True),
     (33, 768, 200, 3072, True), (128, 2048, 1024, 2048, False), (100, 1024, 1000, 520, True),
     (7, 4096, 40, 14336, True)])
-def test_lowrank_forward_decode_kernel(dev, monkeypatch, n, in_f, k, out_f, bias):
+def test_lowrank_forward_decode_kernel(dev, n, in_f, k, out_f, bias):
     """N <= 128: the single-launch weight-streaming kernel (swap-AB, split-`in` phase 1 with fp32
     red.add + ticketed bf16 rounding, grid barrier, phase 2). Forced on for every shape here (small
     factors are normally routed to the fused kernel), compared with the two-launch path and with an
@@ -317,12 +374,18 @@ def test_lowrank_forward_decode_kernel(dev, monkeypatch, n, in_f, k, out_f, bias
     w2 = (torch.randn(out_f, k, generator=g) / k ** 0.5).to(torch.bfloat16)
     b = torch.randn(out_f, generator=g) if bias else None
     args = (x.to(dev), w1.to(dev), w2.to(dev), None if b is None else b.to(dev))
-    monkeypatch.setenv("PTDECO_B200_FORCE_DECODE", "1")
-    y = linalg.lowrank_forward(*args)
-    y_again = linalg.lowrank_forward(*args)  # the workspace is reused: tickets / H must be reset
-    monkeypatch.delenv("PTDECO_B200_FORCE_DECODE")
-    monkeypatch.setenv("PTDECO_B200_NO_DECODE", "1")
-    y_two_launch = linalg.lowrank_forward(*args)
+    from ptdeco_b200 import _native as nat
+    L = nat.lib()
+    try:
+        L.ptdeco_debug_set(200, 1)  # force the decode kernel
+        y = linalg.lowrank_forward(*args)
+        y_again = linalg.lowrank_forward(*args)  # the workspace is reused: tickets / H must be reset
+        L.ptdeco_debug_set(200, 0)
+        L.ptdeco_debug_set(201, 1)  # no decode kernel
+        y_two_launch = linalg.lowrank_forward(*args)
+    finally:
+        L.ptdeco_debug_set(200, 0)
+        L.ptdeco_debug_set(201, 0)
     h = (x.double() @ w1.double().T).to(torch.bfloat16).double()
     ref = h @ w2.double().T + (0.0 if b is None else b.double())
     scale = ref.abs().max()
@@ -374,50 +437,143 @@ def test_lowrank_sequential_matches_torch_sequential(dev, dtype, tol):
     assert (out_c.float() - ref_c).abs().max() <= tol * ref_c.abs().max()
 
 
-def test_paired_trials_verify_before_pairing(dev):
-    """_wrap.PairState: one forward of the doubled batch replaces the trial's two forwards only
-    after the first batch was evaluated both ways and agreed; a model whose forward mixes batch
-    elements keeps the reference's two-forward path."""
+def test_paired_trials_verify_every_layer(dev):
+    """_wrap.PairState: one forward of the doubled batch replaces a trial's two forwards only after
+    the first batch OF THAT LAYER was evaluated both ways and agreed; a model whose forward mixes
+    batch elements, or one that folds the batch into another dimension before the layer (the
+    wrapper then sees a leading dim that is not 2b), keeps the reference's two-forward path. The
+    trial runs the two-factor op: the layer's weight is never written."""
     import ptdeco_b200.falor.decomposition as F
-    from ptdeco_b200 import _wrap
+    from ptdeco_b200 import _wrap, linalg
 
     class Net(torch.nn.Module):
-        def __init__(self, mix):
+        def __init__(self, mode):
             super().__init__()
-            self.fc1, self.fc2, self.mix = torch.nn.Linear(24, 40), torch.nn.Linear(40, 7), mix
+            self.fc1, self.fc2, self.mode = torch.nn.Linear(24, 40), torch.nn.Linear(40, 7), mode
 
         def forward(self, x):
-            h = torch.relu(self.fc1(x))
-            if self.mix:
+            if self.mode == "fold":  # [B, 24] -> [B/2, 48] -> fc1 on [.., 24] rows in another order
+                h = torch.relu(self.fc1(x.reshape(-1, 2, 24).transpose(0, 1))).transpose(0, 1).reshape(x.shape[0], 40)
+            else:
+                h = torch.relu(self.fc1(x))
+            if self.mode == "mix":
                 h = h - h.mean(0, keepdim=True)
             return self.fc2(h)
 
     g = torch.Generator().manual_seed(5)
     x = torch.randn(6, 24, generator=g).to(dev)
-    for mix, want in ((False, "on"), (True, "off")):
+    for mode, want in (("plain", "on"), ("mix", "off"), ("fold", "off")):
         torch.manual_seed(3)
-        net = Net(mix).to(dev).eval()
+        net = Net(mode).to(dev).eval()
         F._wrap_in_place(net, "fc1")
         wrapper = net.get_submodule("fc1")
         w = wrapper.get_weight_copy()
-        deco = w * 0.5
-        st = _wrap.PairState()
+        q, _ = torch.linalg.qr(torch.randn(40, 40, generator=g))
+        uk = q[:, :10].contiguous().to(dev)
+        w1 = linalg.factor_w1(w, uk)
+        deco = uk @ w1
+        st = _wrap.PairState(net)
+        st.begin_layer()
         with torch.no_grad():
-            y_deco, y_orig = st.forward_pair(net, wrapper, x, w, deco)
-            assert st.probe is not None and (st.probe["rel_err"] <= 1e-4) == (not mix)
-            if not mix and st.mode == "off":  # agreed but not measurably faster on this box: allowed
-                assert st.probe["paired_ms"] >= 0.9 * st.probe["two_forwards_ms"]
-                st.mode = "on"
-            assert st.mode == want
+            y_deco, y_orig = st.forward_pair(net, wrapper, x, (w1, uk))
+            assert st.mode == want, (mode, st.mode, st.probe)
+            ref_orig = net(x)
             wrapper.set_weight(deco)
             ref_deco = net(x)
             wrapper.set_weight(w)
-            ref_orig = net(x)
-            assert torch.allclose(y_deco, ref_deco, atol=1e-5) and torch.allclose(y_orig, ref_orig, atol=1e-5)
-            y_deco2, y_orig2 = st.forward_pair(net, wrapper, x, w, deco)  # second batch: paired iff verified
+            assert torch.allclose(y_deco, ref_deco, atol=2e-5) and torch.allclose(y_orig, ref_orig, atol=1e-6)
+            y_deco2, y_orig2 = st.forward_pair(net, wrapper, x, (w1, uk))  # second batch: paired iff verified
             assert (st.paired_forwards == 1) == (want == "on")
-            assert torch.allclose(y_deco2, ref_deco, atol=1e-5) and torch.allclose(y_orig2, ref_orig, atol=1e-5)
-            assert torch.equal(wrapper.get_weight_copy(), w) and wrapper.pair_weight is None
+            assert torch.allclose(y_deco2, ref_deco, atol=2e-5) and torch.allclose(y_orig2, ref_orig, atol=1e-5)
+            assert torch.equal(wrapper.get_weight_copy(), w) and wrapper.trial_factors is None
+            st.begin_layer()
+            assert st.mode == "unverified"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_trial_factors_match_materialised_weight(dev, dtype):
+    """f2: a rank trial through the wrapper's two-factor op (ptdeco_lowrank_forward) gives the
+    layer output of the reference's route, deco_weight = uk uk^T W copied into the layer
+    (F:347-348,222 / D:427-429,262), for Linear and 1x1 conv targets."""
+    import ptdeco_b200.falor.decomposition as F
+    from ptdeco_b200 import linalg
+    g = torch.Generator().manual_seed(17)
+    lin = torch.nn.Sequential(torch.nn.Linear(96, 160)).to(dev).to(dtype).eval()
+    conv = torch.nn.Sequential(torch.nn.Conv2d(32, 48, 1)).to(dev).to(dtype).eval()
+    for net, x in ((lin, torch.randn(3, 7, 96, generator=g)), (conv, torch.randn(2, 32, 5, 6, generator=g))):
+        x = x.to(dev).to(dtype)
+        F._wrap_in_place(net, "0")
+        wr = net.get_submodule("0")
+        w = wr.get_weight_copy()
+        q, _ = torch.linalg.qr(torch.randn(w.shape[0], w.shape[0], generator=g))
+        uk = q[:, :24].contiguous().to(dev)
+        w1 = linalg.factor_w1(w.float(), uk)
+        with torch.no_grad():
+            wr.set_trial(w1, uk)
+            y = net(x).float()
+            wr.clear_trial()
+            wr.set_weight((uk @ w1).to(dtype))
+            ref = net(x).float()
+            wr.set_weight(w)
+        tol = 1e-5 if dtype == torch.float32 else 3e-2
+        assert y.shape == ref.shape and (y - ref).abs().max() <= tol * ref.abs().max()
+
+
+def test_strided_conv_covariance_matches_reference_formulation(dev):
+    """Strided / padded 1x1 conv targets: the covariance is the reference's, formed from ALL input
+    positions (F:125-126,159), not from the (subsampled / bordered) layer output."""
+    import ptdeco_b200.falor.decomposition as F
+    from oracle import drivers as OD
+    for kw in (dict(stride=2), dict(padding=1)):
+        torch.manual_seed(7)
+        net = torch.nn.Sequential(torch.nn.Conv2d(3, 16, 3, padding=1), torch.nn.GELU(),
+                                  torch.nn.Conv2d(16, 24, 1, **kw), torch.nn.Flatten(), torch.nn.LazyLinear(5)).eval()
+        stream_a = cases.IndexedStream(lambda i: cases.streams.lowrank_image_batch(9, i, 6, 3, 8, 12))
+        stream_b = cases.IndexedStream(lambda i: cases.streams.lowrank_image_batch(9, i, 6, 3, 8, 12))
+        with torch.no_grad():
+            net(next(cases.IndexedStream(lambda i: cases.streams.lowrank_image_batch(9, i, 6, 3, 8, 12))))  # lazy init
+        w = net[2].weight.detach()[..., 0, 0].clone()
+        tap = OD._Tap(net[2])
+        net[2] = tap
+        with torch.no_grad():
+            u_ref = OD.falor_eigenvectors(net, "2", stream_a, w.numpy(), 3, True, False, True)
+        net[2] = tap.inner
+        net.to(dev)
+        F._wrap_in_place(net, "2")
+        with torch.no_grad():
+            u = F._compute_decompositon_of_covariance_matrix(
+                root_module=net, decomposed_submodule_name="2", data_iterator=stream_b, weight=w.to(dev),
+                num_data_steps=3, device=dev, use_float64=True, use_mean=False, use_damping=True)
+        assert stream_a.position == stream_b.position == 3
+        for k in (2, 4, 8):
+            assert P.min_principal_cosine(P.top_k(u_ref, k), P.top_k(u.double().cpu().numpy(), k)) >= COS_TOL
+
+
+@pytest.mark.parametrize("input_side", [False, True])
+def test_bf16_covariance_module_matches_fp32_einsum_of_same_activations(dev, input_side):
+    """dwain's CovarianceComputingLinearModule on a bf16 layer against einsum(y.float(), y.float())
+    of the SAME bf16 activations (the reference's own bf16 einsum rounds every
+    per-step product to bf16 and is ~1e-3 noisy, so it is not the yardstick for a 1e-5 bar)."""
+    import ptdeco_b200.dwain.decomposition as D
+    g = torch.Generator().manual_seed(23)
+    in_f, out_f = (64, 192) if input_side else (192, 96)
+    lin = torch.nn.Linear(in_f, out_f, bias=False).to(dev).to(torch.bfloat16)
+    mod = D.CovarianceComputingLinearModule(lin.weight, None, True, 16 if input_side else None)
+    assert mod.input_side == input_side
+    ref = torch.zeros(mod.acc.d, mod.acc.d, dtype=torch.float64, device=dev)
+    steps = 3
+    with torch.no_grad():
+        for _ in range(steps):
+            x = (torch.randn(2, 50, in_f, generator=g) * torch.logspace(0, -1, in_f)).to(torch.bfloat16).to(dev)
+            y = mod(x)  # no bias: the module's output IS the bf16 y = x W^T it folded in
+            assert y.dtype == torch.bfloat16 and tuple(y.shape) == (2, 50, out_f)
+            rows = (x if input_side else y).reshape(-1, mod.acc.d).double()
+            ref += rows.T @ rows / rows.shape[0]
+            y_ref = torch.nn.functional.linear(x.float(), lin.weight.float())
+            assert (y.float() - y_ref).abs().max() <= 1e-2 * y_ref.abs().max()
+    assert mod.num_data_steps == steps
+    cov = mod.acc.finalize(False, 0.0)
+    assert _rel(cov.double().cpu().numpy(), (ref / steps).cpu().numpy()) < COV_TOL
 
 
 # ------------------------------------------------------------------------------------ K6
@@ -572,19 +728,46 @@ def test_dwain_edge_cases_match_oracle(dev):
         assert c1[n]["__meta__"]["drop_in_params"] == c0[n]["__meta__"]["drop_in_params"]
 
 
+# Trials of the golden runs whose accept / reject decision sits within 0.5 % of a threshold (a
+# bisection ends next to the threshold by construction): (layer, tested rank) -> relative margin
+# |metric - threshold| / threshold of the reference's own run. Only after one of THESE trials may a
+# layer's trial sequence leave the golden one; everything else must be identical. The list is
+# re-derived from the committed golden traces below, so it cannot drift.
+FRAGILE_TRIALS = {
+    "deit_tiny": {("blocks.0.mlp.fc1", 114): 0.0007, ("blocks.6.mlp.fc1", 24): 0.0028},
+    "convnext_tiny": {("features.5.5.block.5", 17): 0.0004, ("features.5.6.block.3", 96): 0.0016,
+                      ("features.7.1.block.5", 216): 0.0019, ("features.7.1.block.3", 417): 0.0021,
+                      ("features.7.2.block.5", 183): 0.0028, ("features.5.4.block.3", 81): 0.0029,
+                      ("features.5.3.block.5", 30): 0.0034, ("features.7.1.block.3", 414): 0.0034,
+                      ("features.7.0.block.5", 240): 0.0038, ("features.5.1.block.5", 44): 0.0049},
+}
+FRAGILE_MARGIN = 0.005
+
+
+def _golden_margin(t, nsr_thr, kl_thr):
+    """Relative distance of a golden trial from flipping its decision (accept iff both below)."""
+    mn, mk = abs(t["nsr"] - nsr_thr) / nsr_thr, abs(t["kl"] - kl_thr) / kl_thr
+    if t["nsr"] < nsr_thr and t["kl"] < kl_thr:
+        return min(mn, mk)
+    return max(m for m, bad in ((mn, t["nsr"] >= nsr_thr), (mk, t["kl"] >= kl_thr)) if bad)
+
+
 @pytest.mark.parametrize("name", ["deit_tiny", "convnext_tiny"])
 def test_falor_baseline_configs_match_reference(dev, golden_dir, name):
     """BASELINE.json configs[0] (DeiT-tiny layout, (5,3,224,224) inputs) and configs[1]
     (torchvision convnext_tiny): the whole trial sequence (339 / 285 rank trials) and the chosen
-    ranks must be the unmodified reference's."""
+    ranks must be the unmodified reference's. No blanket tolerance on ranks: a layer may differ
+    only downstream of a trial listed by name in FRAGILE_TRIALS (golden margin < 0.5 %)."""
     import ptdeco_b200.falor as falor
     gold = json.load(open(os.path.join(golden_dir, f"falor_{name}.json")))
     model, stream, kw = cases.falor_case(name)
+    nsr_thr, kl_thr = kw["nsr_final_threshold"], kw["kl_final_threshold"]
+    derived = {(g["name"], g["rank"]) for g in gold["trace"] if _golden_margin(g, nsr_thr, kl_thr) < FRAGILE_MARGIN}
+    assert derived == set(FRAGILE_TRIALS[name]), sorted(derived ^ set(FRAGILE_TRIALS[name]))
     model.to(dev)
     trace = []
     cfg = falor.decompose_in_place(module=model, device=dev, data_iterator=stream, trace=trace, **kw)
     assert stream.position == gold["stream_position"]  # trial COUNTS are data independent
-    thr = kw["nsr_final_threshold"]
     by_layer_gold: dict = {}
     for g in gold["trace"]:
         by_layer_gold.setdefault(g["name"], []).append(g)
@@ -592,25 +775,32 @@ def test_falor_baseline_configs_match_reference(dev, golden_dir, name):
     for t in trace:
         by_layer_mine.setdefault(t["name"], []).append(t)
     assert list(by_layer_mine) == list(by_layer_gold)
-    identical, fragile = 0, []
+    diverged = []
     for name_, gl in by_layer_gold.items():
         ml = by_layer_mine[name_]
+        assert len(ml) == len(gl)
         if [t["rank"] for t in ml] == [g["rank"] for g in gl]:
-            identical += 1
             continue
-        # A layer may only diverge at a trial whose golden decision margin is inside the noise of
-        # an ill-conditioned (flat-spectrum) subspace: |nsr - thr| / thr < 10 % (parity).
         first = next(i for i, (t, g) in enumerate(zip(ml, gl)) if t["rank"] != g["rank"])
-        margin = abs(gl[first - 1]["nsr"] - thr) / thr
-        assert margin < 0.10, (name_, first, gl[first - 1], ml[first - 1])
-        fragile.append(name_)
-    assert identical >= 0.9 * len(by_layer_gold), (identical, fragile)
+        assert first > 0, name_  # the first tested rank is data independent
+        flipped = gl[first - 1]  # the decision that went the other way
+        assert (name_, flipped["rank"]) in FRAGILE_TRIALS[name], (name_, flipped, ml[first - 1])
+        diverged.append(name_)
     ranks, granks = _ranks(cfg), _ranks(gold["decompose_config"])
-    assert all(ranks.get(n) == granks.get(n) for n in set(ranks) | set(granks) if n not in fragile)
-    # metrics: tight wherever the tested rank lies inside the well-determined part of the spectrum
+    assert all(ranks.get(n) == granks.get(n) for n in set(ranks) | set(granks) if n not in diverged)
+    # metrics of the trials both runs evaluated at the same rank. Decision-relevant ones (golden NSR
+    # within 20 % of the threshold) must agree tightly; the rest of the distribution is bounded by
+    # its 90th percentile (ranks cutting through a flat, ill-conditioned part of a random-init
+    # spectrum have subspace-dependent NSR: the reference's own fp32 / fp64 runs differ there too).
     pairs = [(t, g) for t, g in zip(trace, gold["trace"]) if (t["name"], t["rank"]) == (g["name"], g["rank"])]
+    assert len(pairs) >= 0.95 * len(gold["trace"])
     rel = sorted(abs(t["nsr"] - g["nsr"]) / max(g["nsr"], 1e-9) for t, g in pairs)
-    assert rel[len(rel) // 2] < 1e-3
+    near = [abs(t["nsr"] - g["nsr"]) / g["nsr"] for t, g in pairs if abs(g["nsr"] - nsr_thr) < 0.2 * nsr_thr]
+    assert rel[len(rel) // 2] < 1e-3, rel[len(rel) // 2]
+    assert rel[int(0.9 * len(rel))] < 5e-2, rel[int(0.9 * len(rel))]
+    assert near and max(near) < 5e-2, max(near)
+    print(f"falor {name}: {len(diverged)} diverged layers {diverged}; rel NSR diff median {rel[len(rel) // 2]:.2e} "
+          f"p90 {rel[int(0.9 * len(rel))]:.2e} max {rel[-1]:.2e}; near-threshold max {max(near):.2e} over {len(near)}")
 
 
 @pytest.mark.parametrize("name", list(cases.DWAIN_CASES))
@@ -626,8 +816,13 @@ def test_dwain_decompose_in_place_matches_reference(dev, golden_dir, name):
     assert stream.position == gold["stream_position"]
     assert mstream.position == gold["metric_stream_position"]
     assert [(t["name"], t["rank"]) for t in trace] == [(t["name"], t["rank"]) for t in gold["trace"]]
+    # bf16 cases: the golden run is the reference's bf16 arithmetic on CPU (every per-step y^T y
+    # rounded to bf16, D:152; bf16 factor GEMMs, D:423-429); the product forms exact bf16 products
+    # with fp32 accumulation and the user model runs on cuBLAS instead of oneDNN. The reference's
+    # own fp32 and bf16 runs of this model differ by up to 7 % in NSR; decisions have >= 1.9x margin.
+    rel = 0.15 if "bf16" in name else 1e-2
     for t, g in zip(trace, gold["trace"]):
-        assert t["nsr"] == pytest.approx(g["nsr"], rel=1e-2, abs=1e-6)
+        assert t["nsr"] == pytest.approx(g["nsr"], rel=rel, abs=1e-6)
     assert list(cfg.keys()) == list(gold["decompose_config"].keys())  # reversed module order
     assert _ranks(cfg) == _ranks(gold["decompose_config"])
     for n in cfg:

@@ -309,21 +309,95 @@ def test_pair_state_host_logic():
     assert _wrap.PairState._double({"a": torch.ones(2, 3), "s": torch.tensor(1.0)}) == (None, 0)
     assert _wrap.PairState._double([x]) == (None, 0)
 
+    # policy: a fixed rule, never a timing measurement: env forces, "auto" goes by size
     net = torch.nn.Sequential(torch.nn.Linear(4, 6), torch.nn.ReLU(), torch.nn.Linear(6, 2)).eval()
+    assert _wrap.PairState(net).enabled and _wrap.PairState(net).mode == "unverified"
+    assert not _wrap.PairState(None).enabled
+    big = _wrap.PairState.AUTO_MAX_PARAMS
+    try:
+        _wrap.PairState.AUTO_MAX_PARAMS = 10
+        assert not _wrap.PairState(net).enabled and _wrap.PairState(net).mode == "off"
+    finally:
+        _wrap.PairState.AUTO_MAX_PARAMS = big
+
+    # the wrapper's paired forward on CPU with the two-factor op stubbed by torch (the kernel is
+    # CUDA only): first half through the factors, second half through the layer, and a leading
+    # dimension that is not the doubled batch is refused (seq-first layouts)
     F._wrap_in_place(net, "0")
     wrapper = net.get_submodule("0")
     w = wrapper.get_weight_copy()
-    st = _wrap.PairState()
+    w1, w2 = 0.5 * torch.eye(4), w  # W2 W1 = 0.5 W
+    wrapper._factored_forward = lambda t: torch.nn.functional.linear(
+        torch.nn.functional.linear(t, wrapper.trial_factors[0]), wrapper.trial_factors[1], wrapper.get_bias())
     with torch.no_grad():
-        y_deco, y_orig = st.forward_pair(net, wrapper, x, w, 0.5 * w)  # CPU tensors: no probing
-        assert st.mode == "off" and st.paired_forwards == 0
-        assert torch.equal(wrapper.get_weight_copy(), w) and wrapper.pair_weight is None
-        assert torch.allclose(y_orig, net(x)) and not torch.allclose(y_deco, y_orig)
-        # the wrapper's paired forward itself: first half through the pair weight
-        wrapper.pair_weight = 0.5 * w
+        y_orig = net(x)
+        wrapper.set_trial(w1, w2)
+        y_deco = net(x)
+        wrapper.clear_trial()
+        assert not torch.allclose(y_deco, y_orig)
+        wrapper.set_trial(w1, w2, pair_batch=3)
         yy = net(torch.cat([x, x], 0))
-        wrapper.pair_weight = None
         assert torch.allclose(yy[:3], y_deco, atol=1e-6) and torch.allclose(yy[3:], y_orig, atol=1e-6)
+        with pytest.raises(_wrap.PairLayoutError):
+            net(torch.cat([x, x, x], 0))
+        wrapper.clear_trial()
+        assert torch.equal(wrapper.get_weight_copy(), w) and wrapper.trial_factors is None
+        st = _wrap.PairState(net)
+        st.begin_layer()
+        a, b_ = st.forward_pair(net, wrapper, x, (w1, w2))  # first batch of the layer: verified both ways
+        assert st.mode == "on" and st.probe["rel_err"] <= 1e-4
+        assert torch.allclose(a, y_deco, atol=1e-6) and torch.allclose(b_, y_orig, atol=1e-6)
+        a, b_ = st.forward_pair(net, wrapper, x, (w1, w2))
+        assert st.paired_forwards == 1 and torch.allclose(a, y_deco, atol=1e-6)
+        st.begin_layer()
+        assert st.mode == "unverified"  # every layer re-verifies
+
+
+def test_calibration_forward_stops_after_the_target():
+    """_wrap.calibration_forward: the reference discards the model output of calibration forwards
+    (F:189, D:237), so the forward is cut right after the wrapped layer; the layers behind it do
+    not run, the captured input / output are those of a full forward."""
+    from ptdeco_b200 import _wrap
+    import ptdeco_b200.dwain.decomposition as D
+    calls = []
+
+    class Tail(torch.nn.Module):
+        def forward(self, t):
+            calls.append(1)
+            return t * 2
+
+    net = torch.nn.Sequential(torch.nn.Linear(4, 6), torch.nn.ReLU(), torch.nn.Linear(6, 5), Tail()).eval()
+    x = torch.randn(3, 4)
+    D._wrap_in_place(net, "2")
+    wrapper = net.get_submodule("2")
+    wrapper.capture_output = True
+    with torch.no_grad():
+        full = net(x)
+        assert len(calls) == 1
+        want_in, want_out = wrapper.get_last_input().clone(), wrapper.get_last_output_rows().clone()
+        _wrap.calibration_forward(net, x + 1, wrapper)
+        _wrap.calibration_forward(net, x, wrapper)
+    assert len(calls) == 1 and not wrapper.capture_only  # the tail never ran again
+    assert torch.equal(wrapper.get_last_input(), want_in) and torch.equal(wrapper.get_last_output_rows(), want_out)
+    with torch.no_grad():
+        assert torch.equal(net(x), full)  # and the model is untouched
+
+
+def test_strided_conv_wrapper_uses_input_positions():
+    """Strided / padded 1x1 convs: the reference's covariance runs over ALL input
+    positions (F:125-126,159) and the rebuilt module drops stride / padding (F:136-147). The wrapper
+    says so (the driver then forms y = x W^T from the input instead of hooking the layer output)."""
+    from ptdeco_b200 import _wrap
+    plain = _wrap.WrappedConv2d1x1(torch.nn.Conv2d(4, 8, 1), "a")
+    strided = _wrap.WrappedConv2d1x1(torch.nn.Conv2d(4, 8, 1, stride=2), "b")
+    padded = _wrap.WrappedConv2d1x1(torch.nn.Conv2d(4, 8, 1, padding=1), "c")
+    assert plain.output_covers_input_positions()
+    assert not strided.output_covers_input_positions() and not padded.output_covers_input_positions()
+    x = torch.randn(2, 4, 6, 6)
+    strided(x)
+    assert tuple(strided.get_last_input().shape) == (2 * 6 * 6, 4)  # every input position
+    new = strided.get_decomposed_module(torch.randn(3, 4), torch.randn(8, 3))
+    assert new[0].stride == (1, 1) and tuple(new(x).shape) == (2, 8, 6, 6)  # the reference's shape change
 
 
 def test_memory_pressure_gate_without_cuda_is_a_no_op():
