@@ -12,8 +12,15 @@ sharded over GPUs (weak scaling), the only exchange is the final d x d reduction
           launch whatever N is); the final flush is inside the timed region
   e2e     tokens/s through the public API path (ptdeco_b200.dwain covariance-computing modules
           installed in a random-init Llama-3-8B-shape model): pinned host token ids -> H2D ->
-          full model forward (layer forwards on the tcgen05 GEMM engine, SYRK per target) -> D2H
-          of a per-step checksum
+          full model forward (layer forwards on the tcgen05 GEMM engine, one SYRK per accumulator:
+          q/k/v and gate/up share theirs) -> D2H of a per-step checksum; the deferred SYRK staging
+          is flushed inside the timed region
+  extra   eigh at d = 768 / 2048 / 4096 next to torch.linalg.eigh on the same GPU (cuSOLVER) and
+          on the host CPU; the reference's einsum on device="cuda" (cuBLAS) for the calibration
+          step; fused low-rank forward next to nn.Sequential on cuBLAS; whole-model
+          decompose_in_place wall times (falor DeiT-tiny / ConvNeXt-tiny, dwain Llama-3-8B shape)
+  strong_scaling_e2e   (N >= 1) fixed 512 x 2048 tokens of calibration through the public API:
+          sharded forwards -> lower-triangle NCCL reduce -> round-robin eigensolves -> broadcast
   roofline    tensor-bound: algorithmic N*d*(d+1) FLOP / CUDA-event time vs MEASURED_PEAKS.json
   cpu_baseline / --impl reference   the reference's _update_Eyyt_in_place arithmetic (oracle port,
           numpy fp32 on all host cores) on a bounded sample: the 7 targets of ONE decoder layer,
@@ -193,6 +200,206 @@ def workload_config(n_gpus: int) -> dict:
             "l2": "inputs (176 MB) + accumulators (59 GB) exceed the 126 MB L2; no explicit flush"}
 
 
+# ------------------------------------------------------------------------------------ extras
+def _timed_ms(fn, reps: int = 3, warm: int = 1) -> float:
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def extra_eigh(dev, gen, world: int) -> dict:
+    """metric (iii): eigh ms per size; torch.linalg.eigh(device="cuda") is the library-GPU
+    comparator of BASELINE.md section 3, the host CPU is the reference's own path."""
+    import torch
+
+    from ptdeco_b200 import linalg
+    out = {}
+    for d in (768, 2048, 4096):
+        y = torch.randn(4 * d, d, generator=gen, device=dev) * torch.logspace(0, -2, d, device=dev)
+        acc = linalg.CovarianceAccumulator(d, dev)
+        acc.update(y)
+        cov = acc.finalize(False, 0.01).clone()
+        row = {"ms_full": _timed_ms(lambda: linalg.eigh(cov)),
+               "ms_top_half": _timed_ms(lambda: linalg.eigh(cov, k=d // 2)),
+               "torch_cuda_cusolver_ms": _timed_ms(lambda: torch.linalg.eigh(cov), reps=2)}
+        if world == 1 and d == 4096:
+            c = cov.cpu()
+            torch.set_num_threads(os.cpu_count() or 1)
+            t0 = time.perf_counter()
+            torch.linalg.eigh(c)
+            row["host_cpu_fp32_ms"] = 1e3 * (time.perf_counter() - t0)
+            row["host_cores"] = os.cpu_count()
+        out[f"d{d}"] = row
+        del cov, acc, y
+    return out
+
+
+def extra_reference_gpu_syrk(dev, acts) -> dict:
+    """The reference's _update_Eyyt_in_place (D:147-152: Eyyt += einsum(y, y) / N) with its tensors
+    on device="cuda", i.e. torch / cuBLAS: one decoder layer's 7 targets, scaled to 32 layers."""
+    import torch
+    accs = {name: torch.zeros(d, d, device=dev) for name, d in LAYER_DIMS}
+
+    def step():
+        for name, _ in LAYER_DIMS:
+            y = acts[name]
+            accs[name] += torch.einsum("bp,bq->pq", y, y) / y.shape[0]
+
+    ms = _timed_ms(step, reps=5, warm=2)
+    return {"tokens_per_s": SEQ / (N_LAYERS * ms * 1e-3), "ms_per_decoder_layer": ms,
+            "what": "reference arithmetic on device=cuda (torch einsum -> cuBLAS bf16 GEMM, full square, "
+                    "bf16-rounded per-step product), 7 targets of 1 of 32 layers, scaled by 1/32"}
+
+
+def extra_lowrank(dev, gen, peaks) -> dict:
+    import torch
+
+    from ptdeco_b200 import linalg
+    out = {}
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    tf = float(peaks.get("bf16_tflops", 1590.0))
+    for n, fin, k, fout in ((37888, 4096, 128, 4096), (32768, 4096, 128, 4096), (8192, 4096, 128, 4096),
+                            (8192, 4096, 512, 4096), (8192, 4096, 1024, 4096), (8192, 4096, 2048, 14336)):
+        x = torch.randn(n, fin, generator=gen, device=dev, dtype=torch.float32).to(torch.bfloat16)
+        w1 = (torch.randn(k, fin, generator=gen, device=dev) / fin ** 0.5).to(torch.bfloat16)
+        w2 = (torch.randn(fout, k, generator=gen, device=dev) / k ** 0.5).to(torch.bfloat16)
+        ms = _timed_ms(lambda: linalg.lowrank_forward(x, w1, w2, None), reps=10, warm=3)
+        seq = torch.nn.Sequential(torch.nn.Linear(fin, k, bias=False),
+                                  torch.nn.Linear(k, fout, bias=False)).to(dev).to(torch.bfloat16)
+        with torch.no_grad():
+            ms_t = _timed_ms(lambda: seq(x), reps=10, warm=3)
+        alg_bytes = 2.0 * n * (fin + fout) + 2.0 * k * (fin + fout)
+        flops = 2.0 * n * k * (fin + fout)
+        t_hbm, t_tc = alg_bytes / (hbm * 1e9), flops / (tf * 1e12)
+        out[f"N{n}_in{fin}_k{k}_out{fout}"] = {
+            "ms": ms, "torch_sequential_cublas_ms": ms_t, "bound": "hbm" if t_hbm >= t_tc else "tensor",
+            "frac_of_bound": max(t_hbm, t_tc) / (ms * 1e-3), "achieved_gbs": alg_bytes / ms / 1e6,
+            "achieved_tflops": flops / ms / 1e9}
+        del x, w1, w2, seq
+    return out
+
+
+class _DeviceStream:
+    """Pre-generated batches resident on the device (the synthetic CPU RNG stream costs more than
+    the decomposition itself); `position` like synth.streams.IndexedStream."""
+
+    def __init__(self, make, count: int, dev):
+        self.items = [make(i).to(dev) for i in range(count)]
+        self.position = 0
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        item = self.items[self.position]
+        self.position += 1
+        return item
+
+
+def extra_model_runs(dev, with_dwain8b: bool) -> dict:
+    """metric (i): decompose_in_place wall time per model through the public API."""
+    import torch
+
+    import ptdeco_b200.dwain as dwain
+    import ptdeco_b200.falor as falor
+    from synth import cases, models, streams
+    out = {}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    for name in ("deit_tiny", "convnext_tiny"):
+        gold = json.load(open(os.path.join(ROOT, "tests", "golden", f"falor_{name}.json")))
+        model, stream, kw = cases.falor_case(name)
+        dstream = _DeviceStream(stream.make, gold["stream_position"], dev)
+        model.to(dev)
+        trace = []
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        cfg = falor.decompose_in_place(module=model, device=dev, data_iterator=dstream, trace=trace, **kw)
+        torch.cuda.synchronize()
+        ranks = {n: c["modules"]["0"].get("out_features", c["modules"]["0"].get("out_channels")) for n, c in cfg.items()}
+        granks = {n: c["modules"]["0"].get("out_features", c["modules"]["0"].get("out_channels"))
+                  for n, c in gold["decompose_config"].items()}
+        out[f"falor_{name}"] = {"wall_s": time.perf_counter() - t0, "targets_decomposed": len(cfg),
+                                "rank_trials": len(trace), "batches": dstream.position,
+                                "ranks_equal_reference_golden": ranks == granks}
+        del model, dstream
+        torch.cuda.empty_cache()
+    if with_dwain8b:
+        with torch.device(dev):
+            model = models.LlamaLikeDecoder(init=False).to(torch.bfloat16)
+        models.fast_init_(model, 271828)
+        model.eval()
+        data = streams.IndexedStream(lambda i: streams.token_batch(2, i, 1, SEQ, 128256))
+        metric = streams.IndexedStream(lambda i: streams.token_batch(3, i, 1, SEQ, 128256))
+        trace = []
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        cfg = dwain.decompose_in_place(
+            module=model, device=dev, data_iterator=data, metric_iterator=metric,
+            loss_fn=models.llama_ce_loss, finetune_fn=lambda m, d, n: m, num_data_steps=8,
+            num_metric_steps=1, blacklisted_module_names=["lm_head"], nsr_final_threshold=0.05,
+            min_rank=32, decompose_in_float64=True, precomputing_covariance_num_splits=1, trace=trace)
+        torch.cuda.synchronize()
+        hist: dict = {}
+        for c in cfg.values():
+            r = c["modules"]["0"]["out_features"]
+            hist[r] = hist.get(r, 0) + 1
+        out["dwain_llama3_8b_shape"] = {
+            "wall_s": time.perf_counter() - t0, "targets": 224, "targets_decomposed": len(cfg),
+            "rank_trials": len(trace), "num_data_steps": 8, "num_metric_steps": 1,
+            "rank_histogram": hist, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+        del model
+        torch.cuda.empty_cache()
+    return out
+
+
+def strong_scaling_leg(dev, rank: int, world: int, n_layers: int, sequences: int) -> dict:
+    """The design's real multi-GPU path, wall-timed: a FIXED number of 2048-token sequences is
+    calibrated through ptdeco_b200.dwain's precompute (sharded forwards of a Llama-3-8B-shape
+    replica per rank, SYRK per accumulator), the partial covariances are reduced (lower triangles,
+    NCCL, asynchronously), the eigensolves run round-robin and the top-k blocks are broadcast."""
+    import torch
+
+    import ptdeco_b200.dwain.decomposition as D
+    from ptdeco_b200 import parallel
+    from synth import models, streams
+
+    group = parallel.default_group()
+    with torch.device(dev):
+        model = models.LlamaLikeDecoder(layers=n_layers, init=False).to(torch.bfloat16)
+    models.fast_init_(model, 271828)
+    model.eval()
+    names = D._get_decomposeable_submodule_names(model, ["lm_head"])
+    gen = torch.Generator().manual_seed(1314159)
+    ids = torch.randint(0, 128256, (sequences, 1, SEQ), generator=gen).to(dev)
+    data = iter({"input_ids": ids[i]} for i in range(sequences))
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    u = D._precompute_covariance_matrix_decompositions(
+        module=model, submodule_names=names, num_data_steps=sequences, data_iterator=data, device=dev,
+        decompose_in_float64=True, reduction_factor=0.5, group=group)
+    check = float(sum(float(v[0, 0]) for v in list(u.values())[:4]))  # D2H: forces completion
+    torch.cuda.synchronize()
+    wall = parallel.max_over_ranks(time.perf_counter() - t0, dev)
+    del model, u
+    torch.cuda.empty_cache()
+    return {"tokens": sequences * SEQ, "sequences": sequences, "wall_s": wall,
+            "tokens_per_s": sequences * SEQ / wall, "targets": len(names), "n_gpus": world,
+            "scaling": "strong", "check": check,
+            "path": "dwain._precompute_covariance_matrix_decompositions: sharded calibration forwards -> "
+                    "lower-triangle NCCL reduce to round-robin owners -> eigensolves -> broadcast of U[:, -k:]"}
+
+
 # ------------------------------------------------------------------------------------ GPU arm
 def main() -> None:
     ap = argparse.ArgumentParser()
@@ -203,6 +410,10 @@ def main() -> None:
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--layers", type=int, default=N_LAYERS, help="debug: fewer decoder layers")
+    ap.add_argument("--no-model-runs", action="store_true", help="skip the whole-model wall times in extra")
+    ap.add_argument("--no-dwain8b", action="store_true", help="skip the 8B-shape dwain wall time in extra")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling end-to-end leg")
+    ap.add_argument("--strong-sequences", type=int, default=512)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -284,76 +495,24 @@ def main() -> None:
         for li, layer in enumerate(accs):
             for ti, acc in enumerate(layer):
                 parallel.reduce_accumulator_to(acc, parallel.owner_of(li * len(LAYER_DIMS) + ti, world),
-                                               parallel.default_group())
+                                               parallel.default_group(), total_steps=acc.steps * world)
         e1.record()
         barrier()
         exchange_ms = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
     del accs
     torch.cuda.empty_cache()
 
-    # ---------------- extra: eigh @ d=4096 next to the host CPU ---------------------------------
+    # ---------------- extra: comparators and the other BASELINE metrics --------------------------
     extra = {}
     if not args.no_extra and rank == 0:
-        try:
-            d = 4096
-            y = torch.randn(4 * d, d, generator=g, device=dev) * torch.logspace(0, -2, d, device=dev)
-            acc = linalg.CovarianceAccumulator(d, dev)
-            acc.update(y)
-            cov = acc.finalize(False, 0.01).clone()
-            linalg.eigh(cov)
-            torch.cuda.synchronize()
-            e0.record()
-            linalg.eigh(cov)
-            e1.record()
-            torch.cuda.synchronize()
-            extra["eigh_ms_d4096_full"] = e0.elapsed_time(e1)
-            e0.record()
-            linalg.eigh(cov, k=2048)
-            e1.record()
-            torch.cuda.synchronize()
-            extra["eigh_ms_d4096_top2048"] = e0.elapsed_time(e1)
-            if world == 1:
-                c = cov.cpu()
-                torch.set_num_threads(os.cpu_count() or 1)
-                t0 = time.perf_counter()
-                torch.linalg.eigh(c)
-                extra["eigh_ms_d4096_host_cpu_fp32"] = 1e3 * (time.perf_counter() - t0)
-                extra["host_cores"] = os.cpu_count()
-            del cov, acc, y
-        except Exception as exc:  # the headline number must survive an extra failing
-            extra["eigh_error"] = repr(exc)[:200]
-        try:  # decomposed-layer forward (K7) at a prefill shape, next to torch's nn.Sequential
-            n, fin, k, fout = 37888, 4096, 128, 4096  # 2 x 148 token tiles of 128 rows
-            x = torch.randn(n, fin, generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
-            w1 = (torch.randn(k, fin, generator=g, device=dev) / fin ** 0.5).to(torch.bfloat16)
-            w2 = (torch.randn(fout, k, generator=g, device=dev) / k ** 0.5).to(torch.bfloat16)
-            for _ in range(3):
-                linalg.lowrank_forward(x, w1, w2, None)
-            e0.record()
-            for _ in range(10):
-                linalg.lowrank_forward(x, w1, w2, None)
-            e1.record()
-            torch.cuda.synchronize()
-            ms_lr = e0.elapsed_time(e1) / 10
-            alg_bytes = 2.0 * n * (fin + fout) + 2.0 * k * (fin + fout)
-            seq = torch.nn.Sequential(torch.nn.Linear(fin, k, bias=False),
-                                      torch.nn.Linear(k, fout, bias=False)).to(dev).to(torch.bfloat16)
-            with torch.no_grad():
-                for _ in range(3):
-                    seq(x)
-                e0.record()
-                for _ in range(10):
-                    seq(x)
-                e1.record()
-            torch.cuda.synchronize()
-            extra["lowrank_forward"] = {
-                "shape": f"N={n} (= 2 x 148 SMs x 128 rows) in={fin} k={k} out={fout} bf16", "ms": ms_lr,
-                "achieved_gbs": alg_bytes / ms_lr / 1e6, "peak_gbs": float(peaks.get("hbm_gbs", 6650.0)),
-                "frac_hbm": alg_bytes / ms_lr / 1e6 / float(peaks.get("hbm_gbs", 6650.0)),
-                "torch_sequential_ms": e0.elapsed_time(e1) / 10}
-            del x, w1, w2, seq
-        except Exception as exc:
-            extra["lowrank_error"] = repr(exc)[:200]
+        for key, fn in (("eigh", lambda: extra_eigh(dev, g, world)),
+                        ("reference_on_cuda_syrk", lambda: extra_reference_gpu_syrk(dev, acts)),
+                        ("lowrank_forward", lambda: extra_lowrank(dev, g, peaks))):
+            try:  # the headline number must survive an extra failing
+                extra[key] = fn()
+            except Exception as exc:
+                extra[key + "_error"] = repr(exc)[:300]
+            torch.cuda.empty_cache()
     torch.cuda.empty_cache()
 
     # ---------------- e2e: public API path with host token ids ----------------------------------
@@ -391,30 +550,56 @@ def main() -> None:
 
         originals = D._install_covariance_modules(model, names, True, reduction_factor=0.5)
         last = model.get_submodule(names[-1])
+        fwd(host_tokens[0])  # probe forward: decides which targets share an accumulator
+        last.units.finish_probe()
 
         def e2e_step(ids_host):
             fwd(ids_host)
             check.copy_(last.acc.C[0, :1], non_blocking=True)  # D2H read of the step's result
             torch.cuda.current_stream().synchronize()
 
+        cov_units = last.units.units if last.units is not None else []
+
+        def flush_units():
+            for u_ in cov_units:
+                u_.acc.flush()
+
         for i in range(args.warmup):
             e2e_step(host_tokens[i])
+        flush_units()
+        syrk0 = sum(u_.acc.launches for u_ in cov_units)
         barrier()
-        t0 = time.perf_counter()
         e0.record()
         for i in range(args.steps):
             e2e_step(host_tokens[args.warmup + i])
+        flush_units()  # staged (deferred) rows are folded in inside the timed region
         e1.record()
         barrier()
-        wall = time.perf_counter() - t0
+        e2e_syrk_launches = sum(u_.acc.launches for u_ in cov_units) - syrk0
         e2e_ms = parallel.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
         e2e = {"value": tokens_per_step / (e2e_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": SEQ * 8, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
                "model_forward_only_ms": forward_only_ms,
+               "covariance_accumulators": len(cov_units), "syrk_launches": e2e_syrk_launches,
                "path": "ptdeco_b200.dwain covariance-computing modules in a Llama-3-8B-shape model "
-                       "(input-side covariance for gate/up, output-side elsewhere)"}
+                       "(q/k/v and gate/up share one input-side accumulator each, o / down output-side)"}
         D._restore_modules(model, originals)
         del model, originals
+        torch.cuda.empty_cache()
+
+    # ---------------- whole-model wall times (metric i) and the strong-scaling leg ----------------
+    if not args.no_extra and not args.no_model_runs and rank == 0 and world == 1:
+        try:
+            extra["decompose_wall_time"] = extra_model_runs(dev, with_dwain8b=not args.no_dwain8b)
+        except Exception as exc:
+            extra["decompose_wall_time_error"] = repr(exc)[:300]
+        torch.cuda.empty_cache()
+    strong = None
+    if not args.no_strong:
+        try:
+            strong = strong_scaling_leg(dev, rank, world, n_layers, args.strong_sequences)
+        except Exception as exc:
+            strong = {"error": repr(exc)[:300]}
         torch.cuda.empty_cache()
 
     # ---------------- CPU baseline (rank 0, N = 1) ----------------------------------------------
@@ -435,13 +620,15 @@ def main() -> None:
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of ONE d=14336, N=16384 launch
-                         # (the dominant shape: 64 of 224 launches, 88 % of the step), from the ncu
-                         # capture in profiles/r01_syrk_traffic_by_tokens_and_band.txt (4.97 GB read +
+                         # (the dominant shape: 64 of 224 launches, 88 % of the step), from the
+                         # `ncu --set full` capture summarised in
+                         # profiles/r01_syrk_pair_ncu_full_summary.json (gate_proj row: 5.70 GB read +
                          # 0.41 GB written). Algorithmic bytes of that launch: 0.470 GB of tokens +
                          # 0.822 GB accumulator RMW; the excess is operand re-reads between waves (the
                          # ~145 MB working set of one wave of 74 tile pairs exceeds the L2). The kernel
-                         # is tensor / power bound: this traffic is 2.0 TB/s, 31 % of the HBM peak.
-                         "traffic": 5.38e9, "traffic_unit": "B/launch (d=14336, N=16384)",
+                         # is tensor / power bound: this traffic is ~2.5 TB/s, 38 % of the HBM peak.
+                         "traffic": 6.11e9, "traffic_unit": "B/launch (d=14336, N=16384)",
+                         "traffic_source": "profiles/r01_syrk_pair_ncu_full_summary.json",
                          "algorithmic_bytes_per_launch": 1.292e9,
                          "kernel": "gemm_tc2_kernel<MN,MN> (SYRK, lower triangle, 256x256 tiles on CTA pairs, cta_group::2)",
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src})",
@@ -451,6 +638,8 @@ def main() -> None:
         }
         if exchange_ms is not None:
             line["exchange_ms_all_covariances"] = exchange_ms
+        if strong is not None:
+            line["strong_scaling_e2e"] = strong
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

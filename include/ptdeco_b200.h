@@ -13,8 +13,13 @@
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing syncs
  *     unless stated
  *   - return 0 on success, negative errno-style code on failure (ptdeco_strerror); no exceptions
- *   - the caller owns every buffer; scratch comes from the *_workspace_bytes queries
- *   - thread-safe per stream; the only global state is a lazily resolved driver entry point
+ *   - the caller owns every buffer; scratch comes from the *_workspace_bytes queries. A workspace
+ *     (and, for ptdeco_lowrank_forward's decode path, the control words inside it) belongs to ONE
+ *     call at a time: concurrent calls on different streams need different workspaces
+ *   - entry points are re-entrant across streams under that rule; process-wide state is limited to
+ *     a lazily resolved driver entry point, per-device kernel attributes, and the debug knobs
+ *     below. Numerics-affecting options are per call (the `flags` of the *_ex variants), never
+ *     global
  */
 #ifndef PTDECO_B200_H_
 #define PTDECO_B200_H_
@@ -27,6 +32,12 @@ extern "C" {
 
 #define PTDECO_F32 0
 #define PTDECO_BF16 1
+
+/* flags of the *_ex entry points */
+#define PTDECO_FLAG_DETERMINISTIC 1u /* no split-K: every output element is accumulated by one CTA in
+                                        a fixed order (default: short-and-wide reductions are split
+                                        over CTAs and combined with fp32 red.add, whose arrival order
+                                        varies from run to run) */
 
 int ptdeco_version(void);
 const char* ptdeco_strerror(int code);
@@ -44,6 +55,10 @@ size_t ptdeco_syrk_workspace_bytes(int dtype, long long n_tokens, int d);
 int ptdeco_syrk_accumulate(const void* Y, int dtype, long long n_tokens, int d, long long ldy,
                            const float* sub, float* C, long long ldc, float* colsum, float alpha,
                            void* workspace, size_t workspace_bytes, void* stream);
+
+int ptdeco_syrk_accumulate_ex(const void* Y, int dtype, long long n_tokens, int d, long long ldy,
+                              const float* sub, float* C, long long ldc, float* colsum, float alpha,
+                              void* workspace, size_t workspace_bytes, void* stream, unsigned flags);
 
 /* ---- K2: covariance finalize -----------------------------------------------------------------
  * Replaces  F:192-205 (Ey,Eyyt /= steps; cov = Eyyt - outer(Ey,Ey); diag += 0.01*mean(diag))
@@ -65,6 +80,11 @@ int ptdeco_gemm(const void* A, int a_dtype, int a_mn_major, long long lda, const
                 const float* bias, void* C, int c_dtype, long long ldc, int accumulate,
                 void* workspace, size_t workspace_bytes, void* stream);
 
+int ptdeco_gemm_ex(const void* A, int a_dtype, int a_mn_major, long long lda, const void* B,
+                   int b_dtype, int b_mn_major, long long ldb, int M, int N, int K, float alpha,
+                   const float* bias, void* C, int c_dtype, long long ldc, int accumulate,
+                   void* workspace, size_t workspace_bytes, void* stream, unsigned flags);
+
 /* ---- K3: symmetric eigendecomposition ------------------------------------------------------------
  * Replaces  F:207 / D:162  _, u = torch.linalg.eigh(cov)   (and the uk = u[:, d-k:] slice of F:346,
  * D:425): A[d][lda] fp32 symmetric (lower triangle authoritative, torch's UPLO='L'), not modified.
@@ -78,6 +98,10 @@ int ptdeco_gemm(const void* A, int a_dtype, int a_mn_major, long long lda, const
 size_t ptdeco_eigh_workspace_bytes(int d, int k);
 int ptdeco_eigh(const float* A, int d, long long lda, int k, float* evals, float* U, long long ldu,
                 void* workspace, size_t workspace_bytes, void* stream);
+
+int ptdeco_eigh_ex(const float* A, int d, long long lda, int k, float* evals, float* U,
+                   long long ldu, void* workspace, size_t workspace_bytes, void* stream,
+                   unsigned flags);
 
 /* ---- K7: decomposed-layer forward -----------------------------------------------------------------
  * Replaces the forward of the nn.Sequential(Linear(in->k, no bias), Linear(k->out, bias)) built at

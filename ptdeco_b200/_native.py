@@ -36,6 +36,11 @@ SIGNATURES = {
         [c_void_p, c_int, c_ll, c_int, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_float, c_void_p,
          c_size_t, c_void_p],
     ),
+    "ptdeco_syrk_accumulate_ex": (
+        c_int,
+        [c_void_p, c_int, c_ll, c_int, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_float, c_void_p,
+         c_size_t, c_void_p, ctypes.c_uint],
+    ),
     "ptdeco_cov_finalize": (
         c_int, [c_void_p, c_ll, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
     "ptdeco_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
@@ -44,7 +49,15 @@ SIGNATURES = {
         [c_void_p, c_int, c_int, c_ll, c_void_p, c_int, c_int, c_ll, c_int, c_int, c_int, c_float,
          c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p, c_size_t, c_void_p],
     ),
+    "ptdeco_gemm_ex": (
+        c_int,
+        [c_void_p, c_int, c_int, c_ll, c_void_p, c_int, c_int, c_ll, c_int, c_int, c_int, c_float,
+         c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p, c_size_t, c_void_p, ctypes.c_uint],
+    ),
     "ptdeco_eigh_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "ptdeco_eigh_ex": (
+        c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_ll, c_void_p, c_size_t, c_void_p,
+                ctypes.c_uint]),
     "ptdeco_eigh": (
         c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_ll, c_void_p, c_size_t, c_void_p]),
     "ptdeco_lowrank_workspace_bytes": (c_size_t, [c_int, c_ll, c_int, c_int, c_int]),
@@ -91,11 +104,6 @@ def lib() -> ctypes.CDLL:
             if os.environ.get(name) is not None:
                 v = os.environ[name]
                 handle.ptdeco_debug_set(key, int(v) if v.lstrip("-").isdigit() else 1)
-        if os.environ.get("PTDECO_B200_DETERMINISTIC", "0") == "1":
-            # Reproducible mode: no split-K, so every output element is accumulated by exactly one
-            # CTA in a fixed order (the default splits short-and-wide reductions over CTAs and
-            # combines them with fp32 red.add, whose arrival order varies from run to run).
-            handle.ptdeco_debug_set(1, 1)
         _lib = handle
     return _lib
 
@@ -128,19 +136,71 @@ def require_cuda(t: torch.Tensor, name: str) -> None:
                           "(there is no CPU path)")
 
 
+FLAG_DETERMINISTIC = 1
+
+_deterministic = os.environ.get("PTDECO_B200_DETERMINISTIC", "0") == "1"
+
+
+def set_deterministic(on: bool) -> None:
+    """Reproducible mode: no split-K, so every output element is accumulated by exactly one CTA in a
+    fixed order (the default splits short-and-wide reductions over CTAs and combines them with fp32
+    red.add, whose arrival order varies from run to run). A per-call flag of the C-ABI (`*_ex`
+    entry points); this module only remembers what the Python layer should pass.
+    PTDECO_B200_DETERMINISTIC=1 sets the initial value."""
+    global _deterministic
+    _deterministic = bool(on)
+
+
+def call_flags() -> int:
+    return FLAG_DETERMINISTIC if _deterministic else 0
+
+
+def device_of(t: torch.Tensor):
+    """Context manager making `t`'s device current for a C-ABI call: kernel attributes, SM counts
+    and cooperative launches belong to the current device, which is not necessarily the tensor's."""
+    if t.device.index is None or t.device.index == torch.cuda.current_device():
+        return _NULL_CONTEXT
+    return torch.cuda.device(t.device)
+
+
+class _NullContext:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL_CONTEXT = _NullContext()
+
+
 class Workspace:
-    """Grow-only per-device scratch buffer handed to the C-ABI calls."""
+    """Scratch buffers handed to the C-ABI calls, ONE PER (device, stream): calls on one stream are
+    ordered, so they can share a buffer; calls on different streams (or threads using different
+    streams) must not -- the decode kernel keeps its grid-barrier / ticket words and the rank-k
+    intermediate in there. Buffers only grow; a replaced buffer goes back to torch's stream-aware
+    caching allocator, which will not hand it to another stream while this one still uses it.
+    During CUDA-graph capture every request gets its OWN buffer from the graph's pool and it is
+    kept alive for the life of the process: a captured pointer must never be freed or reused."""
 
     def __init__(self) -> None:
-        self._buf: dict[torch.device, torch.Tensor] = {}
+        self._buf: dict[tuple[int, int], torch.Tensor] = {}
+        self._captured: list[torch.Tensor] = []
 
     def get(self, device: torch.device, nbytes: int) -> torch.Tensor:
         device = torch.device(device)
-        if device.index is None:
-            device = torch.device("cuda", torch.cuda.current_device())
-        buf = self._buf.get(device)
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        device = torch.device("cuda", index)
+        if nbytes <= 0:
+            nbytes = 1
+        if torch.cuda.is_current_stream_capturing():
+            buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+            self._captured.append(buf)
+            return buf
+        key = (index, torch.cuda.current_stream(device).cuda_stream)
+        buf = self._buf.get(key)
         if buf is None or buf.numel() < nbytes:
-            self._buf[device] = buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+            self._buf[key] = buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         return buf
 
     def release(self) -> None:

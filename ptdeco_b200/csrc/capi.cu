@@ -78,6 +78,13 @@ size_t ptdeco_syrk_workspace_bytes(int dtype, long long n_tokens, int d) {
 int ptdeco_syrk_accumulate(const void* Y, int dtype, long long n_tokens, int d, long long ldy,
                            const float* sub, float* C, long long ldc, float* colsum, float alpha,
                            void* workspace, size_t workspace_bytes, void* stream) {
+  return ptdeco_syrk_accumulate_ex(Y, dtype, n_tokens, d, ldy, sub, C, ldc, colsum, alpha, workspace,
+                                   workspace_bytes, stream, 0u);
+}
+
+int ptdeco_syrk_accumulate_ex(const void* Y, int dtype, long long n_tokens, int d, long long ldy,
+                              const float* sub, float* C, long long ldc, float* colsum, float alpha,
+                              void* workspace, size_t workspace_bytes, void* stream, unsigned flags) {
   if (dtype != PTDECO_F32 && dtype != PTDECO_BF16) return -22;
   if (d <= 0 || n_tokens < 0 || Y == nullptr || C == nullptr || ldc < d || ldy < d) return -22;
   if (n_tokens == 0) return 0;
@@ -98,6 +105,7 @@ int ptdeco_syrk_accumulate(const void* Y, int dtype, long long n_tokens, int d, 
   ep.ldc = ldc;
   ep.accumulate = 1;
   ep.lower_only = 1;
+  ep.deterministic = (flags & PTDECO_FLAG_DETERMINISTIC) ? 1 : 0;
   return ptd::gemm_tc(op, op, d, d, static_cast<int>(n_tokens), -1, ep, st);
 }
 
@@ -121,6 +129,14 @@ int ptdeco_gemm(const void* A, int a_dtype, int a_mn_major, long long lda, const
                 int b_dtype, int b_mn_major, long long ldb, int M, int N, int K, float alpha,
                 const float* bias, void* C, int c_dtype, long long ldc, int accumulate,
                 void* workspace, size_t workspace_bytes, void* stream) {
+  return ptdeco_gemm_ex(A, a_dtype, a_mn_major, lda, B, b_dtype, b_mn_major, ldb, M, N, K, alpha, bias,
+                        C, c_dtype, ldc, accumulate, workspace, workspace_bytes, stream, 0u);
+}
+
+int ptdeco_gemm_ex(const void* A, int a_dtype, int a_mn_major, long long lda, const void* B,
+                   int b_dtype, int b_mn_major, long long ldb, int M, int N, int K, float alpha,
+                   const float* bias, void* C, int c_dtype, long long ldc, int accumulate,
+                   void* workspace, size_t workspace_bytes, void* stream, unsigned flags) {
   if (A == nullptr || B == nullptr || C == nullptr || M <= 0 || N <= 0 || K <= 0) return -22;
   if (c_dtype == PTDECO_BF16 && accumulate) return -22;
   cudaStream_t st = as_stream(stream);
@@ -139,6 +155,7 @@ int ptdeco_gemm(const void* A, int a_dtype, int a_mn_major, long long lda, const
   ep.alpha = alpha;
   ep.bias = bias;
   ep.accumulate = accumulate;
+  ep.deterministic = (flags & PTDECO_FLAG_DETERMINISTIC) ? 1 : 0;
   if (c_dtype == PTDECO_BF16) {
     ep.Cb = static_cast<__nv_bfloat16*>(C);
     ep.ldcb = ldc;
@@ -156,7 +173,12 @@ size_t ptdeco_eigh_workspace_bytes(int d, int k) {
 
 int ptdeco_eigh(const float* A, int d, long long lda, int k, float* evals, float* U, long long ldu,
                 void* workspace, size_t workspace_bytes, void* stream) {
-  return ptd::eigh(A, d, lda, k, evals, U, ldu, workspace, workspace_bytes, as_stream(stream));
+  return ptd::eigh(A, d, lda, k, evals, U, ldu, workspace, workspace_bytes, as_stream(stream), 0u);
+}
+
+int ptdeco_eigh_ex(const float* A, int d, long long lda, int k, float* evals, float* U, long long ldu,
+                   void* workspace, size_t workspace_bytes, void* stream, unsigned flags) {
+  return ptd::eigh(A, d, lda, k, evals, U, ldu, workspace, workspace_bytes, as_stream(stream), flags);
 }
 
 size_t ptdeco_lowrank_workspace_bytes(int dtype, long long n, int in_features, int k,

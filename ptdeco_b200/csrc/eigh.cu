@@ -811,16 +811,20 @@ struct ResArgs {
   int prof;
 };
 
-// Sum over the CTA; every thread gets the same value (identical order in every CTA): fp32 inside
-// a warp (<= 8 terms per lane, 5 shuffles), fp64 across the 16 warps.
+// Sum over the CTA; every thread gets the same value (identical order in every CTA).
 __device__ __forceinline__ double res_block_sum(float v, float* buf, int warp, int lane) {
   v = warp_sum(v);
   if (lane == 0) buf[warp] = v;
   __syncthreads();
-  double s = 0.0;
+  // fixed pairwise tree in fp32: a chain of 16 dependent fp64 adds cost ~400 cycles per call here
+  float t[RES_WARPS];
 #pragma unroll
-  for (int w = 0; w < RES_WARPS; ++w) s += static_cast<double>(buf[w]);
-  return s;
+  for (int w = 0; w < RES_WARPS; ++w) t[w] = buf[w];
+#pragma unroll
+  for (int span = RES_WARPS / 2; span > 0; span >>= 1)
+#pragma unroll
+    for (int w = 0; w < span; ++w) t[w] += t[w + span];
+  return static_cast<double>(t[0]);
 }
 
 // Sums over the 32 lanes of 8 per-lane values with 9 shuffles instead of 40 (see reduce16_packed):
@@ -1846,7 +1850,8 @@ size_t eigh_workspace_bytes(int d, int k) {
 }
 
 int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, long long ldu,
-         void* ws, size_t ws_bytes, cudaStream_t st) {
+         void* ws, size_t ws_bytes, cudaStream_t st, unsigned flags) {
+  const int deterministic = (flags & 1u) ? 1 : 0;
   if (A == nullptr || evals == nullptr || U == nullptr || d <= 0 || k < 1 || k > d || lda < d ||
       ldu < k)
     return -22;
@@ -1976,6 +1981,7 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
       // mirrored once.
       const int next_sym = (pi + 1 < p.npanels) ? shape_of(pi + 1).sym : 0;
       ep.lower_only = next_sym;
+      ep.deterministic = deterministic;
       const int rc = gemm_tc(a, b, mt, mt, 2 * NB, -1, ep, st);
       if (rc) return rc;
       if (g.sym && !next_sym) {
@@ -2061,6 +2067,7 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
       ep.C = p.X1;
       ep.ldc = p.kp;
       ep.accumulate = 1;
+      ep.deterministic = deterministic;
       const int rc = gemm_tc(a, b, nc, k, m, -1, ep, st);
       if (rc) return rc;
     }
@@ -2078,6 +2085,7 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
       ep.C = U + static_cast<long long>(j0) * ldu;
       ep.ldc = ldu;
       ep.accumulate = 1;
+      ep.deterministic = deterministic;
       const int rc = gemm_tc(a, b, m, k, nc, -1, ep, st);
       if (rc) return rc;
     }

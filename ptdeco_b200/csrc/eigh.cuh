@@ -25,8 +25,9 @@ size_t eigh_workspace_bytes(int d, int k);
 // A [d][lda] fp32 symmetric (lower triangle authoritative, like torch.linalg.eigh's UPLO='L');
 // not modified. evals[d] ascending. U [d][ldu]: column c holds the eigenvector of eigenvalue
 // number d-k+c (the k largest, ascending). Everything is enqueued on `st`; nothing syncs.
+// flags: bit 0 = deterministic (no split-K in the tensor-core stages).
 int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, long long ldu,
-         void* ws, size_t ws_bytes, cudaStream_t st);
+         void* ws, size_t ws_bytes, cudaStream_t st, unsigned flags = 0);
 
 // Debug: per-phase cycle counters of the panel kernel (CTA 0), see eigh.cu.
 void eigh_debug_profile(int enable);

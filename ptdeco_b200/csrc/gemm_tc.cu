@@ -842,7 +842,7 @@ int gemm_tc(const GemmOperand& A, const GemmOperand& B, int M, int N, int K, int
     }
   }
   if (g_dbg[1] > 0) splitk = static_cast<int>(std::min<long long>(g_dbg[1], g.kblocks));
-  if (!ep.accumulate) splitk = 1;
+  if (!ep.accumulate || ep.deterministic) splitk = 1;
   g.splitk = splitk;
   // make every split non-empty
   {

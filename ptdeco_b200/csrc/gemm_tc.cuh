@@ -41,6 +41,7 @@ struct GemmEpilogue {
   const float* bias = nullptr;  // optional, length N, added after alpha scaling
   int accumulate = 0;           // 0: C = result, 1: C += result (red.global.add)
   int lower_only = 0;           // 1: only tiles touching the lower triangle (M == N)
+  int deterministic = 0;        // 1: no split-K (every output element has one producer, fixed order)
 };
 
 // Returns 0 on success, negative errno-style on bad arguments / launch failure.

@@ -31,7 +31,8 @@ namespace {
 // Runtime knobs (set through ptdeco_debug_set keys 200..206; the Python loader maps the
 // PTDECO_B200_* environment variables onto them ONCE at load time -- nothing on the forward path
 // reads the environment): 0 force the decode kernel, 1 no decode kernel, 2 no fused kernel,
-// 3 no persistent kernel, 4 no TMA store, 5 tile rotation (-1 = default), 6 pipeline stages.
+// 3 no persistent kernel, 4 no TMA store, 5 tile rotation (-1 = default), 6 pipeline stages,
+// 7 forced token rows per tile (multiple of 8 in [8, 128]; 0 = cost model).
 long long g_knob[8] = {0, 0, 0, 0, 0, -1, 0, 0};
 
 // cudaFuncSetAttribute is per device: remember which devices were configured.
@@ -84,6 +85,7 @@ constexpr int F_TILE_M = 128;
 constexpr int F_BK = 64;
 constexpr int F_TILE_N = 256;
 constexpr int F_MAX_STAGES = 5;
+constexpr int F_MAX_STAGES1 = 8;  // GEMM-1 ring of the narrow-rank plan (see below)
 constexpr int F_XBYTES = F_TILE_M * F_BK * 2;    // X k-block: 128 rows x 128 B
 constexpr int F_WBYTES = 256 * F_BK * 2;         // W2 tile: 256 rows x 128 B
 constexpr int F_HBLOCK = F_TILE_M * 128;         // one 64-wide k-block of H: 16 KB
@@ -93,6 +95,11 @@ constexpr int F_STG_BYTES = F_EPI_WARPS * 4096;  // output staging, 4 KB per epi
 // Shared-memory plans (the ring must keep ~2 us of TMA latency covered, so it is as deep as fits):
 //   kp <= 128: 4 slots of [X 16 KB | W1 16 KB]; a 32 KB W2 tile fills a whole slot; H 32 KB;
 //              separate 64 KB output staging (4 KB per epilogue warp)         -> 225 KB
+//              GEMM 1 streams 2 MB per token tile through ONE SM; with 4 slots (128 KB in flight)
+//              Little's law caps that at ~75 GB/s (measured: the phase took 27 of the kernel's
+//              47 us at N = 8192). H and the output staging are idle until GEMM 1 is over, so
+//              during GEMM 1 the ring extends over them: 7 slots (6 at kp = 64), its own barriers;
+//              GEMM 2 restarts on the first 4 slots once GEMM 1 has committed.
 //   kp  > 128: 3 slots of [X 16 KB | W 32 KB]; W2 tiles land in the W part; H 64 KB; the idle X
 //              parts of the three slots plus 16 KB are the output staging     -> 224 KB
 
@@ -104,6 +111,14 @@ struct FusedArgs {
   const float* bias;
   int tma_store;  // 1: Y tiles leave through shared memory + cp.async.bulk.tensor stores
   int stages, slot_bytes, w2_off, stg_separate, rotate;
+  int stages1;  // slots of the GEMM-1 ring (== stages: one ring for both phases)
+  // Token rows per tile (multiple of 8, <= 128). The tensor core always works on 128 rows; when
+  // the op is HBM-bound (small k) the rows are what costs, so the host sizes the tiles to fill
+  // whole waves of SMs (N = 32768: 293 tiles of 112 rows = 2 full waves instead of 1.73; N = 8192:
+  // 147 tiles of 56 rows on 147 SMs instead of 64 tiles). X boxes / Y stores are clipped to
+  // tile_m rows; the tile's remaining accumulator rows hold don't-care values (rows are
+  // independent in both GEMMs) and are never stored.
+  int tile_m;
 };
 
 __global__ void __launch_bounds__(F_THREADS, 1)
@@ -123,11 +138,17 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   uint64_t* h_ready = h_full + 1;
   uint64_t* y_full = h_ready + 1;
   uint64_t* y_empty = y_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 2);
+  uint64_t* full1 = y_empty + 2;               // GEMM-1 ring when it is longer than the GEMM-2 ring
+  uint64_t* empty1 = full1 + F_MAX_STAGES1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty1 + F_MAX_STAGES1);
+  const int F_STAGES1 = g.stages1;
+  const bool two_rings = F_STAGES1 != F_STAGES;
+  uint64_t* f1 = two_rings ? full1 : full;
+  uint64_t* e1 = two_rings ? empty1 : empty;
 
   const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const int rt = blockIdx.x / g.groups, og = blockIdx.x % g.groups;
-  const int m0 = rt * F_TILE_M;
+  const int m0 = rt * g.tile_m;
   const int t0 = og * g.tiles_per_group;
   const int t1 = min(g.out_tiles, t0 + g.tiles_per_group);
   const int kb1 = (g.in_f + F_BK - 1) / F_BK;
@@ -147,6 +168,11 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
+    if (two_rings)
+      for (int s = 0; s < F_STAGES1; ++s) {
+        mbar_init(&full1[s], 1);
+        mbar_init(&empty1[s], 1);
+      }
     mbar_init(h_full, 1);
     mbar_init(h_ready, F_EPI_WARPS);
     for (int a = 0; a < 2; ++a) {
@@ -172,15 +198,20 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     uint32_t phase = 0;
     for (int kk = 0; kk < kb1; ++kk) {  // GEMM 1 operands
       const int kb = (kk + rot1) % kb1;
-      mbar_wait(&empty[stage], phase ^ 1);
+      mbar_wait(&e1[stage], phase ^ 1);
       if (elect_one()) {
         uint8_t* sA = smem + stage * F_STAGE;
-        mbar_expect_tx(&full[stage], F_XBYTES + g.kp * 128);
-        tma_load_3d(sA, &tmX, &full[stage], kb * F_BK, m0, 0);
-        tma_load_3d(sA + F_XBYTES, &tmW1, &full[stage], kb * F_BK, 0, 0);
+        mbar_expect_tx(&f1[stage], g.tile_m * 128 + g.kp * 128);
+        tma_load_3d(sA, &tmX, &f1[stage], kb * F_BK, m0, 0);
+        tma_load_3d(sA + F_XBYTES, &tmW1, &f1[stage], kb * F_BK, 0, 0);
       }
       __syncwarp();
-      if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+      if (++stage == F_STAGES1) { stage = 0; phase ^= 1; }
+    }
+    if (two_rings) {  // the long ring overlaps H and the staging: GEMM 2 starts on fresh barriers
+      mbar_wait(h_full, 0);  // every GEMM-1 MMA has read its slot
+      stage = 0;
+      phase = 0;
     }
     for (int tt = 0; tt < ntl; ++tt) {  // GEMM 2: W2 tiles
       const int t = t0 + (tt + rot3) % ntl;
@@ -203,7 +234,7 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = 0; kb < kb1; ++kb) {
-      mbar_wait(&full[stage], phase);
+      mbar_wait(&f1[stage], phase);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sA = smem_base + stage * F_STAGE;
@@ -211,13 +242,17 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         umma_bf16(h_tmem, ad, bd, idesc1, kb > 0 ? 1u : 0u);
 #pragma unroll
         for (int ks = 1; ks < F_BK / 16; ++ks) umma_bf16_acc(h_tmem, ad + 2 * ks, bd + 2 * ks, idesc1);
-        umma_commit(&empty[stage]);
+        umma_commit(&e1[stage]);
       }
       __syncwarp();
-      if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+      if (++stage == F_STAGES1) { stage = 0; phase ^= 1; }
     }
     if (elect_one()) umma_commit(h_full);
     __syncwarp();
+    if (two_rings) {
+      stage = 0;
+      phase = 0;
+    }
     mbar_wait(h_ready, 0);  // H is in shared memory as a swizzled bf16 K-major tile
     tc_fence_after();
     const uint32_t sH = smem_u32(hbuf);
@@ -337,11 +372,15 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0 && n0 < g.out_f && m0 + q * 32 < g.n) {
-          tma_store_3d(&tmY, stg, n0, m0 + q * 32, 0);
+        if (lane == 0 && n0 < g.out_f) {  // 8-row boxes: only rows of THIS tile leave
+#pragma unroll
+          for (int r8 = 0; r8 < 4; ++r8) {
+            const int rl = q * 32 + r8 * 8;
+            if (rl < g.tile_m && m0 + rl < g.n) tma_store_3d(&tmY, stg + r8 * 1024, n0, m0 + rl, 0);
+          }
           bulk_commit();
         }
-      } else if (m < g.n && n0 < g.out_f) {
+      } else if (m < g.n && row < g.tile_m && n0 < g.out_f) {
         __nv_bfloat16* yrow = g.Y + static_cast<long long>(m) * g.ldy + n0;
         if (yvec && n0 + 64 <= g.out_f) {
 #pragma unroll
@@ -405,7 +444,7 @@ lowrank_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 1);
 
   const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
-  const int row_tiles = (g.n + F_TILE_M - 1) / F_TILE_M;
+  const int row_tiles = (g.n + g.tile_m - 1) / g.tile_m;
   const int J = (row_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                 static_cast<int>(gridDim.x);  // token tiles of this CTA: blockIdx.x + j * gridDim.x
   const int kb1 = (g.in_f + F_BK - 1) / F_BK;
@@ -444,11 +483,11 @@ lowrank_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     int stage = 0;
     uint32_t phase = 0;
     auto load_k1 = [&](int j, int kb) {
-      const int m0 = (static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x)) * F_TILE_M;
+      const int m0 = (static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x)) * g.tile_m;
       mbar_wait(&empty[stage], phase ^ 1);
       if (elect_one()) {
         uint8_t* slot = smem + stage * P_SLOT;
-        mbar_expect_tx(&full[stage], F_XBYTES + g.kp * 128);
+        mbar_expect_tx(&full[stage], g.tile_m * 128 + g.kp * 128);
         tma_load_3d(slot, &tmX, &full[stage], kb * F_BK, m0, 0);
         tma_load_3d(slot + F_XBYTES, &tmW1, &full[stage], kb * F_BK, 0, 0);
       }
@@ -557,7 +596,7 @@ lowrank_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
     uint8_t* stg = stg_base + (warp - 2) * 4096;
     uint32_t ytile = 0;
     for (int j = 0; j < J; ++j) {
-      const int m0 = (static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x)) * F_TILE_M;
+      const int m0 = (static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x)) * g.tile_m;
       // ---- drain H of token tile j into Hs (bf16, 128B-swizzled K-major tile)
       mbar_wait(&h_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
@@ -631,8 +670,12 @@ lowrank_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0 && n0 < g.out_f && m0 + q * 32 < g.n) {
-          tma_store_3d(&tmY, stg, n0, m0 + q * 32, 0);
+        if (lane == 0 && n0 < g.out_f) {  // 8-row boxes: only rows of THIS tile leave
+#pragma unroll
+          for (int r8 = 0; r8 < 4; ++r8) {
+            const int rl = q * 32 + r8 * 8;
+            if (rl < g.tile_m && m0 + rl < g.n) tma_store_3d(&tmY, stg + r8 * 1024, n0, m0 + rl, 0);
+          }
           bulk_commit();
         }
       }
@@ -1036,49 +1079,75 @@ int launch_fused(const void* X, long long ldx, const void* W1, long long ldw1, c
   g.Y = static_cast<__nv_bfloat16*>(Y);
   g.ldy = ldy;
   g.bias = bias;
-  const int row_tiles = static_cast<int>((n + F_TILE_M - 1) / F_TILE_M);
   const int sms = device_sm_count();
-  const int kb1 = (in_f + F_BK - 1) / F_BK, kb2 = g.kp / F_BK;
-  // split `out` over CTAs of one token tile when token tiles alone cannot fill the GPU
+  // Shape of the launch: rows per token tile (multiple of 8) and, when token tiles alone cannot
+  // fill the GPU, a split of `out` over the CTAs of one token tile. Two-term model per candidate:
+  // tensor time = waves x (128-row MMAs of one unit; the tensor core always works on 128 rows),
+  // memory time = bytes / HBM bandwidth (X re-read by the CTAs sharing a token tile counted at half:
+  // mostly L2 hits), plus a per-wave prologue / drain overhead.
+  // Per-SM streaming rate: what one CTA's TMA ring sustains (bytes in flight / latency), measured
+  // ~75 GB/s with 4 x 32 KB slots and ~1.3x that with the 7-slot GEMM-1 ring. Every unit streams
+  // its X rows AND the weights (W1 whole, its share of W2), which is what makes small tiles lose.
+  const double mma_rate = 1.6e15 / sms, hbm = 6.5e12, sm_stream = 95e9, wave_overhead = 3e-6;
   double best = 1e300;
   g.groups = 1;
   g.tiles_per_group = g.out_tiles;
-  for (int G = 1; G <= g.out_tiles; ++G) {
-    const int tpg = (g.out_tiles + G - 1) / G;
-    const int geff = (g.out_tiles + tpg - 1) / tpg;
-    const long long units = static_cast<long long>(row_tiles) * geff;
-    const long long waves = (units + sms - 1) / sms;
-    const double cost = static_cast<double>(waves) *
-                        (static_cast<double>(kb1) * g.kp + static_cast<double>(tpg) * kb2 * F_TILE_N);
-    if (cost < best * 0.999) {
-      best = cost;
-      g.groups = geff;
-      g.tiles_per_group = tpg;
+  g.tile_m = F_TILE_M;
+  const int tm_lo = g_knob[7] > 0 ? static_cast<int>(g_knob[7]) : 32;
+  const int tm_hi = g_knob[7] > 0 ? static_cast<int>(g_knob[7]) : F_TILE_M;
+  for (int tm = tm_hi; tm >= tm_lo; tm -= 8) {
+    const long long rtiles = (n + tm - 1) / tm;
+    for (int G = 1; G <= g.out_tiles; ++G) {
+      const int tpg = (g.out_tiles + G - 1) / G;
+      const int geff = (g.out_tiles + tpg - 1) / tpg;
+      const long long units = rtiles * geff;
+      const long long waves = (units + sms - 1) / sms;
+      const double t_mma = static_cast<double>(waves) * 2.0 * F_TILE_M * g.kp *
+                           (static_cast<double>(in_f) + static_cast<double>(tpg) * F_TILE_N) / mma_rate;
+      const double bytes = 2.0 * static_cast<double>(n) * (in_f * (1.0 + 0.5 * (geff - 1)) + out_f);
+      const double unit_bytes = 2.0 * (static_cast<double>(tm) * in_f + static_cast<double>(g.kp) * in_f +
+                                       static_cast<double>(tpg) * F_TILE_N * (g.kp + tm));
+      const double t_mem = std::max(bytes / hbm, static_cast<double>(waves) * unit_bytes / sm_stream);
+      const double cost = std::max(t_mma, t_mem) + wave_overhead * static_cast<double>(waves);
+      if (cost < best * 0.98) {
+        best = cost;
+        g.groups = geff;
+        g.tiles_per_group = tpg;
+        g.tile_m = tm;
+      }
     }
   }
+  const int row_tiles = static_cast<int>((n + g.tile_m - 1) / g.tile_m);
   CUtensorMap tx, tw1, tw2, ty;
   int rc;
   const bool persistent = g.kp <= 128 && row_tiles >= sms && aligned16(Y) && (ldy % 8) == 0 &&
                           g_knob[3] == 0;
   g.tma_store = (aligned16(Y) && (ldy % 8) == 0 && g_knob[4] == 0) ? 1 : 0;
   if (g.tma_store) {
-    if ((rc = make_tma_2d_bf16(&ty, Y, out_f, n, ldy, 32))) return rc;
+    if ((rc = make_tma_2d_bf16(&ty, Y, out_f, n, ldy, 8))) return rc;
   } else {
     memset(&ty, 0, sizeof(ty));
   }
-  if ((rc = make_tma_2d_bf16(&tx, X, in_f, n, ldx, F_TILE_M))) return rc;
+  if ((rc = make_tma_2d_bf16(&tx, X, in_f, n, ldx, g.tile_m))) return rc;
   if ((rc = make_tma_2d_bf16(&tw1, W1, in_f, k, ldw1, g.kp))) return rc;
   if ((rc = make_tma_2d_bf16(&tw2, W2, k, out_f, ldw2, F_TILE_N))) return rc;
   if (g.kp <= 128) {
     g.stages = 4; g.slot_bytes = 32768; g.w2_off = 0; g.stg_separate = 1;
+    // GEMM-1 ring over the slots + the (then idle) H block and output staging
+    g.stages1 = g_knob[6] == 1 ? g.stages
+                               : g.stages + ((g.kp / F_BK) * F_HBLOCK + F_STG_BYTES) / g.slot_bytes;
   } else {
     g.stages = 3; g.slot_bytes = 49152; g.w2_off = F_XBYTES; g.stg_separate = 0;
+    g.stages1 = g.stages;
   }
   g.rotate = 1;
   if (g_knob[5] >= 0) g.rotate = static_cast<int>(g_knob[5]);
-  if (g_knob[6] >= 2 && g_knob[6] <= g.stages) g.stages = static_cast<int>(g_knob[6]);  // experiment knob
+  if (g_knob[6] >= 2 && g_knob[6] <= g.stages) {  // experiment knob: a shorter single ring
+    g.stages = static_cast<int>(g_knob[6]);
+    g.stages1 = g.stages;
+  }
   const int F_SMEM = g.stages * g.slot_bytes + (g.kp / F_BK) * F_HBLOCK +
-                     (g.stg_separate ? F_STG_BYTES : 4 * 4096) + 1024 + 256;
+                     (g.stg_separate ? F_STG_BYTES : 4 * 4096) + 1024 + 512;
   bool& attr = *lr_attr_flag(1);
   if (!attr) {
     if (cudaFuncSetAttribute(lowrank_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

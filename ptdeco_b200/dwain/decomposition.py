@@ -24,6 +24,7 @@ from __future__ import annotations
 
 import collections.abc
 import logging
+import os
 import time
 from typing import Any, Optional
 
@@ -74,8 +75,15 @@ def decompose_in_place(
     decompose_in_float64: bool = True,
     precomputing_covariance_num_splits: Optional[int] = None,
     trace: Optional[list] = None,
+    process_group: Any = None,
 ) -> dict[str, Any]:
-    """D:677-800. Returns the decompose_config (insertion order = reversed module order)."""
+    """D:677-800. Returns the decompose_config (insertion order = reversed module order).
+
+    `process_group` (not in the reference) opts into the multi-GPU path: pass a torch.distributed
+    group (or "world") when EVERY rank runs this call on its own replica of the model with
+    IDENTICAL data / metric iterators and a deterministic `finetune_fn`. Calibration steps, rank
+    trials and metric batches are then sharded over the ranks and every rank ends with the same
+    modules. Without it the call is single-GPU even when torch.distributed is initialised."""
     start_time = time.perf_counter()
     device = torch.device(device)
     if device.type != "cuda":
@@ -93,7 +101,7 @@ def decompose_in_place(
 
     decompose_config: dict[str, Any] = {}
     decomposed_submodules: list[str] = []
-    group = parallel.default_group()
+    group = parallel.resolve_group(process_group)
 
     if precomputing_covariance_num_splits is not None and precomputing_covariance_num_splits > 0:
         u_dict = _precompute_covariance_matrix_decompositions_in_splits(
@@ -121,7 +129,7 @@ def decompose_in_place(
                 max_accepted_ppl_diff=max_accepted_ppl_diff, min_rank=min_rank,
                 decompose_in_float64=decompose_in_float64,
                 u_matrix=u_dict.pop(name) if len(u_dict) > 0 else None, trace=trace,
-                pair_state=pair_state)
+                pair_state=pair_state, group=group)
             logger.info(f"stop reserved gpu mem={utils.get_gpu_reserved_memory_gb():.2f} GB")
         current_params -= result.get("drop_in_params", 0)
         logger.info(f"CURRENT PARAMS IN M: {current_params / 1e6}")
@@ -164,6 +172,7 @@ def _process_module(
     u_matrix: Optional[torch.Tensor] = None,
     trace: Optional[list] = None,
     pair_state: Optional[_wrap.PairState] = None,
+    group: Any = None,
 ) -> dict[str, Any]:
     """D:333-537."""
     indent = "    "
@@ -226,19 +235,22 @@ def _process_module(
 
     # ---- ... evaluate every candidate (the reference evaluates all of them too: the smallest
     # accepted rank wins even when a larger one was rejected). The model does not change inside
-    # one layer's search, so with a process group trial t is evaluated by rank t mod world; every
-    # rank draws every metric batch, keeping iterator positions those of the reference.
-    group = parallel.default_group()
+    # one layer's search, so with a process group the (trial, metric batch) pairs are dealt
+    # round-robin to the ranks; every rank draws every metric batch, keeping iterator positions
+    # those of the reference, and the per-trial sums meet in one all-reduce.
     my_rank, world = parallel.rank_and_world(group)
     results = torch.zeros((max(1, len(plan)), 3), dtype=torch.float64, device=orig_device)
+    job = 0
     for t, (rank_t, _, _, _) in enumerate(plan):
         batches = [next(metric_iterator) for _ in range(num_metric_steps)]
-        if t % world != my_rank:
+        mine = [b for j, b in enumerate(batches, start=job) if j % world == my_rank]
+        job += num_metric_steps
+        if not mine:
             continue
         # no K5 GEMM (D:429) and no weight copy: the wrapper runs the two-factor op for the trial
         uk, w1 = factors(rank_t)
         acc = torch.zeros(3, dtype=torch.float64, device=orig_device)
-        for batch in batches:
+        for batch in mine:
             input_dict = utils.to_device(batch, device)
             nsr_sample, ppl_deco_sample, ppl_orig_sample = _compute_metrics(
                 input_dict=input_dict, root_module=root_module, decomposed_submodule=wrapper,
@@ -248,7 +260,7 @@ def _process_module(
                                 ppl_deco_sample.double()])
         results[t] = acc / num_metric_steps
     if group is not None and len(plan) > 0:
-        torch.distributed.all_reduce(results, group=group)  # rows of other ranks are zero here
+        torch.distributed.all_reduce(results, group=group)  # every (trial, batch) lives on one rank
     measured = results.tolist() if len(plan) > 0 else []  # the one host sync of the layer
 
     # ---- ... then apply the accept / reject rules in order (D:445-487)
@@ -389,30 +401,59 @@ def _precompute_covariance_matrix_decompositions(
     group=None,
 ) -> dict[str, torch.Tensor]:
     """D:580-633: one set of num_data_steps forwards updates the covariances of every listed
-    Linear at once. With a process group, rank r only runs the steps i = r (mod world) -- every
-    rank still draws all num_data_steps batches, so iterator positions stay those of the
-    reference -- partial covariances are summed over NVLink, and the eigensolves are distributed
-    round-robin with the owners broadcasting their top-k blocks."""
+    Linear at once. Targets that read the SAME input tensor (q/k/v, gate/up) share one input-side
+    accumulator (see CovarianceUnits). With a process group, rank r only runs the steps i = r
+    (mod world) -- every rank still draws all num_data_steps batches, so iterator positions stay
+    those of the reference -- the partial covariances are summed over NVLink (lower triangles,
+    asynchronously) and the eigensolves are distributed round-robin over the accumulators, each
+    owner broadcasting its top-k blocks while the other ranks are still solving theirs."""
     originals = _install_covariance_modules(module, submodule_names, decompose_in_float64,
-                                            reduction_factor)
+                                            reduction_factor, share_inputs=True)
+    units = module.get_submodule(submodule_names[0]).units if submodule_names else None
 
     module.eval()
     rank, world = parallel.rank_and_world(group)
+    first_batch = None
+    ran = 0
     with torch.no_grad():
         for step in range(num_data_steps):
             batch = next(data_iterator)
+            if step == 0:
+                first_batch = batch
+                parallel.check_identical_batches(batch, group)
             if step % world != rank:
                 continue
             _ = module(utils.to_device(batch, device))
+            ran += 1
+        if units is not None:
+            if ran == 0 and first_batch is not None:
+                # fewer steps than ranks: this rank still needs the layout of the accumulators
+                units.dry = True
+                _ = module(utils.to_device(first_batch, device))
+            units.finish_probe()
     utils.relieve_gpu_memory_pressure()
 
     logger.info("Computing eigenvectors ...")
     u_dict: dict[str, torch.Tensor] = {}
-    for idx, name in enumerate(submodule_names):
-        sub = module.get_submodule(name)
-        k = _max_rank_consumed(sub.in_features, sub.out_features, reduction_factor)
-        u_dict[name] = parallel.owner_computes(
-            idx, group, lambda: sub.get_eigenvectors(k, group=None), sub.acc, (sub.out_features, k))
+    if units is not None:
+        ks = {id(m): _max_rank_consumed(m.in_features, m.out_features, reduction_factor)
+              for u in units.units for m in u.members}
+        jobs = []
+        for u in units.units:
+            sizes = [(m.out_features, ks[id(m)]) for m in u.members]
+            total = sum(a * b for a, b in sizes)
+            jobs.append((u.acc, (lambda u=u: torch.cat(
+                [m.get_eigenvectors(ks[id(m)]).reshape(-1) for m in u.members])), (total,)))
+        flats = parallel.owners_compute_pipelined(jobs, group, total_steps=num_data_steps)
+        by_module = {}
+        for u, flat in zip(units.units, flats):
+            off = 0
+            for m in u.members:
+                n_el = m.out_features * ks[id(m)]
+                by_module[id(m)] = flat[off:off + n_el].reshape(m.out_features, ks[id(m)])
+                off += n_el
+        for name in submodule_names:
+            u_dict[name] = by_module[id(module.get_submodule(name))]
     _restore_modules(module, originals)
     utils.relieve_gpu_memory_pressure()
     return u_dict
@@ -420,10 +461,13 @@ def _precompute_covariance_matrix_decompositions(
 
 def _install_covariance_modules(module: torch.nn.Module, submodule_names: list[str],
                                 decompose_in_float64: bool,
-                                reduction_factor: Optional[float] = None) -> dict[str, torch.nn.Module]:
+                                reduction_factor: Optional[float] = None,
+                                share_inputs: bool = True) -> dict[str, torch.nn.Module]:
     """D:592-603: swap every listed Linear for a CovarianceComputingLinearModule that shares its
-    weight and bias. Returns the originals for _restore_modules."""
+    weight and bias. Returns the originals for _restore_modules. With `share_inputs` the modules
+    of this call form one CovarianceUnits registry (reachable as `<module>.units`)."""
     originals: dict[str, torch.nn.Module] = {}
+    units = CovarianceUnits() if share_inputs else None
     for name in submodule_names:
         old = module.get_submodule(name)
         if not isinstance(old, torch.nn.Linear):
@@ -434,7 +478,8 @@ def _install_covariance_modules(module: torch.nn.Module, submodule_names: list[s
         k = (None if reduction_factor is None
              else _max_rank_consumed(old.in_features, old.out_features, reduction_factor))
         utils.replace_submodule_in_place(
-            module, name, CovarianceComputingLinearModule(old.weight, old.bias, decompose_in_float64, k))
+            module, name,
+            CovarianceComputingLinearModule(old.weight, old.bias, decompose_in_float64, k, units=units))
     return originals
 
 
@@ -445,24 +490,160 @@ def _restore_modules(module: torch.nn.Module, originals: dict[str, torch.nn.Modu
         utils.replace_submodule_in_place(module, name, old)
 
 
+class CovarianceUnit:
+    """One covariance accumulator and the covariance modules that read it: kind "output" (C = E[y y^T]
+    of one module, the reference formulation) or "input" (S = E[x x^T] of the tensor the members
+    share; a member's C = W S W^T follows without touching the activations again)."""
+
+    def __init__(self, kind: str, acc: linalg.CovarianceAccumulator, members: list) -> None:
+        self.kind = kind
+        self.acc = acc
+        self.members = members
+        self.last_call = -1
+        self.last_x: Optional[torch.Tensor] = None
+        self._s_final: Optional[torch.Tensor] = None
+        self._s_eig: Optional[tuple[torch.Tensor, torch.Tensor]] = None
+
+    def finalized_input_covariance(self) -> torch.Tensor:
+        if self._s_final is None:
+            # centring / damping act on C, not on S (damping is a multiple of I on C)
+            self._s_final = self.acc.finalize(use_mean=False, damp_factor=0.0)
+        return self._s_final
+
+    def input_eigensystem(self) -> tuple[torch.Tensor, torch.Tensor]:
+        """eigh(S), computed once for all members that take the in x in route (gate and up)."""
+        if self._s_eig is None:
+            self._s_eig = linalg.eigh(self.finalized_input_covariance())
+        return self._s_eig
+
+
+class CovarianceUnits:
+    """Which covariance modules of one calibration split see the SAME input tensor.
+
+    The reference gives every target its own d_out x d_out accumulator (D:166-208); q/k/v and
+    gate/up of a decoder read one tensor each, so their input covariance S = E[x x^T] is the same
+    matrix accumulated two or three times. The first forward is a probe: every module records the
+    tensor OBJECT it received; modules that received the same object form one unit with a single
+    input-side accumulator (Llama-3-8B decoder layer: 4 SYRK launches per step instead of 7, one of
+    them shared by q/k/v and one by gate/up). Later forwards check the identity again and fail
+    loudly if the model's dataflow changed. A module called twice within one forward (weight
+    sharing) switches the whole split back to private accumulators."""
+
+    def __init__(self) -> None:
+        self.probing = True
+        self.dry = False            # probe for the layout only, fold nothing in
+        self.records: list = []     # (module, x, rows, y_rows) of the probe forward, in call order
+        self.units: list[CovarianceUnit] = []
+        self.calls = 0              # forward number, counted at the first module of the probe order
+        self.first_module = None
+        self.multi_call = False
+
+    def on_forward(self, mod, x: torch.Tensor, rows: torch.Tensor, y_rows: torch.Tensor) -> None:
+        if self.probing:
+            seen = any(r[0] is mod for r in self.records)
+            if self.first_module is None:
+                self.first_module = mod
+            elif mod is self.first_module:
+                self.finish_probe()  # the first module again: the probe forward is over
+            elif seen:
+                self.multi_call = True  # weight sharing inside the model: no input sharing
+            if self.probing:
+                self.records.append((mod, x, rows, y_rows))
+                return
+        if mod is self.first_module:
+            self.calls += 1
+        unit = mod.unit
+        if unit is None:  # not seen by the probe (it ended early on a re-entrant first module)
+            unit = mod.unit = self._private_unit(mod)
+            self.units.append(unit)
+        if unit.kind == "output":
+            _update_Eyyt_in_place(unit.acc, y_rows)
+        elif len(unit.members) == 1:
+            _update_Eyyt_in_place(unit.acc, rows)
+        elif unit.last_call != self.calls:
+            _update_Eyyt_in_place(unit.acc, rows)
+            unit.last_call, unit.last_x = self.calls, x
+        elif x is not unit.last_x:
+            raise RuntimeError(
+                "ptdeco_b200: modules that shared one input tensor in the first calibration forward "
+                f"received different tensors later ({len(unit.members)} members); "
+                "set PTDECO_B200_SHARE_INPUTS=0")
+
+    @staticmethod
+    def _private_unit(mod) -> CovarianceUnit:
+        kind, d = ("input", mod.in_features) if mod.input_side else ("output", mod.out_features)
+        acc = linalg.CovarianceAccumulator(
+            d, mod.weight.device, defer_rows=linalg.default_defer_rows(d, mod.weight.element_size()))
+        return CovarianceUnit(kind, acc, [mod])
+
+    def finish_probe(self) -> None:
+        """Turn the probe forward's records into units and fold the probe batch in."""
+        if not self.probing:
+            return
+        self.probing = False
+        share = os.environ.get("PTDECO_B200_SHARE_INPUTS", "1") != "0" and not self.multi_call
+        groups: dict[int, list] = {}
+        for rec in self.records:
+            groups.setdefault(id(rec[1]) if share else id(rec[0]), []).append(rec)
+        for recs in groups.values():
+            mods = [r[0] for r in recs]
+            in_f = mods[0].in_features
+            shared = (share and len(recs) >= 2 and all(m.in_features == in_f for m in mods)
+                      and in_f <= 2 * max(m.out_features for m in mods))
+            if shared:  # one S = E[x x^T] for every module that read this tensor
+                acc = linalg.CovarianceAccumulator(
+                    in_f, mods[0].weight.device,
+                    defer_rows=linalg.default_defer_rows(in_f, mods[0].weight.element_size()))
+                unit = CovarianceUnit("input", acc, mods)
+                for m in mods:
+                    m.unit = unit
+                if not self.dry:
+                    _update_Eyyt_in_place(acc, recs[0][2])
+                self.units.append(unit)
+                continue
+            for rec in recs:  # private accumulators (one record per call of the module)
+                m = rec[0]
+                if m.unit is None:
+                    m.unit = self._private_unit(m)
+                    self.units.append(m.unit)
+                if not self.dry:
+                    _update_Eyyt_in_place(m.unit.acc, rec[3] if m.unit.kind == "output" else rec[2])
+        self.records = []
+        self.calls = 1
+
+
 class CovarianceComputingLinearModule(torch.nn.Module):
     """D:166-208: stands in for a target Linear during the precompute pass; its forward IS the
     layer forward (y = x W^T on the tcgen05 GEMM engine) and folds the layer's activations into
-    the covariance: the output y like the reference, or -- when in < out and only eigenvectors in
-    range(W) are wanted -- the input x (linalg.eigvecs_from_input_covariance)."""
+    a covariance: the output y like the reference, or -- when in < out and only eigenvectors in
+    range(W) are wanted, or when several targets read the same tensor (CovarianceUnits) -- the
+    input x (C = W S W^T)."""
 
     def __init__(self, weight: torch.nn.Parameter, bias: Optional[torch.nn.Parameter],
-                 decompose_in_float64: bool, num_vectors: Optional[int] = None):
+                 decompose_in_float64: bool, num_vectors: Optional[int] = None,
+                 units: Optional[CovarianceUnits] = None):
         super().__init__()
         self.weight = weight
         self.bias = bias
         self.in_features = weight.shape[1]
         self.out_features = weight.shape[0]
         self.input_side = linalg.use_input_side(self.in_features, self.out_features, num_vectors)
-        d = self.in_features if self.input_side else self.out_features
-        self.acc = linalg.CovarianceAccumulator(
-            d, weight.device, defer_rows=linalg.default_defer_rows(d, weight.element_size()))
+        self.units = units
+        self.unit: Optional[CovarianceUnit] = None
+        if units is None:  # stand-alone module: its own accumulator, decided now
+            d = self.in_features if self.input_side else self.out_features
+            self.unit = CovarianceUnit(
+                "input" if self.input_side else "output",
+                linalg.CovarianceAccumulator(
+                    d, weight.device, defer_rows=linalg.default_defer_rows(d, weight.element_size())),
+                [self])
         self.use_float64 = decompose_in_float64  # accepted; see falor's use_float64 note
+
+    @property
+    def acc(self) -> linalg.CovarianceAccumulator:
+        if self.unit is None:
+            self.units.finish_probe()
+        return self.unit.acc
 
     @property
     def num_data_steps(self) -> int:
@@ -471,7 +652,10 @@ class CovarianceComputingLinearModule(torch.nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         rows = x.reshape(-1, self.in_features)
         y_rows = linalg.linear_nt(rows, self.weight.detach())
-        _update_Eyyt_in_place(self.acc, rows if self.input_side else y_rows)
+        if self.units is not None:
+            self.units.on_forward(self, x, rows, y_rows)
+        else:
+            _update_Eyyt_in_place(self.unit.acc, rows if self.unit.kind == "input" else y_rows)
         y = y_rows.reshape(*x.shape[:-1], self.out_features)
         if self.bias is not None:
             y = y + self.bias
@@ -480,9 +664,23 @@ class CovarianceComputingLinearModule(torch.nn.Module):
     def get_eigenvectors(self, num_vectors: Optional[int] = None, group=None) -> torch.Tensor:
         """Unlike D:206-208 the result stays on the GPU in fp32 (180 GB of HBM make the reference's
         round trip through host memory unnecessary); the rank search casts what it slices."""
-        if self.input_side:
-            return _get_eigenvectors_input_side(self.acc, self.weight.detach(), num_vectors, group)
-        return _get_eigenvectors(self.acc, num_vectors, group)
+        if self.unit is None:
+            self.units.finish_probe()
+        unit = self.unit
+        if unit.kind == "output":
+            return _get_eigenvectors(unit.acc, num_vectors, group)
+        if group is not None:
+            parallel.allreduce_accumulator(unit.acc, group)
+        s_cov = unit.finalized_input_covariance()
+        weight = self.weight.detach()
+        if linalg.use_input_side(self.in_features, self.out_features, num_vectors):
+            return linalg.eigvecs_from_input_covariance(s_cov, weight, num_vectors,
+                                                        s_eig=unit.input_eigensystem())
+        # out <= in (q/k/v/o of a shared tensor): the reference's own out x out problem, with
+        # C = W S W^T formed by two tensor-core GEMMs instead of a SYRK over the activations
+        cov = linalg.covariance_from_input(s_cov, weight, damp_factor=EIGEN_DAMPEN_FACTOR)
+        _, u = linalg.eigh(cov, k=num_vectors)
+        return u
 
 
 def _compute_covariance_matrix_decomposition(

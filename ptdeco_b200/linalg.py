@@ -72,12 +72,14 @@ class CovarianceAccumulator:
         n = y.shape[0]
         need = 0 if (sub is None and _tma_ready(y)) else L.ptdeco_syrk_workspace_bytes(
             nat.dtype_code(y), n, self.d)
-        ws = nat.WORKSPACE.get(y.device, need)
-        nat.check(
-            L.ptdeco_syrk_accumulate(y.data_ptr(), nat.dtype_code(y), n, self.d, y.stride(0),
-                                     nat.ptr(sub), self.C.data_ptr(), self.C.stride(0),
-                                     nat.ptr(self.colsum), alpha, ws.data_ptr(), ws.numel(),
-                                     nat.stream_ptr(y.device)), "ptdeco_syrk_accumulate")
+        with nat.device_of(y):
+            ws = nat.WORKSPACE.get(y.device, need)
+            nat.check(
+                L.ptdeco_syrk_accumulate_ex(y.data_ptr(), nat.dtype_code(y), n, self.d, y.stride(0),
+                                            nat.ptr(sub), self.C.data_ptr(), self.C.stride(0),
+                                            nat.ptr(self.colsum), alpha, ws.data_ptr(), ws.numel(),
+                                            nat.stream_ptr(y.device), nat.call_flags()),
+                "ptdeco_syrk_accumulate")
         self.launches += 1
 
     def update(self, y: torch.Tensor, sub: Optional[torch.Tensor] = None) -> None:
@@ -124,11 +126,12 @@ class CovarianceAccumulator:
         if use_mean and self.colsum is None:
             raise ValueError("accumulator was created without mean tracking")
         self.release_staging()
-        nat.check(
-            nat.lib().ptdeco_cov_finalize(self.C.data_ptr(), self.C.stride(0), self.d,
-                                          nat.ptr(self.colsum), self.steps, int(bool(use_mean)),
-                                          float(damp_factor), None, nat.stream_ptr(self.device)),
-            "ptdeco_cov_finalize")
+        with nat.device_of(self.C):
+            nat.check(
+                nat.lib().ptdeco_cov_finalize(self.C.data_ptr(), self.C.stride(0), self.d,
+                                              nat.ptr(self.colsum), self.steps, int(bool(use_mean)),
+                                              float(damp_factor), None, nat.stream_ptr(self.device)),
+                "ptdeco_cov_finalize")
         return self.C
 
 
@@ -152,10 +155,12 @@ def eigh(cov: torch.Tensor, k: Optional[int] = None) -> tuple[torch.Tensor, torc
     ldu = (k + 3) // 4 * 4
     U = torch.empty((d, ldu), dtype=torch.float32, device=cov.device)
     need = L.ptdeco_eigh_workspace_bytes(d, k)
-    ws = nat.WORKSPACE.get(cov.device, need)
-    nat.check(
-        L.ptdeco_eigh(cov.data_ptr(), d, cov.stride(0), k, evals.data_ptr(), U.data_ptr(), ldu,
-                      ws.data_ptr(), ws.numel(), nat.stream_ptr(cov.device)), "ptdeco_eigh")
+    with nat.device_of(cov):
+        ws = nat.WORKSPACE.get(cov.device, need)
+        nat.check(
+            L.ptdeco_eigh_ex(cov.data_ptr(), d, cov.stride(0), k, evals.data_ptr(), U.data_ptr(), ldu,
+                             ws.data_ptr(), ws.numel(), nat.stream_ptr(cov.device), nat.call_flags()),
+            "ptdeco_eigh")
     return evals, (U if ldu == k else U[:, :k])
 
 
@@ -172,7 +177,26 @@ def use_input_side(in_features: int, out_features: int, num_vectors: Optional[in
             and 1 <= 2 * num_vectors <= in_features)
 
 
-def eigvecs_from_input_covariance(S: torch.Tensor, weight: torch.Tensor, k: int) -> torch.Tensor:
+def covariance_from_input(S: torch.Tensor, weight: torch.Tensor, damp_factor: float = 0.0) -> torch.Tensor:
+    """C = W S W^T ([out, out], fp32, symmetric, damped like D:158-160) from the finalized input
+    covariance S = E[x x^T]: what E[y y^T] of y = x W^T is, formed by two
+    tensor-core GEMMs (fp32 operands go through the bf16x3 split) instead of a SYRK over the
+    activations. Used when several targets share one input tensor."""
+    out_f, in_f = weight.shape
+    if S.shape != (in_f, in_f):
+        raise ValueError(f"S{tuple(S.shape)} does not fit W{tuple(weight.shape)}")
+    ws = gemm(weight, False, S, True, out_f, in_f, in_f)          # W S   (S symmetric)
+    cov = gemm(ws, False, weight, False, out_f, out_f, in_f)       # (W S) W^T
+    with nat.device_of(cov):
+        nat.check(
+            nat.lib().ptdeco_cov_finalize(cov.data_ptr(), cov.stride(0), out_f, None, 1, 0,
+                                          float(damp_factor), None, nat.stream_ptr(cov.device)),
+            "ptdeco_cov_finalize")  # mirrors the lower triangle (exact symmetry) and damps
+    return cov
+
+
+def eigvecs_from_input_covariance(S: torch.Tensor, weight: torch.Tensor, k: int,
+                                  s_eig: Optional[tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
     """Top-k eigenvectors (ascending, [out, k]) of the OUTPUT covariance C = W S W^T computed from
     the input covariance S = E[x x^T] ([in, in], finalized) when in < out.
 
@@ -186,7 +210,7 @@ def eigvecs_from_input_covariance(S: torch.Tensor, weight: torch.Tensor, k: int)
     out_f, in_f = weight.shape
     if S.shape != (in_f, in_f) or not 1 <= k <= in_f:
         raise ValueError(f"S{tuple(S.shape)} / W{tuple(weight.shape)} / k={k} do not fit")
-    ev_s, vs = eigh(S)
+    ev_s, vs = s_eig if s_eig is not None else eigh(S)  # shared by the targets that read one tensor
     scale = ev_s.clamp_min(0.0).sqrt()
     w32 = weight if weight.dtype == torch.float32 else weight.float()
     b = gemm(w32, False, vs * scale, True, out_f, in_f, in_f)             # B = W Vs L^(1/2)
@@ -223,12 +247,14 @@ def gemm(a: torch.Tensor, a_mn_major: bool, b: torch.Tensor, b_mn_major: bool, m
         need = 0
     else:
         need = L.ptdeco_gemm_workspace_bytes(nat.dtype_code(a), nat.dtype_code(b), m, n, k)
-    ws = nat.WORKSPACE.get(a.device, need)
-    nat.check(
-        L.ptdeco_gemm(a.data_ptr(), nat.dtype_code(a), int(a_mn_major), a.stride(0), b.data_ptr(),
-                      nat.dtype_code(b), int(b_mn_major), b.stride(0), m, n, k, float(alpha),
-                      nat.ptr(bias), out.data_ptr(), nat.dtype_code(out), out.stride(0), 0,
-                      ws.data_ptr(), ws.numel(), nat.stream_ptr(a.device)), "ptdeco_gemm")
+    with nat.device_of(a):
+        ws = nat.WORKSPACE.get(a.device, need)
+        nat.check(
+            L.ptdeco_gemm_ex(a.data_ptr(), nat.dtype_code(a), int(a_mn_major), a.stride(0), b.data_ptr(),
+                             nat.dtype_code(b), int(b_mn_major), b.stride(0), m, n, k, float(alpha),
+                             nat.ptr(bias), out.data_ptr(), nat.dtype_code(out), out.stride(0), 0,
+                             ws.data_ptr(), ws.numel(), nat.stream_ptr(a.device), nat.call_flags()),
+            "ptdeco_gemm")
     return out
 
 
@@ -282,10 +308,11 @@ def lowrank_forward(x: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor,
     L = nat.lib()
     code = nat.dtype_code(x)
     need = L.ptdeco_lowrank_workspace_bytes(code, n, in_f, k, out_f)
-    ws = nat.WORKSPACE.get(x.device, need)
-    nat.check(
-        L.ptdeco_lowrank_forward(x.data_ptr(), x.stride(0), w1.data_ptr(), w1.stride(0),
-                                 w2.data_ptr(), w2.stride(0), nat.ptr(bias), y.data_ptr(),
-                                 y.stride(0), code, n, in_f, k, out_f, ws.data_ptr(), ws.numel(),
-                                 nat.stream_ptr(x.device)), "ptdeco_lowrank_forward")
+    with nat.device_of(x):
+        ws = nat.WORKSPACE.get(x.device, need)
+        nat.check(
+            L.ptdeco_lowrank_forward(x.data_ptr(), x.stride(0), w1.data_ptr(), w1.stride(0),
+                                     w2.data_ptr(), w2.stride(0), nat.ptr(bias), y.data_ptr(),
+                                     y.stride(0), code, n, in_f, k, out_f, ws.data_ptr(), ws.numel(),
+                                     nat.stream_ptr(x.device)), "ptdeco_lowrank_forward")
     return y

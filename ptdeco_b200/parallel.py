@@ -22,6 +22,18 @@ def default_group():
     return None
 
 
+def resolve_group(process_group):
+    """The explicit opt-in of the drivers: None -> single GPU; "world" -> the default group when
+    it has more than one rank; a ProcessGroup -> itself (None when it has one rank)."""
+    if process_group is None:
+        return None
+    if isinstance(process_group, str):
+        if process_group != "world":
+            raise ValueError(f"process_group must be None, 'world' or a ProcessGroup, got {process_group!r}")
+        return default_group()
+    return process_group if dist.get_world_size(process_group) > 1 else None
+
+
 def rank_and_world(group) -> tuple[int, int]:
     if group is None:
         return 0, 1

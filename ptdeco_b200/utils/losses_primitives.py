@@ -44,11 +44,12 @@ def calc_per_channel_noise_to_signal_ratio(
     yr = _rows_by_channels(y, tuple(non_channel_dim))
     rows, ch = xr.shape
     L = nat.lib()
-    ws = nat.WORKSPACE.get(x.device, L.ptdeco_nsr_workspace_bytes(ch))
     out = torch.empty((), dtype=torch.float32, device=x.device)
-    nat.check(L.ptdeco_nsr_metric(xr.data_ptr(), yr.data_ptr(), nat.dtype_code(xr), rows, ch,
-                                  float(epsilon), ws.data_ptr(), ws.numel(), out.data_ptr(),
-                                  nat.stream_ptr(x.device)), "ptdeco_nsr_metric")
+    with nat.device_of(x):
+        ws = nat.WORKSPACE.get(x.device, L.ptdeco_nsr_workspace_bytes(ch))
+        nat.check(L.ptdeco_nsr_metric(xr.data_ptr(), yr.data_ptr(), nat.dtype_code(xr), rows, ch,
+                                      float(epsilon), ws.data_ptr(), ws.numel(), out.data_ptr(),
+                                      nat.stream_ptr(x.device)), "ptdeco_nsr_metric")
     return out
 
 
@@ -72,7 +73,8 @@ def calc_kl_loss(student_logits: torch.Tensor, teacher_logits: torch.Tensor) -> 
     if s.dtype != t.dtype or s.dtype not in (torch.float32, torch.bfloat16):
         s, t = s.float(), t.float()
     out = torch.empty((), dtype=torch.float32, device=s.device)
-    nat.check(nat.lib().ptdeco_kl_metric(s.data_ptr(), t.data_ptr(), nat.dtype_code(s), s.shape[0],
-                                         s.shape[1], out.data_ptr(), nat.stream_ptr(s.device)),
-              "ptdeco_kl_metric")
+    with nat.device_of(s):
+        nat.check(nat.lib().ptdeco_kl_metric(s.data_ptr(), t.data_ptr(), nat.dtype_code(s), s.shape[0],
+                                             s.shape[1], out.data_ptr(), nat.stream_ptr(s.device)),
+                  "ptdeco_kl_metric")
     return out

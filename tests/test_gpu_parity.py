@@ -358,6 +358,41 @@ def test_lowrank_forward(dev, dtype, tol, n, in_f, k, out_f):
     assert (y.double().cpu() - ref).abs().max() <= tol * ref.abs().max()
 
 
+@pytest.mark.parametrize("tile_m", [8, 40, 56, 104, 128, 0])
+@pytest.mark.parametrize("n,in_f,k,out_f", [(1000, 256, 64, 520), (5000, 192, 128, 256), (19000, 128, 96, 264),
+                                            (150 * 56 + 3, 128, 64, 128), (300, 320, 200, 1000)])
+def test_lowrank_forward_balanced_token_tiles(dev, tile_m, n, in_f, k, out_f):
+    """The fused / persistent kernels with token tiles of `tile_m` rows (the host normally sizes
+    them so the tiles fill whole waves of SMs; 0 = that cost model): X boxes and Y stores are
+    clipped to the tile, rows past it are never written, ragged last tiles included."""
+    from ptdeco_b200 import _native as nat
+    from ptdeco_b200 import linalg
+    g = torch.Generator().manual_seed(n + k + tile_m)
+    x = torch.randn(n, in_f, generator=g).to(torch.bfloat16)
+    w1 = (torch.randn(k, in_f, generator=g) / in_f ** 0.5).to(torch.bfloat16)
+    w2 = (torch.randn(out_f, k, generator=g) / k ** 0.5).to(torch.bfloat16)
+    b = torch.randn(out_f, generator=g)
+    L = nat.lib()
+    try:
+        L.ptdeco_debug_set(207, tile_m)
+        xd, w1d, w2d, bd = x.to(dev), w1.to(dev), w2.to(dev), b.to(dev)
+        y = linalg.lowrank_forward(xd, w1d, w2d, bd)
+        # a sentinel-filled output must come back fully overwritten and nothing else touched
+        big = torch.full((n + 16, out_f), 7.0, dtype=torch.bfloat16, device=dev)
+        view = big[8:8 + n]
+        nat.check(L.ptdeco_lowrank_forward(
+            xd.data_ptr(), in_f, w1d.data_ptr(), in_f, w2d.data_ptr(), k, bd.data_ptr(),
+            view.data_ptr(), out_f, nat.BF16, n, in_f, k, out_f, None, 0, nat.stream_ptr(dev)),
+            "ptdeco_lowrank_forward")
+        torch.cuda.synchronize()
+    finally:
+        L.ptdeco_debug_set(207, 0)
+    h = (x.double() @ w1.double().T).to(torch.bfloat16).double()
+    ref = h @ w2.double().T + b.double()
+    assert (y.double().cpu() - ref).abs().max() <= 2e-2 * ref.abs().max()
+    assert torch.equal(view, y) and bool((big[:8] == 7.0).all()) and bool((big[8 + n:] == 7.0).all())
+
+
 @pytest.mark.parametrize("n,in_f,k,out_f,bias", [
     (1, 256, 32, 256, False), (5, 320, 96, 1000, True), (16, 4096, 512, 4096, True),
     (33, 768, 200, 3072, True), (128, 2048, 1024, 2048, False), (100, 1024, 1000, 520, True),
@@ -574,6 +609,104 @@ def test_bf16_covariance_module_matches_fp32_einsum_of_same_activations(dev, inp
     assert mod.num_data_steps == steps
     cov = mod.acc.finalize(False, 0.0)
     assert _rel(cov.double().cpu().numpy(), (ref / steps).cpu().numpy()) < COV_TOL
+
+
+def test_deterministic_flag_is_per_call_and_bit_reproducible(dev):
+    """PTDECO_FLAG_DETERMINISTIC (the `flags` of the *_ex entry points, set by
+    nat.set_deterministic): no split-K, so repeated runs agree bit for bit -- the SYRK of a short,
+    wide batch (where the default splits the token dimension over CTAs), a GEMM, and the whole
+    eigensolver; and the flag is not process state of the library (two interleaved calls with
+    different flags do not disturb each other)."""
+    from ptdeco_b200 import _native as nat
+    from ptdeco_b200 import linalg
+    g = torch.Generator().manual_seed(77)
+    y = torch.randn(8192, 256, generator=g).to(torch.bfloat16).to(dev)
+    w = torch.randn(300, 256, generator=g).to(dev)
+
+    def run():
+        acc = linalg.CovarianceAccumulator(256, dev)
+        acc.update(y)
+        cov = acc.finalize(False, 0.01).clone()
+        ev, u = linalg.eigh(cov, k=64)
+        f = linalg.linear_nt(w, cov)
+        return cov, ev, u, f
+
+    try:
+        nat.set_deterministic(True)
+        a = run()
+        nat.set_deterministic(False)
+        other = run()  # default mode in between
+        nat.set_deterministic(True)
+        b = run()
+    finally:
+        nat.set_deterministic(False)
+    for x1, x2 in zip(a, b):
+        assert torch.equal(x1, x2)
+    assert _rel(other[0].cpu().numpy(), a[0].cpu().numpy()) < 1e-6  # same numbers up to summation order
+
+
+def test_workspaces_are_per_stream(dev):
+    """the scratch buffer (the decode kernel keeps its grid-barrier / ticket words and
+    the rank-k intermediate in it) is keyed by (device, stream), so forwards issued on two
+    streams concurrently neither share control words nor free each other's buffer."""
+    from ptdeco_b200 import _native as nat
+    from ptdeco_b200 import linalg
+    g = torch.Generator().manual_seed(3)
+    shapes = [(16, 2048, 512, 2048), (48, 1024, 1024, 4096)]
+    data = []
+    for n, fin, k, fout in shapes:
+        x = torch.randn(n, fin, generator=g).to(torch.bfloat16).to(dev)
+        w1 = (torch.randn(k, fin, generator=g) / fin ** 0.5).to(torch.bfloat16).to(dev)
+        w2 = (torch.randn(fout, k, generator=g) / k ** 0.5).to(torch.bfloat16).to(dev)
+        h = (x.double() @ w1.double().T).to(torch.bfloat16).double()
+        data.append((x, w1, w2, h @ w2.double().T))
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    outs = [[], []]
+    L = nat.lib()
+    try:
+        L.ptdeco_debug_set(200, 1)  # decode kernel for both
+        torch.cuda.synchronize()
+        for _ in range(25):
+            for si, st in enumerate(streams):
+                with torch.cuda.stream(st):
+                    x, w1, w2, _ = data[si]
+                    outs[si].append(linalg.lowrank_forward(x, w1, w2, None))
+        torch.cuda.synchronize()
+    finally:
+        L.ptdeco_debug_set(200, 0)
+    keys = {k for k in nat.WORKSPACE._buf if k[1] in (streams[0].cuda_stream, streams[1].cuda_stream)}
+    assert len(keys) == 2
+    for si in range(2):
+        ref = data[si][3]
+        for y in outs[si]:
+            assert (y.double() - ref).abs().max() <= 1e-2 * ref.abs().max()
+
+
+def test_kernels_run_on_a_non_current_device():
+    """kernel attributes / SM counts are cached per device and the Python layer makes
+    the tensor's device current for the call. Needs two GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from ptdeco_b200 import linalg
+    d1 = torch.device("cuda:1")
+    assert torch.cuda.current_device() == 0
+    g = torch.Generator().manual_seed(9)
+    y = torch.randn(600, 320, generator=g)
+    acc = linalg.CovarianceAccumulator(320, d1)
+    acc.update(y.to(d1))
+    cov = acc.finalize(False, 0.01)
+    ref = (y.double().T @ y.double() / 600).numpy()
+    ref = ref + 0.01 * np.mean(np.diag(ref)) * np.eye(320)
+    assert _rel(cov.cpu().numpy(), ref) < COV_TOL
+    ev, u = linalg.eigh(cov, k=40)
+    assert u.device == d1 and np.abs(ev.cpu().numpy() - np.linalg.eigvalsh(ref)).max() / ref.max() < EVAL_TOL
+    x = torch.randn(300, 320, generator=g).to(torch.bfloat16).to(d1)
+    w1 = torch.randn(64, 320, generator=g).to(torch.bfloat16).to(d1)
+    w2 = torch.randn(512, 64, generator=g).to(torch.bfloat16).to(d1)
+    yl = linalg.lowrank_forward(x, w1, w2, None)
+    refl = (x.double() @ w1.double().T).to(torch.bfloat16).double() @ w2.double().T
+    assert (yl.double() - refl).abs().max() <= 2e-2 * refl.abs().max()
+    assert torch.cuda.current_device() == 0
 
 
 # ------------------------------------------------------------------------------------ K6

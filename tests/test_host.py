@@ -204,6 +204,33 @@ def _gloo_worker(rank, world, port, out_dir):
         u = parallel.owner_computes(layer, group, compute, acc, (d, k))
         assert acc.steps == steps
         results[layer] = u
+    # the pipelined variant (all reductions enqueued up front as lower-triangle bands, owners solve
+    # while later layers are still in flight, asynchronous broadcasts) must give the same blocks
+    accs, jobs = [], []
+    for layer in range(3):
+        acc = _FakeAcc(d)
+        for i in parallel.steps_of_rank(steps, rank, world):
+            part = np.zeros((d, d), np.float32)
+            P.update_Eyyt_in_place(part, cases.step_spectrum_batch(n, d, 10 * layer + i).numpy())
+            acc.C += torch.from_numpy(part)
+            acc.steps += 1
+        acc.C += torch.triu(torch.full((d, d), 1e3 * (rank + 1)), 1)  # the strict upper triangle is
+        accs.append(acc)                                              # unspecified: never sent
+
+        def compute(acc=acc):
+            cov = (torch.tril(acc.C) / acc.steps).numpy()
+            cov = cov + np.tril(cov, -1).T
+            return torch.from_numpy(P.top_k(P.dwain_get_eigenvectors(cov), k).astype(np.float32).copy())
+
+        jobs.append((acc, compute, (d, k)))
+    piped = parallel.owners_compute_pipelined(jobs, group, total_steps=steps)
+    for layer in range(3):
+        assert all(a.steps == steps for a in accs)
+        assert torch.equal(piped[layer], results[layer]), layer
+    parallel.check_identical_batches({"ids": torch.arange(6).reshape(2, 3)}, group)
+    with pytest.raises(RuntimeError):
+        parallel.check_identical_batches(torch.full((2, 2), float(rank)), group)
+    assert parallel.resolve_group(None) is None and parallel.resolve_group("world") is group
     t = parallel.mean_over_ranks(torch.tensor([float(rank)], dtype=torch.float64), group)
     assert t.item() == pytest.approx((world - 1) / 2)
     assert parallel.max_over_ranks(float(rank), torch.device("cpu")) == world - 1
@@ -465,3 +492,78 @@ def test_artifact_round_trip_like_the_reference_readme(tmp_path):
     plain.load_state_dict(torch.load(tmp_path / "fused_state_dict.pt"), strict=True)
     with torch.no_grad():
         torch.testing.assert_close(plain(x), y)
+
+
+def test_covariance_units_share_input_accumulators(monkeypatch):
+    """dwain precompute: targets that read the SAME tensor (q/k/v, gate/up) share one input-side
+    accumulator, decided on the first forward and checked on every later one; a module called
+    twice per forward switches the split back to private accumulators. Host logic only: the
+    accumulator and the layer GEMM are stubbed with torch-CPU doubles."""
+    import ptdeco_b200.dwain.decomposition as D
+    from ptdeco_b200 import linalg
+
+    class FakeAcc:
+        def __init__(self, d, device, with_mean=False, defer_rows=0):
+            self.d, self.C, self.steps = d, torch.zeros(d, d, dtype=torch.float64), 0
+
+        def update(self, y, sub=None):
+            y = y.double()
+            self.C += y.T @ y / y.shape[0]
+            self.steps += 1
+
+    monkeypatch.setattr(linalg, "CovarianceAccumulator", FakeAcc)
+    monkeypatch.setattr(linalg, "linear_nt", lambda rows, w: rows @ w.T)
+
+    class Block(torch.nn.Module):
+        def __init__(self, twice=False):
+            super().__init__()
+            self.q, self.k, self.v = torch.nn.Linear(16, 16), torch.nn.Linear(16, 4), torch.nn.Linear(16, 4)
+            self.gate, self.up, self.down = torch.nn.Linear(16, 48), torch.nn.Linear(16, 48), torch.nn.Linear(48, 16)
+            self.twice = twice
+
+        def forward(self, x):
+            a = self.q(x) + torch.cat([self.k(x), self.v(x)] * 2, -1)
+            h = a * 0.5  # a NEW tensor: gate / up share it, q / k / v do not
+            out = self.down(torch.relu(self.gate(h)) * self.up(h))
+            return self.down(torch.relu(out).repeat(1, 3)) if self.twice else out
+
+    torch.manual_seed(0)
+    names = ["q", "k", "v", "gate", "up", "down"]
+    xs = [torch.randn(5, 16) for _ in range(3)]
+    net = Block().eval()
+    ref = [net(x) for x in xs]
+    originals = D._install_covariance_modules(net, names, True, reduction_factor=0.5)
+    units = net.q.units
+    with torch.no_grad():
+        for x, r in zip(xs, ref):
+            assert torch.allclose(net(x), r, atol=1e-6)  # the wrapped forward is still the layer forward
+    units.finish_probe()
+    kinds = [(u.kind, [n for n in names if getattr(net, n) in u.members]) for u in units.units]
+    assert kinds == [("input", ["q", "k", "v"]), ("input", ["gate", "up"]), ("output", ["down"])]
+    assert all(u.acc.steps == 3 for u in units.units)
+    s_ref = sum(x.double().T @ x.double() / 5 for x in xs)
+    assert torch.allclose(units.units[0].acc.C, s_ref)
+    assert net.k.acc is net.q.acc and net.up.acc is net.gate.acc and net.down.acc.d == 16
+    D._restore_modules(net, originals)
+    assert isinstance(net.q, torch.nn.Linear)
+
+    # weight sharing inside the model: `down` runs twice per forward -> no input sharing at all,
+    # and like the reference (D:204) every call counts as a step
+    net = Block(twice=True).eval()
+    D._install_covariance_modules(net, names, True, reduction_factor=0.5)
+    with torch.no_grad():
+        for x in xs:
+            net(x)
+    net.q.units.finish_probe()
+    assert all(len(u.members) == 1 for u in net.q.units.units) and len(net.q.units.units) == 6
+    assert net.down.acc.steps == 6 and net.q.acc.steps == 3
+
+    # PTDECO_B200_SHARE_INPUTS=0: the reference's one-accumulator-per-target layout
+    monkeypatch.setenv("PTDECO_B200_SHARE_INPUTS", "0")
+    net = Block().eval()
+    D._install_covariance_modules(net, names, True, reduction_factor=0.5)
+    with torch.no_grad():
+        for x in xs:
+            net(x)
+    net.q.units.finish_probe()
+    assert len(net.q.units.units) == 6 and net.k.acc is not net.q.acc

@@ -62,15 +62,44 @@ def main():
     out["min_cosine_sharded_vs_single"] = worst
     assert worst >= 0.9999, worst
 
+    # deterministic mode (PTDECO_FLAG_DETERMINISTIC on every kernel call): bit-identical results
+    # from run to run at a fixed world size; against another world size the partial sums are
+    # grouped differently (rank r folds steps r, r + world, ...), which is fp32 summation order
+    from ptdeco_b200 import _native as nat
+    nat.set_deterministic(True)
+    reruns = []
+    for _ in range(2):
+        m_, s_, _, _ = cases.dwain_case("llama_tiny")
+        m_.to(dev)
+        reruns.append(D._precompute_covariance_matrix_decompositions(
+            module=m_, submodule_names=names, num_data_steps=8, data_iterator=s_, device=dev,
+            decompose_in_float64=True, reduction_factor=0.5, group=group))
+    nat.set_deterministic(False)
+    out["deterministic_reruns_bit_identical"] = all(torch.equal(reruns[0][n], reruns[1][n]) for n in names)
+    assert out["deterministic_reruns_bit_identical"]
+
     gold = json.load(open(os.path.join(ROOT, "tests", "golden", "dwain_llama_tiny_splits.json")))
     model3, s3, m3, kw3 = cases.dwain_case("llama_tiny_splits")
     model3.to(dev)
     cfg = dwain.decompose_in_place(module=model3, device=dev, data_iterator=s3, metric_iterator=m3,
                                    loss_fn=cases.dwain_loss_fn("llama_tiny_splits"),
-                                   finetune_fn=lambda m, d, nn: m, **kw3)
+                                   finetune_fn=lambda m, d, nn: m,
+                                   process_group="world" if world > 1 else None, **kw3)
     ranks = {n: c["modules"]["0"]["out_features"] for n, c in cfg.items()}
     granks = {n: c["modules"]["0"]["out_features"] for n, c in gold["decompose_config"].items()}
     out["ranks_equal_golden"] = ranks == granks
+    # the bf16 golden case (the headline dtype) through the sharded path as well
+    gold16 = json.load(open(os.path.join(ROOT, "tests", "golden", "dwain_llama_tiny_bf16_splits.json")))
+    model4, s4, m4, kw4 = cases.dwain_case("llama_tiny_bf16_splits")
+    model4.to(dev)
+    cfg16 = dwain.decompose_in_place(module=model4, device=dev, data_iterator=s4, metric_iterator=m4,
+                                     loss_fn=cases.dwain_loss_fn("llama_tiny_bf16_splits"),
+                                     finetune_fn=lambda m, d, nn: m,
+                                     process_group="world" if world > 1 else None, **kw4)
+    r16 = {n: c["modules"]["0"]["out_features"] for n, c in cfg16.items()}
+    g16 = {n: c["modules"]["0"]["out_features"] for n, c in gold16["decompose_config"].items()}
+    out["bf16_ranks_equal_golden"] = r16 == g16
+    assert r16 == g16, (r16, g16)
     out["positions"] = [s3.position, m3.position, gold["stream_position"], gold["metric_stream_position"]]
     assert ranks == granks, (ranks, granks)
     if world > 1:

@@ -53,7 +53,8 @@ def main():
         loss_fn=models.llama_ce_loss, finetune_fn=lambda m, d, n: m, num_data_steps=args.data_steps,
         num_metric_steps=args.metric_steps, blacklisted_module_names=["lm_head"],
         nsr_final_threshold=args.nsr, min_rank=args.min_rank, decompose_in_float64=True,
-        precomputing_covariance_num_splits=args.splits, trace=trace)
+        precomputing_covariance_num_splits=args.splits, trace=trace,
+        process_group="world" if world > 1 else None)
     torch.cuda.synchronize()
     wall = time.time() - t0
     if rank == 0:
