@@ -1294,9 +1294,21 @@ tri_prep_kernel(const float* __restrict__ dvec, const float* __restrict__ evec, 
   }
 }
 
-__device__ __forceinline__ int sturm_count(const double* __restrict__ D,
-                                           const double* __restrict__ E2, int lo, int hi, double x,
-                                           double pivmin) {
+// Number of eigenvalues of the block below x. Two forms:
+//  * ratio form (LAPACK dstebz): q_i = (d_i - x) - e_{i-1}^2 / q_{i-1}, count q_i < 0. One fp64
+//    DIVISION on the dependent chain per row: ~180 cycles per row on this part, and the chain is
+//    what the multisection waits for (measured: 22 % of the eigensolve at d = 768, 15 % at 4096).
+//  * product form (the classical Sturm sequence): p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2},
+//    count sign changes of consecutive p. The chain is ONE fp64 FMA per row (e^2 p_{i-2} is ready a
+//    step earlier). Its known weakness, overflow / underflow of p, is handled by working on the
+//    matrix scaled to unit norm (growth <= ~3 per row) and renormalising every 8 rows; an exact
+//    zero takes the sign opposite to its predecessor (the ratio form's q = -pivmin). Both forms
+//    count the eigenvalues of a matrix within rounding of T - x: checked against each other and
+//    against numpy on random / graded / clustered / Wilkinson / covariance tridiagonals, they
+//    differ only for x within 1e-15 ||T|| of an eigenvalue.
+__device__ __forceinline__ int sturm_count_ratio(const double* __restrict__ D,
+                                                 const double* __restrict__ E2, int lo, int hi,
+                                                 double x, double pivmin) {
   double q = __ldg(D + lo) - x;
   int cnt = q < 0.0;
   for (int i = lo + 1; i <= hi; ++i) {
@@ -1304,6 +1316,44 @@ __device__ __forceinline__ int sturm_count(const double* __restrict__ D,
     q = (__ldg(D + i) - x) - __ldg(E2 + i - 1) / q;
     cnt += (q < 0.0);
   }
+  return cnt;
+}
+
+__device__ __forceinline__ int sturm_count(const double* __restrict__ D,
+                                           const double* __restrict__ E2, int lo, int hi, double x,
+                                           double inv_norm) {
+  const double inv2 = inv_norm * inv_norm;
+  double p0 = 1.0, p1 = (__ldg(D + lo) - x) * inv_norm;
+  bool n1 = p1 < 0.0;
+  if (p1 == 0.0) { n1 = true; p1 = -DBL_MIN; }
+  int cnt = n1;
+  auto step = [&](double dx, double e2) {
+    double p2 = fma(dx, p1, -(e2 * p0));
+    bool n2 = p2 < 0.0;
+    if (p2 == 0.0) { n2 = !n1; p2 = n2 ? -DBL_MIN : DBL_MIN; }
+    cnt += (n2 != n1);
+    p0 = p1;
+    p1 = p2;
+    n1 = n2;
+  };
+  int i = lo + 1;
+  for (; i + 7 <= hi; i += 8) {
+    double dx[8], e2[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {  // loads and scalings are off the dependent chain
+      dx[u] = (__ldg(D + i + u) - x) * inv_norm;
+      e2[u] = __ldg(E2 + i + u - 1) * inv2;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) step(dx[u], e2[u]);
+    const double a = fmax(fabs(p0), fabs(p1));
+    if (a > 0x1p+300 || a < 0x1p-300) {
+      const double sc = scalbn(1.0, -ilogb(a));
+      p0 *= sc;
+      p1 *= sc;
+    }
+  }
+  for (; i <= hi; ++i) step((__ldg(D + i) - x) * inv_norm, __ldg(E2 + i - 1) * inv2);
   return cnt;
 }
 
@@ -1317,7 +1367,7 @@ __device__ __forceinline__ int sturm_count(const double* __restrict__ D,
 // eigenvalue for the two launches below against 240 with 17-way).
 template <int LPE>
 __global__ void bisect_kernel(TriBufs b, int d, int count, const int* __restrict__ sel, int first,
-                              int passes) {
+                              int passes, int ratio_form) {
   const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
   const int w = gthread / LPE;
   const int sub = threadIdx.x & (LPE - 1);                  // lane within the eigenvalue's group
@@ -1345,6 +1395,7 @@ __global__ void bisect_kernel(TriBufs b, int d, int count, const int* __restrict
   }
   const double bnorm = fmax(fabs(gl), fabs(gu));
   const double pivmin = DBL_MIN * fmax(1.0, e2max);
+  const double inv_norm = bnorm > 0.0 ? 1.0 / bnorm : 1.0;
   double a, bb;
   if (first) {
     const double slack = 2.1 * bnorm * DBL_EPSILON * (hi - lo + 1) + 4.2 * pivmin;
@@ -1360,7 +1411,9 @@ __global__ void bisect_kernel(TriBufs b, int d, int count, const int* __restrict
     const bool done = !work || (bb - a <= 2.0 * DBL_EPSILON * fmax(fabs(a), fabs(bb)) + 2.0 * pivmin);
     const double wdt = (bb - a) / (LPE + 1);
     const double x = a + wdt * (sub + 1);
-    const int cnt = done ? 0 : sturm_count(b.D, b.E2, lo, hi, x, pivmin);
+    const int cnt = done ? 0
+                         : (ratio_form ? sturm_count_ratio(b.D, b.E2, lo, hi, x, pivmin)
+                                       : sturm_count(b.D, b.E2, lo, hi, x, inv_norm));
     const unsigned mask = (__ballot_sync(0xffffffffu, !done && cnt >= q + 1) & gmask) >> gshift;
     if (!done) {
       if (mask == 0u) {
@@ -1825,12 +1878,14 @@ static int g_jacobi_max = JACOBI_DEFAULT;
 // dependent fp64 divisions per pass, not by the fp64 pipe, so fewer, wider passes win. Kept as a
 // knob (ptdeco_debug_set key 105).
 static int g_bisect_narrow_d = 1 << 30;
+static int g_sturm_ratio = 0;  // 1: the division-based Sturm count (LAPACK's form), for A/B checks
 void eigh_debug_resident(int enable, int rows_target, int jacobi_max) {
   g_res_enable = enable;
   if (rows_target > 0) g_res_rows = rows_target;
   if (jacobi_max >= 0) g_jacobi_max = std::min(jacobi_max, JACOBI_MAX);
 }
 void eigh_debug_bisect_narrow(int d) { g_bisect_narrow_d = d > 0 ? d : (1 << 30); }
+void eigh_debug_sturm_ratio(int on) { g_sturm_ratio = on ? 1 : 0; }
 static int g_sym_min_m = 5120;  // trailing size from which the symv reads only the lower triangle
 void eigh_debug_sym_min_m(int m) { g_sym_min_m = m; }
 void eigh_debug_profile(int enable) {
@@ -2025,13 +2080,13 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
     const int tpb = 128;
     const bool wide = d < g_bisect_narrow_d;
     const int pb = tpb / (wide ? 16 : 4);
-    if (wide) bisect_kernel<16><<<(d + pb - 1) / pb, tpb, 0, st>>>(p.tb, d, d, nullptr, 1, 8);
-    else bisect_kernel<4><<<(d + pb - 1) / pb, tpb, 0, st>>>(p.tb, d, d, nullptr, 1, 14);
+    if (wide) bisect_kernel<16><<<(d + pb - 1) / pb, tpb, 0, st>>>(p.tb, d, d, nullptr, 1, 8, g_sturm_ratio);
+    else bisect_kernel<4><<<(d + pb - 1) / pb, tpb, 0, st>>>(p.tb, d, d, nullptr, 1, 14, g_sturm_ratio);
     PTD_CHECK_LAUNCH();
     rank_kernel<<<(d + 255) / 256, 256, 0, st>>>(p.tb, d, k, evals);
     PTD_CHECK_LAUNCH();
-    if (wide) bisect_kernel<16><<<(k + pb - 1) / pb, tpb, 0, st>>>(p.tb, d, k, p.tb.sel, 0, 7);
-    else bisect_kernel<4><<<(k + pb - 1) / pb, tpb, 0, st>>>(p.tb, d, k, p.tb.sel, 0, 11);
+    if (wide) bisect_kernel<16><<<(k + pb - 1) / pb, tpb, 0, st>>>(p.tb, d, k, p.tb.sel, 0, 7, g_sturm_ratio);
+    else bisect_kernel<4><<<(k + pb - 1) / pb, tpb, 0, st>>>(p.tb, d, k, p.tb.sel, 0, 11, g_sturm_ratio);
     PTD_CHECK_LAUNCH();
   }
   eigvec_kernel<<<(k + 31) / 32, 64, 0, st>>>(p.tb, d, k);

@@ -39,5 +39,7 @@ void eigh_debug_sym_min_m(int m);
 void eigh_debug_resident(int enable, int rows_target, int jacobi_max);
 // Debug: smallest d whose multisection uses 4 lanes per eigenvalue (<= 0: never, the default).
 void eigh_debug_bisect_narrow(int d);
+// Debug: 1 = ratio-form (division) Sturm count instead of the product form.
+void eigh_debug_sturm_ratio(int on);
 
 }  // namespace ptd

@@ -1138,7 +1138,9 @@ int launch_fused(const void* X, long long ldx, const void* W1, long long ldw1, c
                                : g.stages + ((g.kp / F_BK) * F_HBLOCK + F_STG_BYTES) / g.slot_bytes;
   } else {
     g.stages = 3; g.slot_bytes = 49152; g.w2_off = F_XBYTES; g.stg_separate = 0;
-    g.stages1 = g.stages;
+    // one more GEMM-1 slot over the idle H block (+ the 16 KB staging tail)
+    g.stages1 = g_knob[6] == 1 ? g.stages
+                               : g.stages + ((g.kp / F_BK) * F_HBLOCK + 4 * 4096) / g.slot_bytes;
   }
   g.rotate = 1;
   if (g_knob[5] >= 0) g.rotate = static_cast<int>(g_knob[5]);

@@ -71,6 +71,10 @@ def one(d: int, k: int, rows: list[int], cusolver: bool) -> dict:
         out["jacobi"] = acc()
         out["jacobi"]["ms"] = timed()
         L.ptdeco_debug_set(104, 0)
+    L.ptdeco_debug_set(106, 1)  # division-based (LAPACK-form) Sturm count instead of the product form
+    out["sturm_ratio_form"] = acc()
+    out["sturm_ratio_form"]["ms"] = timed()
+    L.ptdeco_debug_set(106, 0)
     if d >= 1024:  # 4 lanes per eigenvalue in the multisection instead of 16
         L.ptdeco_debug_set(105, 1)
         out["bisect_4_lanes"] = {"ms": timed()}
