@@ -304,14 +304,18 @@ class _DeviceStream:
         return item
 
 
-def extra_model_runs(dev, with_dwain8b: bool) -> dict:
-    """metric (i): decompose_in_place wall time per model through the public API."""
+def extra_model_runs(dev, with_dwain8b: bool, world: int = 1) -> dict:
+    """metric (i): decompose_in_place wall time per model through the public API. With world > 1
+    EVERY rank runs this (process_group="world": falor layers and dwain's calibration steps /
+    rank trials are sharded); times are the max over ranks."""
     import torch
 
     import ptdeco_b200.dwain as dwain
     import ptdeco_b200.falor as falor
+    from ptdeco_b200 import parallel
     from synth import cases, models, streams
     out = {}
+    pg = "world" if world > 1 else None
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     for name in ("deit_tiny", "convnext_tiny"):
@@ -320,14 +324,18 @@ def extra_model_runs(dev, with_dwain8b: bool) -> dict:
         dstream = _DeviceStream(stream.make, gold["stream_position"], dev)
         model.to(dev)
         trace = []
+        if world > 1:
+            torch.distributed.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        cfg = falor.decompose_in_place(module=model, device=dev, data_iterator=dstream, trace=trace, **kw)
+        cfg = falor.decompose_in_place(module=model, device=dev, data_iterator=dstream, trace=trace,
+                                       process_group=pg, **kw)
         torch.cuda.synchronize()
+        wall = parallel.max_over_ranks(time.perf_counter() - t0, dev)
         ranks = {n: c["modules"]["0"].get("out_features", c["modules"]["0"].get("out_channels")) for n, c in cfg.items()}
         granks = {n: c["modules"]["0"].get("out_features", c["modules"]["0"].get("out_channels"))
                   for n, c in gold["decompose_config"].items()}
-        out[f"falor_{name}"] = {"wall_s": time.perf_counter() - t0, "targets_decomposed": len(cfg),
+        out[f"falor_{name}"] = {"wall_s": wall, "n_gpus": world, "targets_decomposed": len(cfg),
                                 "rank_trials": len(trace), "batches": dstream.position,
                                 "ranks_equal_reference_golden": ranks == granks}
         del model, dstream
@@ -340,20 +348,24 @@ def extra_model_runs(dev, with_dwain8b: bool) -> dict:
         data = streams.IndexedStream(lambda i: streams.token_batch(2, i, 1, SEQ, 128256))
         metric = streams.IndexedStream(lambda i: streams.token_batch(3, i, 1, SEQ, 128256))
         trace = []
+        if world > 1:
+            torch.distributed.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         cfg = dwain.decompose_in_place(
             module=model, device=dev, data_iterator=data, metric_iterator=metric,
             loss_fn=models.llama_ce_loss, finetune_fn=lambda m, d, n: m, num_data_steps=8,
             num_metric_steps=1, blacklisted_module_names=["lm_head"], nsr_final_threshold=0.05,
-            min_rank=32, decompose_in_float64=True, precomputing_covariance_num_splits=1, trace=trace)
+            min_rank=32, decompose_in_float64=True, precomputing_covariance_num_splits=1, trace=trace,
+            process_group=pg)
         torch.cuda.synchronize()
+        wall = parallel.max_over_ranks(time.perf_counter() - t0, dev)
         hist: dict = {}
         for c in cfg.values():
             r = c["modules"]["0"]["out_features"]
             hist[r] = hist.get(r, 0) + 1
         out["dwain_llama3_8b_shape"] = {
-            "wall_s": time.perf_counter() - t0, "targets": 224, "targets_decomposed": len(cfg),
+            "wall_s": wall, "n_gpus": world, "targets": 224, "targets_decomposed": len(cfg),
             "rank_trials": len(trace), "num_data_steps": 8, "num_metric_steps": 1,
             "rank_histogram": hist, "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
         del model
@@ -433,7 +445,9 @@ def main() -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a rank that fails inside a sharded extra must not leave the others waiting for ever
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=420))
     nat.lib()
     n_layers = args.layers
     peaks, peak_src = load_peaks()
@@ -589,9 +603,9 @@ def main() -> None:
         torch.cuda.empty_cache()
 
     # ---------------- whole-model wall times (metric i) and the strong-scaling leg ----------------
-    if not args.no_extra and not args.no_model_runs and rank == 0 and world == 1:
+    if not args.no_extra and not args.no_model_runs:  # every rank: the runs are sharded over the group
         try:
-            extra["decompose_wall_time"] = extra_model_runs(dev, with_dwain8b=not args.no_dwain8b)
+            extra["decompose_wall_time"] = extra_model_runs(dev, with_dwain8b=not args.no_dwain8b, world=world)
         except Exception as exc:
             extra["decompose_wall_time_error"] = repr(exc)[:300]
         torch.cuda.empty_cache()

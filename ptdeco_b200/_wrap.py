@@ -36,6 +36,7 @@ class WrappedModule(torch.nn.Module):
         self.output: Optional[torch.Tensor] = None
         self.capture_output = False
         self.capture_only = False  # raise StopForward after capturing (calibration forwards)
+        self.calls = 0             # forward calls seen (a layer used twice per model forward: no early exit)
         # rank trial (see set_trial): rows go through the two-factor op W2 (W1 x) instead of a
         # materialised W2 W1 copied into the layer (F:347-348 / D:427-429 + set_weight)
         self.trial_factors: Optional[tuple[torch.Tensor, torch.Tensor]] = None
@@ -90,6 +91,7 @@ class WrappedModule(torch.nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         self.input = x
+        self.calls += 1
         if self.trial_factors is not None:
             b = self.trial_pair_batch
             if b == 0:
@@ -218,9 +220,15 @@ class WrappedConv2d1x1(WrappedModule):
 def calibration_forward(forward_fn, inputs: Any, wrapper: WrappedModule) -> None:
     """One calibration forward of the user model (F:189 / D:237), stopped right after the wrapped
     target produced its activation: the reference discards the model output of these calls, so the
-    rest of the network is dead work. PTDECO_B200_EARLY_EXIT=0 runs the whole forward."""
-    if os.environ.get("PTDECO_B200_EARLY_EXIT", "1") == "0":
+    rest of the network is dead work. The first calibration forward of a layer always runs in
+    full and counts the calls of the wrapper: a layer the model calls more than once per forward
+    keeps full forwards (the reference's `self.input = x` keeps the LAST call's activations,
+    F:63-65, which an exit at the first call would not see). PTDECO_B200_EARLY_EXIT=0 runs every
+    forward in full."""
+    if os.environ.get("PTDECO_B200_EARLY_EXIT", "1") == "0" or getattr(wrapper, "_calls_per_forward", None) != 1:
+        before = wrapper.calls
         forward_fn(inputs)
+        wrapper._calls_per_forward = wrapper.calls - before
         return
     wrapper.capture_only = True
     try:

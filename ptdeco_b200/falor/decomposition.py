@@ -26,7 +26,7 @@ from typing import Any, Optional
 import torch
 
 from .. import _native as nat
-from .. import _wrap, linalg, utils
+from .. import _wrap, linalg, parallel, utils
 
 EIGEN_DAMPEN_FACTOR = 0.01  # F:22
 
@@ -66,9 +66,18 @@ def decompose_in_place(
     use_mean: bool,
     use_damping: bool,
     trace: Optional[list] = None,
+    process_group: Any = None,
 ) -> dict[str, Any]:
     """F:424-511. Every target is analysed against the unmodified model; swaps happen afterwards.
-    Returns the decompose_config (insertion order = forward module order)."""
+    Returns the decompose_config (insertion order = forward module order).
+
+    `process_group` (not in the reference) opts into the multi-GPU path: falor's layers are
+    independent of each other (all are analysed against the ORIGINAL model, F:451-471), so with a
+    group (or "world") layer number l is analysed by rank l mod world and the others only draw --
+    and drop -- that layer's batches, whose count is data independent (`num_data_steps` plus
+    `num_metric_steps` per bisection step), so every rank's iterator stays at the reference's
+    position. The owners then broadcast their results and every rank installs identical modules.
+    Requires identical replicas and iterators on all ranks (checked by a batch checksum)."""
     start_time = time.perf_counter()
     device = torch.device(device)
     if device.type != "cuda":
@@ -83,10 +92,23 @@ def decompose_in_place(
     n = len(names)
     module.eval()
     pair_state = _wrap.PairState(module)
+    group = parallel.resolve_group(process_group)
+    my_rank, world = parallel.rank_and_world(group)
+    owners: dict[str, int] = {}
+    n_live = 0
     for i, name in enumerate(names, start=1):
         msg_prefix = f"Processing {name}: module {i} of {n}"
         if name in blacklisted_module_names:
             logger.info(f"{msg_prefix}, skipped as blacklisted")
+            continue
+        owners[name] = n_live % world
+        n_live += 1
+        if owners[name] != my_rank:
+            # another rank analyses this layer: consume exactly the batches it consumes
+            skipped = _batches_consumed_by_layer(module.get_submodule(name), num_data_steps, num_metric_steps)
+            for _ in range(skipped):
+                next(data_iterator)
+            logger.info(f"{msg_prefix}, analysed by rank {owners[name]} ({skipped} batches skipped)")
             continue
         logger.info(msg_prefix)
         with torch.no_grad():
@@ -96,6 +118,9 @@ def decompose_in_place(
                 num_data_steps=num_data_steps, num_metric_steps=num_metric_steps, device=device,
                 use_float64=use_float64, use_mean=use_mean, use_damping=use_damping, trace=trace,
                 pair_state=pair_state)
+
+    if group is not None:
+        _exchange_layer_results(module, owners, results_all, my_rank, group, device, trace)
 
     counter: collections.Counter[str] = collections.Counter()
     for name in names:
@@ -235,6 +260,69 @@ def _process_module(
     _unwrap_in_place(root_module, decomposed_submodule_name)
     return {"proportion": proportion, "nsr_final": nsr_new, "kl_final": kl_new,
             "decomposed_module": new_module}
+
+
+def _batches_consumed_by_layer(target: torch.nn.Module, num_data_steps: int, num_metric_steps: int) -> int:
+    """How many batches _process_module draws for this layer: data independent (F:188, F:340-375):
+    num_data_steps for the covariance plus num_metric_steps per bisection step, and the number of
+    steps depends only on full_rank (the width halves until it is 0); a rank-1 layer draws none."""
+    w = target.weight
+    full_rank = min(w.shape[0], w.shape[1])
+    if full_rank == 1:
+        return 0
+    steps, width = 0, full_rank // 2
+    while width > 0:
+        steps += 1
+        width //= 2
+    return num_data_steps + steps * num_metric_steps
+
+
+def _exchange_layer_results(module: torch.nn.Module, owners: dict[str, int], results_all: dict,
+                            my_rank: int, group, device: torch.device, trace: Optional[list]) -> None:
+    """Layer-sharded falor: every owner broadcasts its layer's outcome (scalars + the two factor
+    matrices) so that all ranks build identical replacement modules; traces are merged in layer
+    order on every rank."""
+    import torch.distributed as dist
+    per_layer_trace: dict[str, list] = {}
+    if trace is not None:
+        for t in trace:
+            per_layer_trace.setdefault(t["name"], []).append(t)
+        trace.clear()
+    for name, owner in owners.items():
+        src = dist.get_global_rank(group, owner)
+        payload = [None]
+        if owner == my_rank:
+            r = results_all[name]
+            new = r["decomposed_module"]
+            payload[0] = {"proportion": r["proportion"], "nsr_final": r["nsr_final"], "kl_final": r["kl_final"],
+                          "rank": None if new is None else int(new[0].weight.shape[0]),
+                          "dtype": None if new is None else str(new[0].weight.dtype).replace("torch.", ""),
+                          "trace": per_layer_trace.get(name, [])}
+        dist.broadcast_object_list(payload, src=src, group=group)
+        meta = payload[0]
+        if trace is not None:
+            trace.extend(meta["trace"])
+        if owner == my_rank:
+            new = results_all[name]["decomposed_module"]
+        else:
+            new = None
+            if meta["rank"] is not None:
+                _wrap_in_place(module, name)
+                wrapper = module.get_submodule(name)
+                w = wrapper.get_weight_copy()
+                dt = getattr(torch, meta["dtype"])
+                new = wrapper.get_decomposed_module(
+                    u=torch.empty((meta["rank"], w.shape[1]), dtype=dt, device=w.device),
+                    v=torch.empty((w.shape[0], meta["rank"]), dtype=dt, device=w.device))
+                _unwrap_in_place(module, name)
+            results_all[name] = {"proportion": meta["proportion"], "nsr_final": meta["nsr_final"],
+                                 "kl_final": meta["kl_final"], "decomposed_module": new}
+        if new is not None:
+            for prm in (new[0].weight, new[1].weight):
+                buf = prm.data.contiguous()
+                dist.broadcast(buf, src=src, group=group)
+                if owner != my_rank:
+                    prm.data = buf
 
 
 def _compute_metrics(

@@ -805,6 +805,43 @@ def test_falor_decompose_in_place_matches_reference(dev, golden_dir, name):
         torch.testing.assert_close(fresh(xb), model(xb))
 
 
+def test_falor_on_a_bf16_model_keeps_the_model_dtype(dev):
+    """falor's replacement modules follow the layer's dtype (the reference leaves fp32
+    factors in place, F:387, which breaks the next forward of a bf16 model); the decomposed bf16
+    model runs, its config round-trips, and its logits stay close to the original's."""
+    import ptdeco_b200.falor as falor
+    from ptdeco_b200 import utils
+    model, stream, kw = cases.falor_case("mlp")
+    model = model.to(torch.bfloat16).to(dev)
+    ref_model, _, _ = cases.falor_case("mlp")
+    ref_model = ref_model.to(torch.bfloat16).to(dev)
+
+    class Cast:
+        def __init__(self, it):
+            self.it = it
+
+        def __iter__(self):
+            return self
+
+        def __next__(self):
+            return next(self.it).to(torch.bfloat16)
+
+    kw = dict(kw, nsr_final_threshold=0.08, kl_final_threshold=0.05)
+    cfg = falor.decompose_in_place(module=model, device=dev, data_iterator=Cast(stream), **kw)
+    assert len(cfg) >= 1
+    for name in cfg:
+        sub = model.get_submodule(name)
+        assert all(p.dtype == torch.bfloat16 for p in sub.parameters())
+    x = next(Cast(stream)).to(dev)
+    with torch.no_grad():
+        y, y_ref = model(x).float(), ref_model(x).float()
+    assert y.dtype == torch.float32 and torch.isfinite(y).all()
+    assert float((y - y_ref).norm() / y_ref.norm()) < 0.5
+    fresh, _, _ = cases.falor_case("mlp")
+    utils.apply_decompose_config_in_place(fresh, json.loads(json.dumps(cfg)))
+    fresh.to(torch.bfloat16).load_state_dict(model.state_dict(), strict=True)
+
+
 def test_falor_edge_cases_match_oracle(dev):
     """Rank-1 target, grouped / 3x3 convs, blacklist (incl. a name that does not exist), a layer
     that cannot reduce parameters, the proportion_threshold gate: product (GPU) vs oracle (CPU)."""

@@ -402,12 +402,33 @@ def test_calibration_forward_stops_after_the_target():
         full = net(x)
         assert len(calls) == 1
         want_in, want_out = wrapper.get_last_input().clone(), wrapper.get_last_output_rows().clone()
+        _wrap.calibration_forward(net, x + 1, wrapper)  # first one: in full, counts the wrapper's calls
+        assert len(calls) == 2 and wrapper._calls_per_forward == 1
         _wrap.calibration_forward(net, x + 1, wrapper)
         _wrap.calibration_forward(net, x, wrapper)
-    assert len(calls) == 1 and not wrapper.capture_only  # the tail never ran again
+    assert len(calls) == 2 and not wrapper.capture_only  # the tail never ran again
     assert torch.equal(wrapper.get_last_input(), want_in) and torch.equal(wrapper.get_last_output_rows(), want_out)
     with torch.no_grad():
         assert torch.equal(net(x), full)  # and the model is untouched
+
+    class Twice(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(4, 4)
+
+        def forward(self, t):
+            return self.lin(self.lin(t) + 1)
+
+    tw = Twice().eval()
+    D._wrap_in_place(tw, "lin")
+    wr = tw.get_submodule("lin")
+    with torch.no_grad():
+        _wrap.calibration_forward(tw, x, wr)
+        _wrap.calibration_forward(tw, x, wr)
+        last_in = wr.get_last_input().clone()
+    assert wr._calls_per_forward == 2  # called twice per forward: no early exit,
+    with torch.no_grad():
+        assert torch.equal(last_in, tw.lin.get_orig_module()(x) + 1)  # the LAST call's input like F:63-65
 
 
 def test_strided_conv_wrapper_uses_input_positions():

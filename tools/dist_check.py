@@ -102,6 +102,34 @@ def main():
     assert r16 == g16, (r16, g16)
     out["positions"] = [s3.position, m3.position, gold["stream_position"], gold["metric_stream_position"]]
     assert ranks == granks, (ranks, granks)
+    # falor: layers are independent -> layer l is analysed by rank l mod world, the others skip its
+    # batches; every rank must end with the golden config, the golden iterator position, and
+    # bit-identical replacement modules
+    import time
+
+    import ptdeco_b200.falor as falor
+    for fname in ("convmlp", "deit_small"):
+        goldf = json.load(open(os.path.join(ROOT, "tests", "golden", f"falor_{fname}.json")))
+        fm, fs, fkw = cases.falor_case(fname)
+        fm.to(dev)
+        ftrace = []
+        t0 = time.perf_counter()
+        fcfg = falor.decompose_in_place(module=fm, device=dev, data_iterator=fs, trace=ftrace,
+                                        process_group="world" if world > 1 else None, **fkw)
+        torch.cuda.synchronize()
+        out[f"falor_{fname}_s"] = time.perf_counter() - t0
+        fr = {n: c["modules"]["0"].get("out_features", c["modules"]["0"].get("out_channels")) for n, c in fcfg.items()}
+        gr = {n: c["modules"]["0"].get("out_features", c["modules"]["0"].get("out_channels"))
+              for n, c in goldf["decompose_config"].items()}
+        assert fr == gr, (fr, gr)
+        assert fs.position == goldf["stream_position"], (fs.position, goldf["stream_position"])
+        assert [(t["name"], t["rank"]) for t in ftrace] == [(t["name"], t["rank"]) for t in goldf["trace"]]
+        if world > 1:
+            for k_, v_ in fm.state_dict().items():
+                ref = v_.clone()
+                dist.broadcast(ref, src=0)
+                assert torch.equal(ref, v_), f"rank {rank}: {k_} differs from rank 0"
+        out[f"falor_{fname}_ranks_equal_golden"] = True
     if world > 1:
         dist.barrier()
     if rank == 0:
