@@ -444,7 +444,8 @@ def _precompute_covariance_matrix_decompositions(
             total = sum(a * b for a, b in sizes)
             jobs.append((u.acc, (lambda u=u: torch.cat(
                 [m.get_eigenvectors(ks[id(m)]).reshape(-1) for m in u.members])), (total,)))
-        flats = parallel.owners_compute_pipelined(jobs, group, total_steps=num_data_steps)
+        flats = parallel.owners_compute_pipelined(jobs, group, total_steps=num_data_steps,
+                                                  costs=[_unit_cost(u, ks) for u in units.units])
         by_module = {}
         for u, flat in zip(units.units, flats):
             off = 0
@@ -457,6 +458,20 @@ def _precompute_covariance_matrix_decompositions(
     _restore_modules(module, originals)
     utils.relieve_gpu_memory_pressure()
     return u_dict
+
+
+def _unit_cost(unit, ks: dict) -> float:
+    """Relative eigensolve cost of one accumulator (d^3 per eigensolve) for balancing its owners."""
+    if unit.kind == "output":
+        return float(unit.members[0].out_features) ** 3
+    cost, shared_eig = 0.0, False
+    for m in unit.members:
+        if linalg.use_input_side(m.in_features, m.out_features, ks[id(m)]):
+            cost += float(m.in_features) ** 3  # eigh of the in x in Gram matrix (+ its GEMMs)
+            shared_eig = True
+        else:
+            cost += float(m.out_features) ** 3 + 0.1 * float(m.in_features) ** 3  # C = W S W^T, eigh(C)
+    return cost + (float(unit.members[0].in_features) ** 3 if shared_eig else 0.0)
 
 
 def _install_covariance_modules(module: torch.nn.Module, submodule_names: list[str],

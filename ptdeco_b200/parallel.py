@@ -143,10 +143,27 @@ def owner_computes(layer_index: int, group, compute: Callable[[], torch.Tensor],
     return out
 
 
+def balanced_owners(costs: list[float], world: int) -> list[int]:
+    """Owner of every job by greedy longest-processing-time assignment (deterministic: every rank
+    computes the same table). Plain round-robin hands whole CLASSES of jobs to the same ranks when
+    the job list is periodic -- a decoder's accumulators come as (q/k/v, o, gate/up, down) per layer,
+    so with 2 or 8 ranks the gate/up units (three eigensolves each) all landed on the same ranks."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    load = [0.0] * world
+    owners = [0] * len(costs)
+    for i in order:
+        r = min(range(world), key=lambda q: (load[q], q))
+        owners[i] = r
+        load[r] += costs[i]
+    return owners
+
+
 def owners_compute_pipelined(jobs: list, group, total_steps: Optional[int] = None,
-                             dtype: torch.dtype = torch.float32) -> list[torch.Tensor]:
-    """All accumulators of a calibration split at once: jobs[i] = (acc, compute, shape), owner of
-    job i = i mod world. Three phases, each without a host synchronisation:
+                             dtype: torch.dtype = torch.float32,
+                             costs: Optional[list[float]] = None) -> list[torch.Tensor]:
+    """All accumulators of a calibration split at once: jobs[i] = (acc, compute, shape); owners
+    are balanced by `costs` (relative eigensolve cost per job; round-robin without). Three phases,
+    each without a host synchronisation:
       1. every reduction (lower-triangle bands) is enqueued up front; NCCL runs them back to back;
       2. every rank runs the eigensolves of ITS jobs back to back;
       3. the [d, k] results are broadcast in job order.
@@ -159,20 +176,22 @@ def owners_compute_pipelined(jobs: list, group, total_steps: Optional[int] = Non
     if group is None:
         return [compute() for _, compute, _ in jobs]
     rank, world = rank_and_world(group)
-    pending = [start_reduce_lower(acc, owner_of(i, world), group, total_steps)
+    owners = (balanced_owners(costs, world) if costs is not None
+              else [owner_of(i, world) for i in range(len(jobs))])
+    pending = [start_reduce_lower(acc, owners[i], group, total_steps)
                for i, (acc, _, _) in enumerate(jobs)]
     for i, (acc, _, _) in enumerate(jobs):
         finish_reduce_lower(acc, pending[i])
     pending.clear()
     outs: list = [None] * len(jobs)
     for i, (acc, compute, shape) in enumerate(jobs):
-        if rank == owner_of(i, world):
+        if rank == owners[i]:
             out = compute().contiguous()
             assert tuple(out.shape) == tuple(shape), (out.shape, shape)
             outs[i] = out
     works = []
     for i, (acc, _, shape) in enumerate(jobs):
-        owner = owner_of(i, world)
+        owner = owners[i]
         if outs[i] is None:
             outs[i] = torch.empty(shape, dtype=dtype, device=acc.C.device)
         works.append(dist.broadcast(outs[i], src=dist.get_global_rank(group, owner), group=group,

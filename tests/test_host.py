@@ -162,6 +162,12 @@ def test_modconfig_roundtrip_and_schema():
 
 def test_shard_plan():
     from ptdeco_b200 import parallel
+    # periodic job lists: round-robin would give one rank every heavy job; LPT balances them
+    costs = [3.0, 1.0, 9.0, 1.0] * 8
+    owners = parallel.balanced_owners(costs, 2)
+    loads = [sum(c for c, o in zip(costs, owners) if o == r) for r in range(2)]
+    assert max(loads) - min(loads) <= 1.0 and sorted(set(owners)) == [0, 1]
+    assert parallel.balanced_owners(costs, 2) == owners  # deterministic
     assert parallel.steps_of_rank(10, 1, 4) == [1, 5, 9]
     assert sorted(sum((parallel.steps_of_rank(7, r, 3) for r in range(3)), [])) == list(range(7))
     assert [parallel.owner_of(i, 8) for i in (0, 7, 8, 225)] == [0, 7, 0, 1]
