@@ -16,10 +16,11 @@ import torch
 from . import linalg
 
 
-class StopForward(Exception):
+class StopForward(BaseException):
     """Raised by a wrapper in capture-only mode once it has seen its input (and produced its
     output): the calibration forward of F:189 / D:237 discards the model output, so the layers
-    AFTER the target need not run. Caught by `calibration_forward`."""
+    AFTER the target need not run. Caught by `calibration_forward`. A BaseException so that a broad
+    `except Exception` inside a user model does not swallow it."""
 
 
 class PairLayoutError(RuntimeError):
