@@ -273,13 +273,16 @@ class PairState:
     Whether pairing is attempted at all is a fixed policy, never a timing measurement:
     PTDECO_B200_PAIRED_TRIALS=1 / 0 forces it on / off; the default ("auto") pairs models of at
     most 100 M parameters (launch-bound forwards) and leaves larger ones -- whose forward already
-    fills the GPU: an 8B decoder at 2048 tokens measured slower paired -- on two forwards."""
+    fills the GPU: an 8B decoder at 2048 tokens measured slower paired -- on two forwards.
+    The deterministic mode (_native.set_deterministic) never pairs: a layer's verification batch is
+    evaluated unpaired and the rest paired, and which batch that is depends on how the trial jobs
+    are dealt over GPUs."""
 
     AUTO_MAX_PARAMS = 100_000_000
 
     def __init__(self, root_module: Optional[torch.nn.Module] = None) -> None:
         env = os.environ.get("PTDECO_B200_PAIRED_TRIALS", "auto")
-        if env == "0":
+        if env == "0" or (linalg.nat.call_flags() & linalg.nat.FLAG_DETERMINISTIC):
             self.enabled = False
         elif env == "1":
             self.enabled = True

@@ -239,28 +239,30 @@ def _process_module(
     # round-robin to the ranks; every rank draws every metric batch, keeping iterator positions
     # those of the reference, and the per-trial sums meet in one all-reduce.
     my_rank, world = parallel.rank_and_world(group)
-    results = torch.zeros((max(1, len(plan)), 3), dtype=torch.float64, device=orig_device)
+    # one slot per (trial, batch): the all-reduce only adds zeros to each value and the batch sum
+    # is taken in the same order on any number of GPUs, so the measured metrics -- and the ranks
+    # chosen from them -- do not depend on how the jobs were dealt
+    slots = torch.zeros((max(1, len(plan)), num_metric_steps, 3), dtype=torch.float64, device=orig_device)
     job = 0
     for t, (rank_t, _, _, _) in enumerate(plan):
         batches = [next(metric_iterator) for _ in range(num_metric_steps)]
-        mine = [b for j, b in enumerate(batches, start=job) if j % world == my_rank]
+        mine = [(j - job, b) for j, b in enumerate(batches, start=job) if j % world == my_rank]
         job += num_metric_steps
         if not mine:
             continue
         # no K5 GEMM (D:429) and no weight copy: the wrapper runs the two-factor op for the trial
         uk, w1 = factors(rank_t)
-        acc = torch.zeros(3, dtype=torch.float64, device=orig_device)
-        for batch in mine:
+        for b_idx, batch in mine:
             input_dict = utils.to_device(batch, device)
             nsr_sample, ppl_deco_sample, ppl_orig_sample = _compute_metrics(
                 input_dict=input_dict, root_module=root_module, decomposed_submodule=wrapper,
                 factors=(w1, uk), loss_fn=loss_fn, pair_state=pair_state)
             ppl_diff_sample = (ppl_deco_sample - ppl_orig_sample) / ppl_orig_sample
-            acc += torch.stack([ppl_diff_sample.double(), nsr_sample.double(),
-                                ppl_deco_sample.double()])
-        results[t] = acc / num_metric_steps
+            slots[t, b_idx] = torch.stack([ppl_diff_sample.double(), nsr_sample.double(),
+                                           ppl_deco_sample.double()])
     if group is not None and len(plan) > 0:
-        torch.distributed.all_reduce(results, group=group)  # every (trial, batch) lives on one rank
+        torch.distributed.all_reduce(slots, group=group)  # every (trial, batch) lives on one rank
+    results = slots.sum(dim=1) / num_metric_steps
     measured = results.tolist() if len(plan) > 0 else []  # the one host sync of the layer
 
     # ---- ... then apply the accept / reject rules in order (D:445-487)
@@ -407,12 +409,14 @@ def _precompute_covariance_matrix_decompositions(
     those of the reference -- the partial covariances are summed over NVLink (lower triangles,
     asynchronously) and the eigensolves are distributed round-robin over the accumulators, each
     owner broadcasting its top-k blocks while the other ranks are still solving theirs."""
-    originals = _install_covariance_modules(module, submodule_names, decompose_in_float64,
-                                            reduction_factor, share_inputs=True)
+    rank, world = parallel.rank_and_world(group)
+    # deterministic mode: canonical shards make the covariance bits independent of the GPU count
+    originals = _install_covariance_modules(
+        module, submodule_names, decompose_in_float64, reduction_factor, share_inputs=True,
+        shard_plan=(linalg.canonical_shards(world), rank, world))
     units = module.get_submodule(submodule_names[0]).units if submodule_names else None
 
     module.eval()
-    rank, world = parallel.rank_and_world(group)
     first_batch = None
     ran = 0
     with torch.no_grad():
@@ -423,6 +427,8 @@ def _precompute_covariance_matrix_decompositions(
                 parallel.check_identical_batches(batch, group)
             if step % world != rank:
                 continue
+            if units is not None:
+                units.step = step
             _ = module(utils.to_device(batch, device))
             ran += 1
         if units is not None:
@@ -477,12 +483,13 @@ def _unit_cost(unit, ks: dict) -> float:
 def _install_covariance_modules(module: torch.nn.Module, submodule_names: list[str],
                                 decompose_in_float64: bool,
                                 reduction_factor: Optional[float] = None,
-                                share_inputs: bool = True) -> dict[str, torch.nn.Module]:
+                                share_inputs: bool = True,
+                                shard_plan: tuple[int, int, int] = (1, 0, 1)) -> dict[str, torch.nn.Module]:
     """D:592-603: swap every listed Linear for a CovarianceComputingLinearModule that shares its
     weight and bias. Returns the originals for _restore_modules. With `share_inputs` the modules
     of this call form one CovarianceUnits registry (reachable as `<module>.units`)."""
     originals: dict[str, torch.nn.Module] = {}
-    units = CovarianceUnits() if share_inputs else None
+    units = CovarianceUnits(shard_plan) if share_inputs else None
     for name in submodule_names:
         old = module.get_submodule(name)
         if not isinstance(old, torch.nn.Linear):
@@ -544,7 +551,10 @@ class CovarianceUnits:
     loudly if the model's dataflow changed. A module called twice within one forward (weight
     sharing) switches the whole split back to private accumulators."""
 
-    def __init__(self) -> None:
+    def __init__(self, shard_plan: tuple[int, int, int] = (1, 0, 1)) -> None:
+        self.shard_plan = shard_plan  # (canonical shards, rank, world) of the accumulators
+        self.step: Optional[int] = None        # calibration step of the running forward (driver-set)
+        self.probe_step: Optional[int] = None  # ... of the probe forward
         self.probing = True
         self.dry = False            # probe for the layout only, fold nothing in
         self.records: list = []     # (module, x, rows, y_rows) of the probe forward, in call order
@@ -563,6 +573,8 @@ class CovarianceUnits:
             elif seen:
                 self.multi_call = True  # weight sharing inside the model: no input sharing
             if self.probing:
+                if not self.records:
+                    self.probe_step = self.step
                 self.records.append((mod, x, rows, y_rows))
                 return
         if mod is self.first_module:
@@ -572,11 +584,11 @@ class CovarianceUnits:
             unit = mod.unit = self._private_unit(mod)
             self.units.append(unit)
         if unit.kind == "output":
-            _update_Eyyt_in_place(unit.acc, y_rows)
+            _update_Eyyt_in_place(unit.acc, y_rows, step=self.step)
         elif len(unit.members) == 1:
-            _update_Eyyt_in_place(unit.acc, rows)
+            _update_Eyyt_in_place(unit.acc, rows, step=self.step)
         elif unit.last_call != self.calls:
-            _update_Eyyt_in_place(unit.acc, rows)
+            _update_Eyyt_in_place(unit.acc, rows, step=self.step)
             unit.last_call, unit.last_x = self.calls, x
         elif x is not unit.last_x:
             raise RuntimeError(
@@ -584,12 +596,15 @@ class CovarianceUnits:
                 f"received different tensors later ({len(unit.members)} members); "
                 "set PTDECO_B200_SHARE_INPUTS=0")
 
-    @staticmethod
-    def _private_unit(mod) -> CovarianceUnit:
+    def _accumulator(self, d: int, like: torch.Tensor) -> linalg.CovarianceAccumulator:
+        shards, rank, world = self.shard_plan
+        return linalg.CovarianceAccumulator(
+            d, like.device, defer_rows=linalg.default_defer_rows(d, like.element_size()),
+            shards=shards, rank=rank, world=world)
+
+    def _private_unit(self, mod) -> CovarianceUnit:
         kind, d = ("input", mod.in_features) if mod.input_side else ("output", mod.out_features)
-        acc = linalg.CovarianceAccumulator(
-            d, mod.weight.device, defer_rows=linalg.default_defer_rows(d, mod.weight.element_size()))
-        return CovarianceUnit(kind, acc, [mod])
+        return CovarianceUnit(kind, self._accumulator(d, mod.weight), [mod])
 
     def finish_probe(self) -> None:
         """Turn the probe forward's records into units and fold the probe batch in."""
@@ -606,14 +621,12 @@ class CovarianceUnits:
             shared = (share and len(recs) >= 2 and all(m.in_features == in_f for m in mods)
                       and in_f <= 2 * max(m.out_features for m in mods))
             if shared:  # one S = E[x x^T] for every module that read this tensor
-                acc = linalg.CovarianceAccumulator(
-                    in_f, mods[0].weight.device,
-                    defer_rows=linalg.default_defer_rows(in_f, mods[0].weight.element_size()))
+                acc = self._accumulator(in_f, mods[0].weight)
                 unit = CovarianceUnit("input", acc, mods)
                 for m in mods:
                     m.unit = unit
                 if not self.dry:
-                    _update_Eyyt_in_place(acc, recs[0][2])
+                    _update_Eyyt_in_place(acc, recs[0][2], step=self.probe_step)
                 self.units.append(unit)
                 continue
             for rec in recs:  # private accumulators (one record per call of the module)
@@ -622,7 +635,8 @@ class CovarianceUnits:
                     m.unit = self._private_unit(m)
                     self.units.append(m.unit)
                 if not self.dry:
-                    _update_Eyyt_in_place(m.unit.acc, rec[3] if m.unit.kind == "output" else rec[2])
+                    _update_Eyyt_in_place(m.unit.acc, rec[3] if m.unit.kind == "output" else rec[2],
+                                          step=self.probe_step)
         self.records = []
         self.calls = 1
 
@@ -760,9 +774,9 @@ def _get_eigenvectors(acc: linalg.CovarianceAccumulator, num_vectors: Optional[i
 
 
 def _update_Eyyt_in_place(acc: linalg.CovarianceAccumulator, y_reshaped: torch.Tensor,
-                          sub: Optional[torch.Tensor] = None) -> None:
+                          sub: Optional[torch.Tensor] = None, step: Optional[int] = None) -> None:
     """D:147-152: Eyyt += y^T y / N for one batch of rows."""
-    acc.update(y_reshaped, sub=sub)
+    acc.update(y_reshaped, sub=sub, step=step)
 
 
 def _max_rank_consumed(dim_in: int, dim_out: int, reduction_factor: float) -> int:

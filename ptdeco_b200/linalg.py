@@ -51,9 +51,17 @@ class CovarianceAccumulator:
     `defer_rows > 0` batches of equal N are first copied into a staging buffer and folded in with
     ONE call once `defer_rows` rows are pending (sum_steps y^T y / N is a SYRK over the
     concatenated rows); `flush()` / `finalize()` drain it. Results are identical up to fp32
-    summation order."""
+    summation order.
 
-    def __init__(self, d: int, device: torch.device, with_mean: bool = False, defer_rows: int = 0):
+    Canonical shards (`shards = V > 1`, the multi-GPU reproducibility mode): calibration step i is
+    folded into partial matrix C_(i mod V), one SYRK launch per step, and the covariance is
+    ((C_0 + C_1) + ...) + C_(V-1). Which GPU ran step i no longer enters the arithmetic: a rank of
+    a `world`-GPU run (world divides V) holds the shards v = rank (mod world) and the owner adds
+    all V in index order (parallel.gather_shards_to), so 1, 2, 4 and 8 GPUs produce the same
+    bits. Costs V accumulators of memory and the deferral."""
+
+    def __init__(self, d: int, device: torch.device, with_mean: bool = False, defer_rows: int = 0,
+                 shards: int = 1, rank: int = 0, world: int = 1):
         self.d = int(d)
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -66,8 +74,20 @@ class CovarianceAccumulator:
         self._pending_rows = 0
         self._pending_n = 0
         self.launches = 0
+        self.shards = int(shards)
+        self.shard_rank, self.shard_world = int(rank), int(world)
+        self.shard_C: list[Optional[torch.Tensor]] = [None] * self.shards
+        self._collapsed = self.shards <= 1
+        if self.shards > 1:
+            if with_mean:
+                raise ValueError("canonical shards do not track the mean (dwain precompute only)")
+            if self.shards % self.shard_world or not 0 <= self.shard_rank < self.shard_world:
+                raise ValueError(f"{world=} must divide the {shards} canonical shards")
+            self.defer_rows = 0
 
-    def _syrk(self, y: torch.Tensor, sub: Optional[torch.Tensor], alpha: float) -> None:
+    def _syrk(self, y: torch.Tensor, sub: Optional[torch.Tensor], alpha: float,
+              C: Optional[torch.Tensor] = None) -> None:
+        C = self.C if C is None else C
         L = nat.lib()
         n = y.shape[0]
         need = 0 if (sub is None and _tma_ready(y)) else L.ptdeco_syrk_workspace_bytes(
@@ -76,14 +96,17 @@ class CovarianceAccumulator:
             ws = nat.WORKSPACE.get(y.device, need)
             nat.check(
                 L.ptdeco_syrk_accumulate_ex(y.data_ptr(), nat.dtype_code(y), n, self.d, y.stride(0),
-                                            nat.ptr(sub), self.C.data_ptr(), self.C.stride(0),
+                                            nat.ptr(sub), C.data_ptr(), C.stride(0),
                                             nat.ptr(self.colsum), alpha, ws.data_ptr(), ws.numel(),
                                             nat.stream_ptr(y.device), nat.call_flags()),
                 "ptdeco_syrk_accumulate")
         self.launches += 1
 
-    def update(self, y: torch.Tensor, sub: Optional[torch.Tensor] = None) -> None:
-        """C += (y - sub)^T (y - sub) / N ; colsum += mean_rows(y - sub). y: [N, d] fp32 or bf16."""
+    def update(self, y: torch.Tensor, sub: Optional[torch.Tensor] = None,
+               step: Optional[int] = None) -> None:
+        """C += (y - sub)^T (y - sub) / N ; colsum += mean_rows(y - sub). y: [N, d] fp32 or bf16.
+        `step` (canonical shards only): the calibration step this batch belongs to; by default
+        this rank's j-th update is taken to be step rank + j * world."""
         y = _check_2d(y, "y")
         if y.shape[1] != self.d:
             raise ValueError(f"y has {y.shape[1]} features, accumulator has {self.d}")
@@ -94,6 +117,16 @@ class CovarianceAccumulator:
             raise ValueError("empty activation batch")
         if sub is not None:
             sub = sub.detach().to(device=y.device, dtype=torch.float32).contiguous()
+        if self.shards > 1:
+            if step is None:
+                step = self.shard_rank + self.steps * self.shard_world
+            v = step % self.shards
+            if self.shard_C[v] is None:
+                self.shard_C[v] = torch.zeros_like(self.C)
+            self.steps += 1
+            self._collapsed = False
+            self._syrk(y, sub, 1.0 / n, C=self.shard_C[v])
+            return
         self.steps += 1
         if self.defer_rows <= n or sub is not None:
             self.flush()
@@ -119,6 +152,19 @@ class CovarianceAccumulator:
         self.flush()
         self._stage = None
 
+    def collapse_shards(self) -> None:
+        """C = ((C_0 + C_1) + ...) over the shards held HERE, in index order, then drop them. The
+        whole sum when one GPU holds every shard; parallel.gather_shards_to does the same walk with
+        the remote shards spliced in at their index."""
+        if self._collapsed:
+            return
+        self.C.zero_()
+        for v in range(self.shards):
+            if self.shard_C[v] is not None:
+                self.C += self.shard_C[v]
+                self.shard_C[v] = None
+        self._collapsed = True
+
     def finalize(self, use_mean: bool, damp_factor: float) -> torch.Tensor:
         """In place: /steps, optional centring, mirror to the upper triangle, damping. Returns C."""
         if self.steps == 0:
@@ -126,6 +172,7 @@ class CovarianceAccumulator:
         if use_mean and self.colsum is None:
             raise ValueError("accumulator was created without mean tracking")
         self.release_staging()
+        self.collapse_shards()
         with nat.device_of(self.C):
             nat.check(
                 nat.lib().ptdeco_cov_finalize(self.C.data_ptr(), self.C.stride(0), self.d,
@@ -133,6 +180,20 @@ class CovarianceAccumulator:
                                               float(damp_factor), None, nat.stream_ptr(self.device)),
                 "ptdeco_cov_finalize")
         return self.C
+
+
+CANONICAL_SHARDS = 8  # world sizes 1, 2, 4, 8 divide it
+
+
+def canonical_shards(world: int) -> int:
+    """Number of canonical shards a sharded calibration uses: CANONICAL_SHARDS when the
+    deterministic flag is on (bits independent of the GPU count), else 1 (plain partial sums)."""
+    if not (nat.call_flags() & nat.FLAG_DETERMINISTIC):
+        return 1
+    if CANONICAL_SHARDS % world:
+        raise ValueError(f"deterministic multi-GPU calibration needs a world size dividing "
+                         f"{CANONICAL_SHARDS}, got {world}")
+    return CANONICAL_SHARDS
 
 
 def eigh(cov: torch.Tensor, k: Optional[int] = None) -> tuple[torch.Tensor, torch.Tensor]:

@@ -125,6 +125,37 @@ def reduce_accumulator_to(acc, owner: int, group, total_steps: Optional[int] = N
     finish_reduce_lower(acc, start_reduce_lower(acc, owner, group, total_steps))
 
 
+def gather_shards_to(acc, owner: int, group, total_steps: int) -> None:
+    """Reproducibility mode of the exchange (CovarianceAccumulator with canonical shards): instead
+    of an NCCL reduction, whose summation order follows the ring / tree of the day and the world
+    size, the owner receives every non-empty shard C_v from its holder (v mod world) and adds them
+    in index order -- the arithmetic of a single GPU holding all V shards. Full matrices, point to
+    point; every rank walks (v = 0..V-1) in the same order, so the sends and receives pair up."""
+    rank, world = rank_and_world(group)
+    if acc.shard_world != world:
+        raise ValueError(f"accumulator was sharded for {acc.shard_world} ranks, group has {world}")
+    if rank == owner:
+        acc.C.zero_()
+    tmp = None
+    for v in range(min(acc.shards, int(total_steps))):  # shard v is non-empty iff step v exists
+        holder = v % world
+        mine = acc.shard_C[v]
+        if holder == owner:
+            if rank == owner:
+                acc.C += mine
+        elif rank == holder:
+            dist.send(mine, dst=dist.get_global_rank(group, owner), group=group)
+        elif rank == owner:
+            if tmp is None:
+                tmp = torch.empty_like(acc.C)
+            dist.recv(tmp, src=dist.get_global_rank(group, holder), group=group)
+            acc.C += tmp
+        if rank == holder:
+            acc.shard_C[v] = None
+    acc._collapsed = True
+    acc.steps = int(total_steps)
+
+
 def owner_computes(layer_index: int, group, compute: Callable[[], torch.Tensor], acc,
                    shape: tuple[int, int], dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """Reduce `acc` to the layer's owner, let the owner run `compute()` (finalize + eigensolve on
@@ -178,11 +209,17 @@ def owners_compute_pipelined(jobs: list, group, total_steps: Optional[int] = Non
     rank, world = rank_and_world(group)
     owners = (balanced_owners(costs, world) if costs is not None
               else [owner_of(i, world) for i in range(len(jobs))])
-    pending = [start_reduce_lower(acc, owners[i], group, total_steps)
-               for i, (acc, _, _) in enumerate(jobs)]
-    for i, (acc, _, _) in enumerate(jobs):
-        finish_reduce_lower(acc, pending[i])
-    pending.clear()
+    if any(getattr(acc, "shards", 1) > 1 for acc, _, _ in jobs):
+        if total_steps is None:
+            raise ValueError("canonical shards need the calibration's total step count")
+        for i, (acc, _, _) in enumerate(jobs):
+            gather_shards_to(acc, owners[i], group, total_steps)
+    else:
+        pending = [start_reduce_lower(acc, owners[i], group, total_steps)
+                   for i, (acc, _, _) in enumerate(jobs)]
+        for i, (acc, _, _) in enumerate(jobs):
+            finish_reduce_lower(acc, pending[i])
+        pending.clear()
     outs: list = [None] * len(jobs)
     for i, (acc, compute, shape) in enumerate(jobs):
         if rank == owners[i]:

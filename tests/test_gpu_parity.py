@@ -645,6 +645,60 @@ def test_deterministic_flag_is_per_call_and_bit_reproducible(dev):
     assert _rel(other[0].cpu().numpy(), a[0].cpu().numpy()) < 1e-6  # same numbers up to summation order
 
 
+def test_canonical_shards_make_the_covariance_independent_of_the_gpu_count(dev):
+    """in deterministic mode calibration step i goes to canonical shard i mod 8
+    whatever GPU ran it and the shards are added in index order, so a 1-, 2-, 4- or 8-way split of
+    the steps yields the same bits. The split is emulated on one GPU with the accumulators of every
+    "rank" (tools/dist_check.py repeats it across real GPUs with NCCL point-to-point gathers); a
+    plain sharded sum of the same steps differs in the low bits."""
+    from ptdeco_b200 import _native as nat
+    from ptdeco_b200 import linalg
+    d, n, steps = 320, 1024, 11
+    g = torch.Generator().manual_seed(5)
+    ys = [(torch.randn(n, d, generator=g) * 10.0 ** float(torch.randint(-2, 3, (1,), generator=g)))
+          .to(torch.bfloat16).to(dev) for _ in range(steps)]
+    try:
+        nat.set_deterministic(True)
+        V = linalg.canonical_shards(1)
+        assert V == linalg.CANONICAL_SHARDS == 8
+        with pytest.raises(ValueError):
+            linalg.canonical_shards(3)
+        covs = {}
+        for world in (1, 2, 4, 8):
+            accs = [linalg.CovarianceAccumulator(d, dev, shards=V, rank=r, world=world) for r in range(world)]
+            for i, y in enumerate(ys):
+                accs[i % world].update(y)            # default step numbering: rank + j * world
+            owner = accs[0]
+            if world > 1:                            # what parallel.gather_shards_to does over NCCL
+                owner.C.zero_()
+                for v in range(min(V, steps)):
+                    owner.C += accs[v % world].shard_C[v]
+                owner._collapsed, owner.steps = True, steps
+            covs[world] = owner.finalize(False, 0.01).clone()
+        # explicit step numbers (the dwain precompute passes them) give the same shards
+        acc = linalg.CovarianceAccumulator(d, dev, shards=V, rank=1, world=2)
+        for i in range(1, steps, 2):
+            acc.update(ys[i], step=i)
+        ref = linalg.CovarianceAccumulator(d, dev, shards=V, rank=1, world=2)
+        for i in range(1, steps, 2):
+            ref.update(ys[i])
+        assert all((a is None) == (b is None) and (a is None or torch.equal(a, b))
+                   for a, b in zip(acc.shard_C, ref.shard_C))
+        plain = linalg.CovarianceAccumulator(d, dev)
+        for y in ys:
+            plain.update(y)
+        cov_plain = plain.finalize(False, 0.01).clone()
+    finally:
+        nat.set_deterministic(False)
+    assert linalg.canonical_shards(2) == 1  # default mode: plain partial sums
+    for world in (2, 4, 8):
+        assert torch.equal(covs[world], covs[1]), world
+    assert _rel(cov_plain.cpu().numpy(), covs[1].cpu().numpy()) < 1e-6
+    cov_ref = sum((y.double().T @ y.double()) / n for y in ys) / steps
+    cov_ref += 0.01 * cov_ref.diagonal().mean() * torch.eye(d, device=dev, dtype=torch.float64)
+    assert _rel(covs[1].double().cpu().numpy(), cov_ref.cpu().numpy()) < COV_TOL
+
+
 def test_workspaces_are_per_stream(dev):
     """the scratch buffer (the decode kernel keeps its grid-barrier / ticket words and
     the rank-k intermediate in it) is keyed by (device, stream), so forwards issued on two

@@ -183,6 +183,31 @@ class _FakeAcc:
         self.steps = 0
 
 
+class _FakeShardedAcc(_FakeAcc):
+    """The canonical-shard side of CovarianceAccumulator (attributes parallel.gather_shards_to uses)."""
+
+    def __init__(self, d, shards, rank, world):
+        super().__init__(d)
+        self.shards, self.shard_rank, self.shard_world = shards, rank, world
+        self.shard_C = [None] * shards
+        self._collapsed = False
+
+    def update(self, part, step):
+        v = step % self.shards
+        if self.shard_C[v] is None:
+            self.shard_C[v] = torch.zeros_like(self.C)
+        self.shard_C[v] += part
+        self.steps += 1
+
+
+def _canonical_parts(d, n, steps, layer):
+    from synth import cases
+    g = torch.Generator().manual_seed(77 + layer)
+    # badly scaled partial products: any change of summation order shows in the low bits
+    return [(cases.step_spectrum_batch(n, d, 10 * layer + i).T @ cases.step_spectrum_batch(n, d, 10 * layer + i))
+            * float(10.0 ** torch.randint(-3, 4, (1,), generator=g).item()) for i in range(steps)]
+
+
 def _gloo_worker(rank, world, port, out_dir):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
@@ -233,6 +258,19 @@ def _gloo_worker(rank, world, port, out_dir):
     for layer in range(3):
         assert all(a.steps == steps for a in accs)
         assert torch.equal(piped[layer], results[layer]), layer
+    # canonical shards (deterministic mode): the owner adds the V shard matrices in index order,
+    # which is bit for bit the sum a single process holding all V shards forms
+    shards, c_steps = 4, 7
+    jobs = []
+    for layer in range(3):
+        acc = _FakeShardedAcc(d, shards, rank, world)
+        parts = _canonical_parts(d, n, c_steps, layer)
+        for i in parallel.steps_of_rank(c_steps, rank, world):
+            acc.update(parts[i], i)
+        jobs.append((acc, (lambda acc=acc: acc.C.clone()), (d, d)))
+    canon = parallel.owners_compute_pipelined(jobs, group, total_steps=c_steps, costs=[1.0, 5.0, 2.0])
+    assert all(a.steps == c_steps and all(c is None for c in a.shard_C[rank::world]) for a, _, _ in jobs)
+    results["canonical"] = torch.stack(canon)
     parallel.check_identical_batches({"ids": torch.arange(6).reshape(2, 3)}, group)
     with pytest.raises(RuntimeError):
         parallel.check_identical_batches(torch.full((2, 2), float(rank)), group)
@@ -262,6 +300,20 @@ def test_two_rank_gloo_sharded_covariance(tmp_path):
             P.update_Eyyt_in_place(full, cases.step_spectrum_batch(n, d, 10 * layer + i).numpy())
         u = P.top_k(P.dwain_get_eigenvectors(full / steps), k)
         assert P.min_principal_cosine(u, r0[layer].numpy()) > 0.9999
+    # canonical shards: both ranks hold exactly the single-process sum ((C_0 + C_1) + C_2) + C_3
+    assert torch.equal(r0["canonical"], r1["canonical"])
+    shards, c_steps = 4, 7
+    for layer in range(3):
+        parts = _canonical_parts(d, n, c_steps, layer)
+        single = _FakeShardedAcc(d, shards, 0, 1)
+        for i in range(c_steps):
+            single.update(parts[i], i)
+        total = torch.zeros(d, d)
+        for v in range(shards):
+            total += single.shard_C[v]
+        assert torch.equal(r0["canonical"][layer], total), layer
+        plain = sum(parts[1:], parts[0])
+        assert not torch.equal(plain, total)  # the order does matter for these inputs
 
 
 def test_lowrank_sequential_is_a_sequential():
@@ -530,10 +582,10 @@ def test_covariance_units_share_input_accumulators(monkeypatch):
     from ptdeco_b200 import linalg
 
     class FakeAcc:
-        def __init__(self, d, device, with_mean=False, defer_rows=0):
+        def __init__(self, d, device, with_mean=False, defer_rows=0, shards=1, rank=0, world=1):
             self.d, self.C, self.steps = d, torch.zeros(d, d, dtype=torch.float64), 0
 
-        def update(self, y, sub=None):
+        def update(self, y, sub=None, step=None):
             y = y.double()
             self.C += y.T @ y / y.shape[0]
             self.steps += 1

@@ -63,20 +63,36 @@ def main():
     assert worst >= 0.9999, worst
 
     # deterministic mode (PTDECO_FLAG_DETERMINISTIC on every kernel call): bit-identical results
-    # from run to run at a fixed world size; against another world size the partial sums are
-    # grouped differently (rank r folds steps r, r + world, ...), which is fp32 summation order
+    # from run to run AND against the single-GPU computation: calibration step i is folded into
+    # canonical shard i mod 8 whatever GPU ran it, and the owner adds the shards in index order
     from ptdeco_b200 import _native as nat
     nat.set_deterministic(True)
     reruns = []
-    for _ in range(2):
+    for g in (group, group, None):
         m_, s_, _, _ = cases.dwain_case("llama_tiny")
         m_.to(dev)
         reruns.append(D._precompute_covariance_matrix_decompositions(
             module=m_, submodule_names=names, num_data_steps=8, data_iterator=s_, device=dev,
-            decompose_in_float64=True, reduction_factor=0.5, group=group))
-    nat.set_deterministic(False)
+            decompose_in_float64=True, reduction_factor=0.5, group=g))
     out["deterministic_reruns_bit_identical"] = all(torch.equal(reruns[0][n], reruns[1][n]) for n in names)
+    out["deterministic_sharded_equals_single_gpu_bits"] = all(
+        torch.equal(reruns[0][n], reruns[2][n]) for n in names)
     assert out["deterministic_reruns_bit_identical"]
+    assert out["deterministic_sharded_equals_single_gpu_bits"]
+    # ... and so is the whole decomposition: every trial's measured metrics, not just the ranks
+    traces = []
+    for g in ("world" if world > 1 else None, None):
+        m_, s_, mm_, kw_ = cases.dwain_case("llama_tiny_splits")
+        m_.to(dev)
+        tr = []
+        dwain.decompose_in_place(module=m_, device=dev, data_iterator=s_, metric_iterator=mm_,
+                                 loss_fn=cases.dwain_loss_fn("llama_tiny_splits"),
+                                 finetune_fn=lambda m, d, nn: m, process_group=g, trace=tr, **kw_)
+        traces.append([(t["name"], t["rank"], t["nsr"], t["ppl_diff"], t["ppl_deco"], t["accepted"]) for t in tr])
+    nat.set_deterministic(False)
+    out["deterministic_trial_metrics_equal_single_gpu_bits"] = traces[0] == traces[1]
+    out["deterministic_trials_compared"] = len(traces[0])
+    assert traces[0] == traces[1], [x for x, y in zip(*traces) if x != y][:3]
 
     gold = json.load(open(os.path.join(ROOT, "tests", "golden", "dwain_llama_tiny_splits.json")))
     model3, s3, m3, kw3 = cases.dwain_case("llama_tiny_splits")
