@@ -51,7 +51,15 @@ class CovarianceAccumulator:
     `defer_rows > 0` batches of equal N are first copied into a staging buffer and folded in with
     ONE call once `defer_rows` rows are pending (sum_steps y^T y / N is a SYRK over the
     concatenated rows); `flush()` / `finalize()` drain it. Results are identical up to fp32
-    summation order.
+    summation order. Staged work leaves the caller's stream: the copies run on a per-device copy
+    stream (ordered after the producer of `y` and after the SYRK that last read the staging rows)
+    and the group SYRKs on a per-device SYRK stream (ordered after their copies), so the copies of
+    one accumulator overlap the SYRK of another and both overlap the model's next layers;
+    `flush()` / `finalize()` order the caller's stream after them. The first group of every
+    accumulator is shortened by a per-instance phase so that the launches of many accumulators
+    spread over the steps instead of all landing on every 8th (otherwise 7 of 8 steps are copies
+    only, with nothing to hide behind). PTDECO_B200_ASYNC_STAGING=0 or the deterministic flag
+    restores in-stream copies and SYRKs and full-length groups.
 
     Canonical shards (`shards = V > 1`, the multi-GPU reproducibility mode): calibration step i is
     folded into partial matrix C_(i mod V), one SYRK launch per step, and the covariance is
@@ -59,6 +67,18 @@ class CovarianceAccumulator:
     a `world`-GPU run (world divides V) holds the shards v = rank (mod world) and the owner adds
     all V in index order (parallel.gather_shards_to), so 1, 2, 4 and 8 GPUs produce the same
     bits. Costs V accumulators of memory and the deferral."""
+
+    _instances = 0
+    _side_streams: dict = {}
+
+    @classmethod
+    def _side_streams_of(cls, device: torch.device) -> tuple:
+        """(copy stream, SYRK stream) of a device, shared by all accumulators on it."""
+        device = torch.device(device)
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        if key not in cls._side_streams:
+            cls._side_streams[key] = (torch.cuda.Stream(device=key), torch.cuda.Stream(device=key))
+        return cls._side_streams[key]
 
     def __init__(self, d: int, device: torch.device, with_mean: bool = False, defer_rows: int = 0,
                  shards: int = 1, rank: int = 0, world: int = 1):
@@ -74,6 +94,15 @@ class CovarianceAccumulator:
         self._pending_rows = 0
         self._pending_n = 0
         self.launches = 0
+        self._async = (os.environ.get("PTDECO_B200_ASYNC_STAGING", "1") != "0"
+                       and not (nat.call_flags() & nat.FLAG_DETERMINISTIC))
+        self._phase = CovarianceAccumulator._instances if self._async else -1
+        CovarianceAccumulator._instances += 1
+        self._limit_rows = 0                 # rows at which the current group is flushed
+        self._ev_ready = self._ev_copied = self._ev_consumed = None  # CUDA events ordering the side streams
+        self._copies_in_flight = False       # staged rows of the current group were copied on the copy stream
+        self._syrk_recorded = False          # a SYRK has run on the SYRK stream (ev_consumed is meaningful)
+        self._stage_shared = False           # the staging buffer is known to the allocator on both side streams
         self.shards = int(shards)
         self.shard_rank, self.shard_world = int(rank), int(world)
         self.shard_C: list[Optional[torch.Tensor]] = [None] * self.shards
@@ -136,17 +165,69 @@ class CovarianceAccumulator:
             self.flush()
         if self._stage is None or self._stage.dtype != y.dtype or self._stage.shape[0] < n:
             cap = max(1, self.defer_rows // n) * n
+            self.flush()
             self._stage = torch.empty((cap, self.d), dtype=y.dtype, device=y.device)
-        self._stage[self._pending_rows:self._pending_rows + n].copy_(y)
+            self._stage_shared = False
+            self._limit_rows = 0
+        if self._pending_rows == 0 and self._limit_rows == 0:
+            groups = self._stage.shape[0] // n
+            # first group after construction / an explicit flush: 1..groups steps, by instance phase
+            self._limit_rows = ((self._phase % groups) + 1) * n if self._phase >= 0 else groups * n
+        dst = self._stage[self._pending_rows:self._pending_rows + n]
+        if self._async and not torch.cuda.is_current_stream_capturing():
+            cur = torch.cuda.current_stream(y.device)
+            copy_s, syrk_s = self._side_streams_of(y.device)
+            if self._ev_ready is None:
+                self._ev_ready, self._ev_copied, self._ev_consumed = (torch.cuda.Event() for _ in range(3))
+                self.C.record_stream(syrk_s)
+            if not self._stage_shared:
+                self._stage.record_stream(copy_s)
+                self._stage.record_stream(syrk_s)
+                self._stage_shared = True
+            self._ev_ready.record(cur)              # y (and everything this accumulator did in-stream) is complete
+            copy_s.wait_event(self._ev_ready)
+            if self._syrk_recorded:
+                copy_s.wait_event(self._ev_consumed)  # the SYRK that last read the staging rows is done
+            with torch.cuda.stream(copy_s):
+                dst.copy_(y)
+            y.record_stream(copy_s)
+            self._ev_copied.record(copy_s)
+            self._copies_in_flight = True
+        else:
+            dst.copy_(y)
         self._pending_rows += n
         self._pending_n = n
-        if self._pending_rows + n > self._stage.shape[0]:
-            self.flush()
+        if self._pending_rows >= self._limit_rows:
+            self._launch_group()
+            self._limit_rows = self._stage.shape[0] // n * n  # steady state: full groups
+
+    def _launch_group(self) -> None:
+        """SYRK over the staged rows: on the SYRK side stream when their copies ran on the copy
+        stream (the current stream is not made to wait -- `flush()` does that), else in-stream."""
+        if not self._pending_rows:
+            return
+        rows = self._stage[:self._pending_rows]
+        alpha = 1.0 / self._pending_n
+        if self._copies_in_flight:
+            _, syrk_s = self._side_streams_of(self.device)
+            syrk_s.wait_event(self._ev_copied)
+            with torch.cuda.stream(syrk_s):
+                self._syrk(rows, None, alpha)
+            self._ev_consumed.record(syrk_s)
+            self._syrk_recorded = True
+            self._copies_in_flight = False
+        else:
+            if self._syrk_recorded:
+                torch.cuda.current_stream(self.device).wait_event(self._ev_consumed)
+            self._syrk(rows, None, alpha)
+        self._pending_rows = 0
+        self._limit_rows = 0
 
     def flush(self) -> None:
-        if self._pending_rows:
-            self._syrk(self._stage[:self._pending_rows], None, 1.0 / self._pending_n)
-            self._pending_rows = 0
+        """Fold every staged row in; afterwards C is valid for work enqueued on the current stream."""
+        self._launch_group()
+        if self._syrk_recorded:
+            torch.cuda.current_stream(self.device).wait_event(self._ev_consumed)
 
     def release_staging(self) -> None:
         self.flush()
