@@ -234,7 +234,9 @@ struct PanelArgs {
   int prof;       // 1: CTA 0 accumulates per-phase cycle counts into g_phase_cycles
 };
 
-// P1 | barrier A | reflector + v | symv + dots | barrier B | P3   (cycles of CTA 0, summed over columns)
+// Panel kernel, cycles of the middle CTA summed over columns: 0 P1 | 1 barrier A | 6 column gather +
+// scalars | 2 v fill + V writes | 7 symv row items | 8 symv segment sums | 3 partial dots + atomics |
+// 4 barrier B | 9 P3 gather | 5 P3 w rows   (the resident kernel uses the same slots for its own phases)
 __device__ unsigned long long g_phase_cycles[16];
 
 // Grid barrier of the cooperative panel kernel: release-arrive on one counter, acquire-poll.
@@ -454,14 +456,15 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
   for (int idx = tid; idx < NB * (NB + 1); idx += PANEL_THREADS) Ts[idx] = 0.f;
   __syncthreads();
 
-  const bool prof = g.prof && cta == 0 && tid == 0;
+  const bool prof = g.prof && cta == G / 2 && tid == 0;  // a CTA that keeps its rows to the end
   long long tp = prof ? clock64() : 0;
-#define PTD_PHASE(k)                                             \
-  if (prof) {                                                    \
-    const long long tn = clock64();                              \
-    atomicAdd(&g_phase_cycles[k], (unsigned long long)(tn - tp)); \
-    tp = tn;                                                     \
+#define PTD_PHASE(k)                 \
+  if (prof) {                        \
+    const long long tn = clock64();  \
+    pc[k] += tn - tp;                \
+    tp = tn;                         \
   }
+  long long pc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int i = 0; i < g.ncols; ++i) {
     const int j = g.j0 + i;
     // ---------------------------------------------------------------- P1: updated column i
@@ -537,6 +540,8 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
       g.evec[j] = beta;
       g.taus[j] = tau;
     }
+    if (prof && tau == 123.456f) pc[9] += 1;  // (profile only) the stamp below waits for the gathered scalars
+    PTD_PHASE(6)
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int c = tid + u * PANEL_THREADS;
@@ -600,6 +605,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
           const float s = warp_sum(s0 + s1);
           if (lane == 0) pseg[rr * nseg + (sg - seg0)] = s;
         }
+        PTD_PHASE(7)
         __syncthreads();
         for (int rr = tid; rr < R; rr += PANEL_THREADS) {
           float s = 0.f;
@@ -609,6 +615,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
           if (r < NB) g.ptop[r] = s;
         }
         __syncthreads();
+        PTD_PHASE(8)
       }
       float aw0 = 0.f, aw1 = 0.f, av0 = 0.f, av1 = 0.f;
       double vp = 0.0;
@@ -669,6 +676,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
           pbuf[r - r0] = static_cast<float>(__ldcg(pcur + r));
       }
       __syncthreads();
+      PTD_PHASE(9)
       if (warp == 0) {
         double s = 0.0;
         for (int c = lane; c < i; c += 32) s += static_cast<double>(gVs[c]) * gWs[c];
@@ -731,6 +739,8 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) sytrd_panel_kernel(const Pan
     __syncthreads();
     PTD_PHASE(5)
   }
+  if (prof)
+    for (int k2 = 0; k2 < 10; ++k2) atomicAdd(&g_phase_cycles[k2], static_cast<unsigned long long>(pc[k2]));
 #undef PTD_PHASE
   if (cta == 0) {
     __syncthreads();
@@ -1322,16 +1332,19 @@ __device__ __forceinline__ int sturm_count_ratio(const double* __restrict__ D,
 __device__ __forceinline__ int sturm_count(const double* __restrict__ D,
                                            const double* __restrict__ E2, int lo, int hi, double x,
                                            double inv_norm) {
+  // The dependent chain is exactly one DFMA per row: the signs are read off the high words by the
+  // integer pipe and never feed back into p. An exact zero p_i counts as a sign opposite to its
+  // predecessor's and is left in place: the next term is then -e^2 p_{i-1}, which carries that same
+  // opposite sign (e^2 > 0 inside an unreduced block; tri_prep_kernel zeroes off-diagonals below
+  // 2^-27 ||T||, so the scaled e^2 cannot underflow), i.e. one change is counted across the zero.
   const double inv2 = inv_norm * inv_norm;
   double p0 = 1.0, p1 = (__ldg(D + lo) - x) * inv_norm;
-  bool n1 = p1 < 0.0;
-  if (p1 == 0.0) { n1 = true; p1 = -DBL_MIN; }
+  int n1 = (__double2hiint(p1) < 0) || (p1 == 0.0);
   int cnt = n1;
   auto step = [&](double dx, double e2) {
-    double p2 = fma(dx, p1, -(e2 * p0));
-    bool n2 = p2 < 0.0;
-    if (p2 == 0.0) { n2 = !n1; p2 = n2 ? -DBL_MIN : DBL_MIN; }
-    cnt += (n2 != n1);
+    const double p2 = fma(dx, p1, -(e2 * p0));
+    const int n2 = (p2 == 0.0) ? (n1 ^ 1) : static_cast<int>(static_cast<unsigned>(__double2hiint(p2)) >> 31);
+    cnt += n2 ^ n1;
     p0 = p1;
     p1 = p2;
     n1 = n2;
@@ -1346,9 +1359,11 @@ __device__ __forceinline__ int sturm_count(const double* __restrict__ D,
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) step(dx[u], e2[u]);
-    const double a = fmax(fabs(p0), fabs(p1));
-    if (a > 0x1p+300 || a < 0x1p-300) {
-      const double sc = scalbn(1.0, -ilogb(a));
+    // growth is at most ~3x per row on the unit-norm matrix: renormalise by the exponent of the
+    // larger term every 8 rows (integer test on the high word, a power-of-two scale: exact)
+    const int ex = max((__double2hiint(p0) >> 20) & 0x7ff, (__double2hiint(p1) >> 20) & 0x7ff);
+    if (ex > 1023 + 300 || ex < 1023 - 300) {
+      const double sc = scalbn(1.0, 1023 - ex);
       p0 *= sc;
       p1 *= sc;
     }

@@ -27,9 +27,10 @@ if os.environ.get("PANEL_PROF"):
     L.ptdeco_debug_set(100, 1)
     linalg.eigh(cov, k=k)
     torch.cuda.synchronize()
-    cyc = [L.ptdeco_debug_get(100 + i) for i in range(6)]
+    cyc = [L.ptdeco_debug_get(100 + i) for i in range(10)]
     L.ptdeco_debug_set(100, 0)
-    names = ["P1 column update", "barrier A", "reflector + v fill", "symv + partial dots", "barrier B", "P3 w column"]
+    names = ["P1 column update", "barrier A", "v fill + V writes", "partial dots + atomics", "barrier B",
+             "P3 w rows", "column gather + scalars", "symv row items", "symv segment sums", "P3 gather"]
     tot = sum(cyc)
     for n_, c in zip(names, cyc):
         print(f"  panel phase {n_:22s} {c / 1e6:9.2f} Mcycles  {100.0 * c / max(tot, 1):5.1f} %  {c / d / 1.0:8.0f} cycles/column")
