@@ -79,7 +79,7 @@ SIGNATURES = {
 LOWRANK_KNOBS = {200: "PTDECO_B200_FORCE_DECODE", 201: "PTDECO_B200_NO_DECODE",
                  202: "PTDECO_B200_NO_FUSED", 203: "PTDECO_B200_NO_PERSISTENT",
                  204: "PTDECO_B200_NO_TMA_STORE", 205: "PTDECO_B200_FUSED_ROT",
-                 206: "PTDECO_B200_FUSED_STAGES"}
+                 206: "PTDECO_B200_FUSED_STAGES", 208: "PTDECO_B200_FUSED_KSPLIT"}
 
 
 class NativeError(RuntimeError):

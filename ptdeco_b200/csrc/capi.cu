@@ -225,11 +225,12 @@ void ptdeco_debug_set(int key, long long value) {
   else if (key == 104) ptd::eigh_debug_resident(1, 0, static_cast<int>(value));
   else if (key == 105) ptd::eigh_debug_bisect_narrow(static_cast<int>(value));
   else if (key == 106) ptd::eigh_debug_sturm_ratio(static_cast<int>(value));
-  else if (key >= 200 && key < 208) ptd::lowrank_debug_set(key - 200, value);
+  else if (key >= 200 && key < 210) ptd::lowrank_debug_set(key - 200, value);
   else ptd::gemm_tc_debug_set(key, value);
 }
 long long ptdeco_debug_get(int key) {
   if (key >= 100 && key < 116) return ptd::eigh_debug_phase_cycles(key - 100);
+  if (key >= 210 && key < 218) return ptd::lowrank_debug_get(key - 210);
   return ptd::gemm_tc_last_launch_info(key);
 }
 

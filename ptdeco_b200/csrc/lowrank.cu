@@ -33,7 +33,7 @@ namespace {
 // reads the environment): 0 force the decode kernel, 1 no decode kernel, 2 no fused kernel,
 // 3 no persistent kernel, 4 no TMA store, 5 tile rotation (-1 = default), 6 pipeline stages,
 // 7 forced token rows per tile (multiple of 8 in [8, 128]; 0 = cost model).
-long long g_knob[8] = {0, 0, 0, 0, 0, -1, 0, 0};
+long long g_knob[10] = {0, 0, 0, 0, 0, -1, 0, 0, 0, 0};  // [8]: 1 = no k-split clusters, 2 = always when possible
 
 // cudaFuncSetAttribute is per device: remember which devices were configured.
 bool* lr_attr_flag(int which) {
@@ -119,7 +119,20 @@ struct FusedArgs {
   // tile_m rows; the tile's remaining accumulator rows hold don't-care values (rows are
   // independent in both GEMMs) and are never stored.
   int tile_m;
+  // 1: launched as 2-CTA clusters, the two CTAs being the out-groups 2c and 2c+1 of one token tile.
+  // Without it each of them runs the WHOLE GEMM 1 of that tile (X tile and all of W1 streamed
+  // twice, the per-SM TMA stream being what bounds small-N launches); with it each accumulates
+  // H over half of `in`, the fp32 partials cross through distributed shared memory (64 KB each
+  // way, into the output staging area that is idle until the first Y tile), and both add the two
+  // halves in the same order -- so every CTA streams half of X's tile and half of W1, and issues
+  // half of GEMM 1's MMAs. kp <= 128 only (the partial has to fit the staging area).
+  int ksplit;
+  int prof;  // debug: accumulate phase cycles into g_fused_prof
 };
+
+// (debug) cycles of the middle CTA's first epilogue warp: setup | GEMM 1 | H hand-over | first Y tile |
+// remaining Y tiles | store drain; switched on by lowrank_debug_set(9, 1), read by lowrank_debug_get
+__device__ unsigned long long g_fused_prof[8];
 
 __global__ void __launch_bounds__(F_THREADS, 1)
 lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
@@ -140,18 +153,32 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   uint64_t* y_empty = y_full + 2;
   uint64_t* full1 = y_empty + 2;               // GEMM-1 ring when it is longer than the GEMM-2 ring
   uint64_t* empty1 = full1 + F_MAX_STAGES1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty1 + F_MAX_STAGES1);
+  uint64_t* land_free = empty1 + F_MAX_STAGES1;  // k-split: the PEER's staging area may be written
+  uint64_t* land_full = land_free + 1;           // k-split: the peer's partial H has landed here
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(land_full + 1);
   const int F_STAGES1 = g.stages1;
   const bool two_rings = F_STAGES1 != F_STAGES;
   uint64_t* f1 = two_rings ? full1 : full;
   uint64_t* e1 = two_rings ? empty1 : empty;
 
   const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
+  const bool prof = g.prof && blockIdx.x == gridDim.x / 2 && threadIdx.x == 64;
+  long long tp = prof ? clock64() : 0;
+#define LR_PHASE(k)                                                              \
+  if (prof) {                                                                    \
+    const long long tn = clock64();                                              \
+    atomicAdd(&g_fused_prof[k], static_cast<unsigned long long>(tn - tp));       \
+    tp = tn;                                                                     \
+  }
   const int rt = blockIdx.x / g.groups, og = blockIdx.x % g.groups;
   const int m0 = rt * g.tile_m;
   const int t0 = og * g.tiles_per_group;
   const int t1 = min(g.out_tiles, t0 + g.tiles_per_group);
-  const int kb1 = (g.in_f + F_BK - 1) / F_BK;
+  const int kb_all = (g.in_f + F_BK - 1) / F_BK;
+  // k-split: groups is even, so blockIdx.x and og have the same parity = the rank in the cluster
+  const uint32_t crank = g.ksplit ? static_cast<uint32_t>(og & 1) : 0u;
+  const int kb_lo = g.ksplit ? static_cast<int>(crank) * ((kb_all + 1) / 2) : 0;
+  const int kb1 = g.ksplit ? (crank == 0 ? (kb_all + 1) / 2 : kb_all - (kb_all + 1) / 2) : kb_all;
   const int kb2 = g.kp / F_BK;
   // Every CTA streams the SAME W1 k-blocks and W2 tiles; started in lockstep they all hit the
   // same L2 lines at the same time. Each CTA therefore starts at its own offset of the k loop
@@ -179,6 +206,8 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       mbar_init(&y_full[a], 1);
       mbar_init(&y_empty[a], F_EPI_WARPS);
     }
+    mbar_init(land_free, F_EPI_WARPS);
+    mbar_init(land_full, F_EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -187,6 +216,7 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if (g.ksplit) cluster_sync_all();  // the peer's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t h_tmem = tmem_base + 256;  // H accumulates in the upper half; Y tile 0 uses the lower
@@ -197,7 +227,7 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     int stage = 0;
     uint32_t phase = 0;
     for (int kk = 0; kk < kb1; ++kk) {  // GEMM 1 operands
-      const int kb = (kk + rot1) % kb1;
+      const int kb = kb_lo + (kk + rot1) % kb1;
       mbar_wait(&e1[stage], phase ^ 1);
       if (elect_one()) {
         uint8_t* sA = smem + stage * F_STAGE;
@@ -287,8 +317,61 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const int row = q * 32 + lane;
     const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
     // ---- H: TMEM -> bf16 -> swizzled shared memory (the layout TMA would have produced)
+    LR_PHASE(0)
     mbar_wait(h_full, 0);
     tc_fence_after();
+    LR_PHASE(1)
+    if (g.ksplit) {
+      // kp <= 128: at most one 32 x 32 chunk per warp. Partial sums cross as fp32, stored
+      // [column][row] so that a warp's 32 rows of one column are one 128-byte line.
+      const uint32_t peer = crank ^ 1u;
+      const int col0 = cg * 32;
+      const bool has = col0 < g.kp;  // warp-uniform
+      uint32_t r[32];
+      if (has) {
+        tmem_ld_32x32(h_tmem + col0 + lane_bits, r);
+        tmem_ld_wait();
+      }
+      // my GEMM 1 no longer reads its ring (h_full), which overlays my staging area: the peer may write it
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(land_free, peer);
+      mbar_wait_cluster(land_free, 0);
+      LR_PHASE(6)
+      // landing zone: [column][row] fp32, so the 32 rows a warp holds of one column are one 128-byte
+      // line (measured: 4-byte remote stores in this layout take 4.3k cycles for the 64 KB, 16-byte
+      // vector stores into a row-major, XOR-swizzled zone 7.4k)
+      float* zone = reinterpret_cast<float*>(stg_base);
+      if (has) {
+        const uint32_t dst = mapa_u32(smem_u32(zone + col0 * F_TILE_M + row), peer);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st_cluster_f32(dst + j * F_TILE_M * 4, __uint_as_float(r[j]));
+      }
+      fence_acq_rel_cluster();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(land_full, peer);
+      LR_PHASE(7)
+      mbar_wait_cluster(land_full, 0);
+      fence_acq_rel_cluster();
+      if (has) {
+        // both CTAs add (rank 0's half) + (rank 1's half) in that order: identical H in both
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float other = zone[(col0 + j) * F_TILE_M + row];
+          const float mine = __uint_as_float(r[j]);
+          r[j] = __float_as_uint(crank == 0 ? mine + other : other + mine);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = __float2bfloat16_rn(__uint_as_float(r[8 * j + e]));
+          const int col = col0 + 8 * j;
+          const int chunk = (col & 63) >> 3;
+          uint8_t* dst = hbuf + (col >> 6) * F_HBLOCK + row * 128 + ((chunk ^ (row & 7)) << 4);
+          *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(o);
+        }
+      }
+    } else
     for (int col0 = cg * 32; col0 < g.kp; col0 += 4 * 32) {
       uint32_t r[32];
       tmem_ld_32x32(h_tmem + col0 + lane_bits, r);
@@ -308,6 +391,7 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(h_ready);
+    LR_PHASE(2)
     // ---- Y tiles: this warp owns rows [32q, 32q+32) x columns [64cg, 64cg+64) of every tile
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -323,6 +407,7 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       const int t = t0 + (tt + rot3) % ntl;
       mbar_wait(&y_full[acc], acc_phase);
       tc_fence_after();
+      if (tt == 0) { LR_PHASE(3) }
       const int n0 = t * F_TILE_N + cg * 64;
       uint32_t ra[32], rb[32];
       const uint32_t taddr = tmem_base + acc * F_TILE_N + cg * 64 + lane_bits;
@@ -399,11 +484,15 @@ lowrank_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         }
       }
     }
+    LR_PHASE(4)
     if (g.tma_store && lane == 0) bulk_wait_read_all();  // staging must outlive the last store
+    LR_PHASE(5)
   }
+#undef LR_PHASE
 
   tc_fence_before();
   __syncthreads();
+  if (g.ksplit) cluster_sync_all();  // nobody leaves while the peer could still address this CTA
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -1093,8 +1182,14 @@ int launch_fused(const void* X, long long ldx, const void* W1, long long ldw1, c
   g.groups = 1;
   g.tiles_per_group = g.out_tiles;
   g.tile_m = F_TILE_M;
+  g.ksplit = 0;
+  g.prof = g_knob[9] != 0;
   const int tm_lo = g_knob[7] > 0 ? static_cast<int>(g_knob[7]) : 32;
   const int tm_hi = g_knob[7] > 0 ? static_cast<int>(g_knob[7]) : F_TILE_M;
+  // k-split clusters (see FusedArgs::ksplit): pairs of out-groups share one GEMM 1. Needs an even
+  // number of groups, the partial H in the 64 KB staging area (kp <= 128) and two k-blocks.
+  const bool ks_possible = g.kp <= 128 && in_f > F_BK && g_knob[8] != 1;
+  const double exchange = 4e-6;  // measured ~5 us (1.5 us waiting for the peer, 2.3 us of remote stores, 1.2 us back); 4 keeps the N = 2048, k = 32 win
   for (int tm = tm_hi; tm >= tm_lo; tm -= 8) {
     const long long rtiles = (n + tm - 1) / tm;
     for (int G = 1; G <= g.out_tiles; ++G) {
@@ -1102,18 +1197,24 @@ int launch_fused(const void* X, long long ldx, const void* W1, long long ldw1, c
       const int geff = (g.out_tiles + tpg - 1) / tpg;
       const long long units = rtiles * geff;
       const long long waves = (units + sms - 1) / sms;
-      const double t_mma = static_cast<double>(waves) * 2.0 * F_TILE_M * g.kp *
-                           (static_cast<double>(in_f) + static_cast<double>(tpg) * F_TILE_N) / mma_rate;
-      const double bytes = 2.0 * static_cast<double>(n) * (in_f * (1.0 + 0.5 * (geff - 1)) + out_f);
-      const double unit_bytes = 2.0 * (static_cast<double>(tm) * in_f + static_cast<double>(g.kp) * in_f +
-                                       static_cast<double>(tpg) * F_TILE_N * (g.kp + tm));
-      const double t_mem = std::max(bytes / hbm, static_cast<double>(waves) * unit_bytes / sm_stream);
-      const double cost = std::max(t_mma, t_mem) + wave_overhead * static_cast<double>(waves);
-      if (cost < best * 0.98) {
-        best = cost;
-        g.groups = geff;
-        g.tiles_per_group = tpg;
-        g.tile_m = tm;
+      for (int ks = 0; ks <= ((ks_possible && geff % 2 == 0) ? 1 : 0); ++ks) {
+        if (g_knob[8] == 2 && ks_possible && geff % 2 == 0 && ks == 0) continue;
+        const double in_eff = ks ? 0.5 * in_f : static_cast<double>(in_f);
+        const double readers = ks ? 0.5 * geff : static_cast<double>(geff);  // CTAs reading all of X's tile
+        const double t_mma = static_cast<double>(waves) * 2.0 * F_TILE_M * g.kp *
+                             (in_eff + static_cast<double>(tpg) * F_TILE_N) / mma_rate;
+        const double bytes = 2.0 * static_cast<double>(n) * (in_f * (1.0 + 0.5 * (readers - 1.0)) + out_f);
+        const double unit_bytes = 2.0 * (static_cast<double>(tm) * in_eff + static_cast<double>(g.kp) * in_eff +
+                                         static_cast<double>(tpg) * F_TILE_N * (g.kp + tm));
+        const double t_mem = std::max(bytes / hbm, static_cast<double>(waves) * unit_bytes / sm_stream);
+        const double cost = std::max(t_mma, t_mem) + (wave_overhead + (ks ? exchange : 0.0)) * static_cast<double>(waves);
+        if (cost < best * 0.98) {
+          best = cost;
+          g.groups = geff;
+          g.tiles_per_group = tpg;
+          g.tile_m = tm;
+          g.ksplit = ks;
+        }
       }
     }
   }
@@ -1167,19 +1268,47 @@ int launch_fused(const void* X, long long ldx, const void* W1, long long ldw1, c
     }
     g.groups = 1;
     g.tiles_per_group = g.out_tiles;
+    g.ksplit = 0;
     lowrank_persistent_kernel<<<sms, F_THREADS, P_SMEM, st>>>(tx, tw1, tw2, ty, g);
     return cudaGetLastError() == cudaSuccess ? 0 : -5;
   }
   const long long grid = static_cast<long long>(row_tiles) * g.groups;
   if (grid > 0x7fffffffLL) return -22;
+  if (g.ksplit) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(F_THREADS);
+    cfg.dynamicSmemBytes = F_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, lowrank_fused_kernel, tx, tw1, tw2, ty, g) != cudaSuccess) return -5;
+    return cudaGetLastError() == cudaSuccess ? 0 : -5;
+  }
   lowrank_fused_kernel<<<static_cast<unsigned>(grid), F_THREADS, F_SMEM, st>>>(tx, tw1, tw2, ty, g);
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }
 
 }  // namespace
 
+long long lowrank_debug_get(int k) {
+  unsigned long long v[8];
+  if (k < 0 || k >= 8 || cudaMemcpyFromSymbol(v, g_fused_prof, sizeof(v)) != cudaSuccess) return -1;
+  return static_cast<long long>(v[k]);
+}
+
 void lowrank_debug_set(int key, long long value) {
-  if (key >= 0 && key < 8) g_knob[key] = value;
+  if (key == 9) {
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(g_fused_prof, z, sizeof(z));
+  }
+  if (key >= 0 && key < 10) g_knob[key] = value;
 }
 
 size_t lowrank_workspace_bytes(int is_bf16, long long n, int in_f, int k, int out_f) {

@@ -13,7 +13,9 @@ int lowrank_forward(const void* X, long long ldx, const void* W1, long long ldw1
                     long long n, int in_f, int k, int out_f, void* ws, size_t ws_bytes,
                     cudaStream_t st);
 
-// Runtime knobs 0..6 (see lowrank.cu); reached through ptdeco_debug_set keys 200..206.
+// Runtime knobs 0..9 (see lowrank.cu); reached through ptdeco_debug_set keys 200..209. Knob 9
+// switches on the fused kernel's phase-cycle counters, read back through ptdeco_debug_get 210..217.
 void lowrank_debug_set(int key, long long value);
+long long lowrank_debug_get(int k);
 
 }  // namespace ptd

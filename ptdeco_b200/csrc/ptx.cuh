@@ -210,6 +210,38 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
       "r"(rank)
       : "memory");
 }
+// ---------------------------------------------------------------- distributed shared memory
+// Plain (non-TMA) exchange between the CTAs of a cluster: map a local shared-memory address into
+// CTA `rank`'s window, store there, and hand over with a release-arrive on a barrier of that CTA;
+// the receiver waits with cluster-scope acquire.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_cluster() {
+  asm volatile("fence.acq_rel.cluster;" ::: "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t polls = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (++polls > (1u << 26)) __trap();
+  }
+}
 // TMA load into THIS CTA's shared memory whose completion bytes are credited to the LEADER CTA's
 // barrier (same offset; bit 24 of a shared::cluster address is the rank parity inside the pair).
 __device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
