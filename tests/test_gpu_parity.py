@@ -393,6 +393,41 @@ def test_lowrank_forward_balanced_token_tiles(dev, tile_m, n, in_f, k, out_f):
     assert torch.equal(view, y) and bool((big[:8] == 7.0).all()) and bool((big[8 + n:] == 7.0).all())
 
 
+@pytest.mark.parametrize("n,in_f,k,out_f", [(8192, 4096, 128, 4096), (2048, 4096, 32, 4096), (1000, 768, 96, 3072),
+                                            (4100, 200, 64, 1024), (300, 4096, 128, 512)])
+def test_lowrank_forward_k_split_clusters(dev, n, in_f, k, out_f):
+    """K7 with pairs of out-groups sharing GEMM 1 over a 2-CTA cluster (each accumulates H over
+    half of `in`, the fp32 partials cross through distributed shared memory): forced wherever the
+    shape allows it (knob 208 = 2) and switched off (1), both against the fp64 product of the bf16
+    operands; both CTAs of a pair add the halves in the same order, so reruns are bit-identical;
+    ragged token counts and an `in` that is not a multiple of the k-block included."""
+    from ptdeco_b200 import _native as nat
+    from ptdeco_b200 import linalg
+    g = torch.Generator().manual_seed(n + k + out_f)
+    x = torch.randn(n, in_f, generator=g).to(torch.bfloat16)
+    w1 = (torch.randn(k, in_f, generator=g) / in_f ** 0.5).to(torch.bfloat16)
+    w2 = (torch.randn(out_f, k, generator=g) / k ** 0.5).to(torch.bfloat16)
+    b = torch.randn(out_f, generator=g)
+    xd, w1d, w2d, bd = x.to(dev), w1.to(dev), w2.to(dev), b.to(dev)
+    L = nat.lib()
+    outs = {}
+    try:
+        for mode in (2, 2, 1):
+            L.ptdeco_debug_set(208, mode)
+            outs.setdefault(mode, []).append(linalg.lowrank_forward(xd, w1d, w2d, bd))
+        torch.cuda.synchronize()
+    finally:
+        L.ptdeco_debug_set(208, 0)
+    h = (x.double() @ w1.double().T).to(torch.bfloat16).double()
+    ref = h @ w2.double().T + b.double()
+    for mode, ys in outs.items():
+        for y in ys:
+            assert (y.double().cpu() - ref).abs().max() <= 2e-2 * ref.abs().max(), mode
+    assert torch.equal(outs[2][0], outs[2][1])
+    # H differs from the unsplit sum only by fp32 rounding before its bf16 rounding
+    assert (outs[2][0].float() - outs[1][0].float()).abs().max() <= 2e-2 * ref.abs().max()
+
+
 @pytest.mark.parametrize("n,in_f,k,out_f,bias", [
     (1, 256, 32, 256, False), (5, 320, 96, 1000, True), (16, 4096, 512, 4096, True),
     (33, 768, 200, 3072, True), (128, 2048, 1024, 2048, False), (100, 1024, 1000, 520, True),
