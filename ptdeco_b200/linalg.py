@@ -52,9 +52,10 @@ class CovarianceAccumulator:
     ONE call once `defer_rows` rows are pending (sum_steps y^T y / N is a SYRK over the
     concatenated rows); `flush()` / `finalize()` drain it. Results are identical up to fp32
     summation order. Staged work leaves the caller's stream: the copies run on a per-device copy
-    stream (ordered after the producer of `y` and after the SYRK that last read the staging rows)
+    stream (ordered after the producer of `y` and after the SYRK that last read the staging rows;
+    the caller's stream waits for its copy, so `y` may be overwritten as soon as `update` returns)
     and the group SYRKs on a per-device SYRK stream (ordered after their copies), so the copies of
-    one accumulator overlap the SYRK of another and both overlap the model's next layers;
+    one accumulator overlap the SYRK of another and the SYRKs overlap the model's next layers;
     `flush()` / `finalize()` order the caller's stream after them. The first group of every
     accumulator is shortened by a per-instance phase so that the launches of many accumulators
     spread over the steps instead of all landing on every 8th (otherwise 7 of 8 steps are copies
@@ -192,6 +193,10 @@ class CovarianceAccumulator:
                 dst.copy_(y)
             y.record_stream(copy_s)
             self._ev_copied.record(copy_s)
+            # the caller may overwrite y in place right after this call (an inplace activation behind
+            # a hooked layer): its stream continues only once the rows are staged. That costs the
+            # caller what an in-stream copy cost; the group SYRKs still run beside it.
+            cur.wait_event(self._ev_copied)
             self._copies_in_flight = True
         else:
             dst.copy_(y)

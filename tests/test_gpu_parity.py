@@ -734,6 +734,36 @@ def test_canonical_shards_make_the_covariance_independent_of_the_gpu_count(dev):
     assert _rel(covs[1].double().cpu().numpy(), cov_ref.cpu().numpy()) < COV_TOL
 
 
+def test_staged_updates_survive_in_place_reuse_of_the_batch(dev):
+    """The staging copies and group SYRKs of CovarianceAccumulator run on side streams; the batch
+    handed to update() may still be overwritten in place right afterwards (an inplace activation
+    behind a hooked layer output), reused for the next step, or freed. Covariance must be that of
+    the values at call time, for several interleaved accumulators, with a flush in the middle."""
+    from ptdeco_b200 import linalg
+    d, n, steps = 1024, 2048, 21
+    g = torch.Generator(device=dev).manual_seed(11)
+    accs = [linalg.CovarianceAccumulator(d, dev, defer_rows=8 * n) for _ in range(3)]
+    refs = [torch.zeros(d, d, dtype=torch.float64, device=dev) for _ in accs]
+    buf = torch.empty(n, d, dtype=torch.bfloat16, device=dev)   # one buffer reused for every batch
+    for i in range(steps):
+        for a, (acc, ref) in enumerate(zip(accs, refs)):
+            buf.copy_(torch.randn(n, d, generator=g, device=dev) * (1.0 + a))
+            ref += buf.double().T @ buf.double() / n
+            acc.update(buf)
+            buf.relu_()                                         # in place, right after the call
+            tmp = torch.randn(n, d, generator=g, device=dev).to(torch.bfloat16)
+            ref += tmp.double().T @ tmp.double() / n
+            acc.update(tmp)
+            del tmp                                             # freed while its copy may be pending
+        if i == 9:
+            accs[1].flush()
+    for acc, ref in zip(accs, refs):
+        assert acc.steps == 2 * steps
+        cov = acc.finalize(False, 0.0)
+        want = ref / (2 * steps)
+        assert _rel(torch.tril(cov).double().cpu().numpy(), torch.tril(want).cpu().numpy()) < COV_TOL
+
+
 def test_workspaces_are_per_stream(dev):
     """the scratch buffer (the decode kernel keeps its grid-barrier / ticket words and
     the rank-k intermediate in it) is keyed by (device, stream), so forwards issued on two
