@@ -237,6 +237,13 @@ def extra_eigh(dev, gen, world: int) -> dict:
             torch.linalg.eigh(c)
             row["host_cpu_fp32_ms"] = 1e3 * (time.perf_counter() - t0)
             row["host_cores"] = os.cpu_count()
+        if world == 1 and d == 2048:  # the reference's decompose_in_float64 path (D:155-163 on fp64)
+            c = cov.double().cpu()
+            torch.set_num_threads(os.cpu_count() or 1)
+            t0 = time.perf_counter()
+            torch.linalg.eigh(c)
+            row["host_cpu_fp64_ms"] = 1e3 * (time.perf_counter() - t0)
+            row["host_cores"] = os.cpu_count()
         out[f"d{d}"] = row
         del cov, acc, y
     return out
@@ -283,6 +290,17 @@ def extra_lowrank(dev, gen, peaks) -> dict:
             "ms": ms, "torch_sequential_cublas_ms": ms_t, "bound": "hbm" if t_hbm >= t_tc else "tensor",
             "frac_of_bound": max(t_hbm, t_tc) / (ms * 1e-3), "achieved_gbs": alg_bytes / ms / 1e6,
             "achieved_tflops": flops / ms / 1e9}
+        if (n, k) == (8192, 128):  # the reference's decomposed module on the host (fp32, all cores)
+            torch.set_num_threads(os.cpu_count() or 1)
+            seq_cpu = seq.float().cpu()
+            x_cpu = x[:2048].float().cpu()
+            with torch.no_grad():
+                seq_cpu(x_cpu)
+                t0 = time.perf_counter()
+                seq_cpu(x_cpu)
+                dt = time.perf_counter() - t0
+            out[f"N{n}_in{fin}_k{k}_out{fout}"]["host_cpu_fp32_ms_scaled_from_2048_rows"] = 1e3 * dt * n / 2048
+            out[f"N{n}_in{fin}_k{k}_out{fout}"]["host_cores"] = os.cpu_count()
         del x, w1, w2, seq
     return out
 
