@@ -225,6 +225,7 @@ void ptdeco_debug_set(int key, long long value) {
   else if (key == 104) ptd::eigh_debug_resident(1, 0, static_cast<int>(value));
   else if (key == 105) ptd::eigh_debug_bisect_narrow(static_cast<int>(value));
   else if (key == 106) ptd::eigh_debug_sturm_ratio(static_cast<int>(value));
+  else if (key == 107) ptd::eigh_debug_small(static_cast<int>(value));
   else if (key >= 200 && key < 210) ptd::lowrank_debug_set(key - 200, value);
   else ptd::gemm_tc_debug_set(key, value);
 }

@@ -1126,6 +1126,180 @@ __global__ void __launch_bounds__(RES_THREADS, 1) sytd2_resident_kernel(const Re
 #undef RES_PHASE
 }
 
+// ---------------------------------------------------------------------------- d <= 128: one CTA
+// The whole matrix fits one SM's shared memory, so the reduction needs no grid-wide exchange at
+// all: unblocked sytd2 (LAPACK, lower) with three block barriers per column, every warp owning
+// rows {warp, warp + 16, ...} of the trailing block for both the symv dots and the rank-2 update
+// (lanes run over columns: conflict-free, warp-synchronous reductions). Same outputs as the
+// resident kernel (d / e / tau, reflectors as rows of VT), so T factors, the tridiagonal stage and
+// the back-transformation are shared. fp32 working precision like the other two kernels.
+constexpr int SMALL_MAX = 128;
+constexpr int SMALL_THREADS = 512;
+__global__ void __launch_bounds__(SMALL_THREADS, 1)
+sytd2_small_kernel(const float* __restrict__ A, long long ldA, int d, int L, float* __restrict__ VT,
+                   long long ldvt, float* __restrict__ dvec, float* __restrict__ evec,
+                   float* __restrict__ taus, int prof_on) {
+  extern __shared__ float sma[];
+  const int LD = d | 1;  // odd row stride: column walks are conflict-free too
+  float* As = sma;                 // [d][LD]
+  float* v = As + d * LD;          // [SMALL_MAX]
+  float* pvec = v + SMALL_MAX;     // [SMALL_MAX]
+  __shared__ float s_tau;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int NW = SMALL_THREADS / 32;
+  for (int idx = tid; idx < d * d; idx += SMALL_THREADS) {
+    const int r = idx / d, c = idx - r * d;
+    As[r * LD + c] = A[static_cast<long long>(r) * ldA + c];
+  }
+  __syncthreads();
+  const bool prof = prof_on && tid == 32;  // a thread outside warp 0: sees warp 0's phase as barrier wait
+  long long tp = prof ? clock64() : 0, pc[6] = {0, 0, 0, 0, 0, 0};
+#define SM_PHASE(kk)               \
+  if (prof) {                      \
+    const long long tn = clock64(); \
+    pc[kk] += tn - tp;             \
+    tp = tn;                       \
+  }
+  for (int i = 0; i + 1 < d; ++i) {
+    // ---- reflector of column i (warp 0), v into shared memory and into row i of VT
+    if (warp == 0) {
+      float part = 0.f;
+      for (int r = i + 2 + lane; r < d; r += 32) {
+        const float a = As[r * LD + i];
+        part += a * a;
+      }
+      const float xnorm2 = warp_sum(part);
+      const float alpha = As[(i + 1) * LD + i];
+      float beta = alpha, tau = 0.f, scale = 0.f;
+      if (xnorm2 > 0.f) {
+        beta = -copysignf(sqrtf(alpha * alpha + xnorm2), alpha);
+        tau = (beta - alpha) / beta;
+        scale = 1.f / (alpha - beta);
+      }
+      for (int c = lane; c < L; c += 32) {
+        const float x = (c >= i + 2 && c < d) ? As[c * LD + i] * scale : (c == i + 1 ? 1.f : 0.f);
+        if (c < SMALL_MAX) v[c] = x;
+        VT[static_cast<long long>(i) * ldvt + c] = x;
+      }
+      if (lane == 0) {
+        dvec[i] = As[i * LD + i];
+        evec[i] = beta;
+        taus[i] = tau;
+        s_tau = tau;
+      }
+    }
+    __syncthreads();
+    SM_PHASE(0)
+    const float tau = s_tau;
+    if (tau != 0.f) {
+      // ---- p = A22 v (rows of this warp; full symmetric storage). d <= 128: at most 8 rows per
+      // warp, kept as independent accumulators and reduced together (9 shuffles instead of 40)
+      {
+        float part[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) part[u] = 0.f;
+        for (int c = i + 1 + lane; c < d; c += 32) {
+          const float vc = v[c];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int r = i + 1 + warp + u * NW;
+            if (r < d) part[u] += As[r * LD + c] * vc;
+          }
+        }
+        const float rsum = reduce8_packed(part, lane);
+        if ((lane & 3) == 0) {
+          const int u = (((lane >> 4) & 1) << 2) + (((lane >> 3) & 1) << 1) + ((lane >> 2) & 1);
+          const int r = i + 1 + warp + u * NW;
+          if (r < d) pvec[r] = rsum;
+        }
+      }
+      SM_PHASE(1)
+      __syncthreads();
+      SM_PHASE(2)
+      // ---- w = tau p - (tau^2 / 2)(p^T v) v, redundantly per warp; A22 -= v w^T + w v^T
+      float pv = 0.f;
+      for (int c = i + 1 + lane; c < d; c += 32) pv += pvec[c] * v[c];
+      pv = warp_sum(pv);
+      const float alpha2 = -0.5f * tau * tau * pv;
+      float vr[8], wr[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = i + 1 + warp + u * NW;
+        vr[u] = r < d ? v[r] : 0.f;
+        wr[u] = r < d ? tau * pvec[r] + alpha2 * vr[u] : 0.f;
+      }
+      for (int c = i + 1 + lane; c < d; c += 32) {
+        const float vc = v[c], wc = tau * pvec[c] + alpha2 * vc;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = i + 1 + warp + u * NW;
+          if (r < d) As[r * LD + c] -= vr[u] * wc + wr[u] * vc;
+        }
+      }
+    }
+    SM_PHASE(3)
+    __syncthreads();
+    SM_PHASE(4)
+  }
+  if (prof)
+    for (int k2 = 0; k2 < 5; ++k2) atomicAdd(&g_phase_cycles[k2], static_cast<unsigned long long>(pc[k2]));
+#undef SM_PHASE
+  if (tid == 0) dvec[d - 1] = As[(d - 1) * LD + (d - 1)];
+}
+
+// Back-transformation for d <= 128 in one CTA: U <- H_0 H_1 ... H_{d-2} Z with the reflectors (rows
+// of VT) and Z = U both resident in shared memory, one reflector at a time (w = v^T Z, Z -= tau v w^T;
+// 2 d^2 k FLOP in all: 2.4 MFLOP at d = k = 96). Replaces, at these sizes, the T factors, the
+// bf16x3 reflector store and four launches per panel of the compact-WY path, which cost ~100 us
+// of launch latency and tiny GEMMs for the same arithmetic.
+__global__ void __launch_bounds__(SMALL_THREADS, 1)
+backtransform_small_kernel(const float* __restrict__ VT, long long ldvt, const float* __restrict__ taus,
+                           int d, int k, float* __restrict__ U, long long ldu) {
+  extern __shared__ float smb[];
+  const int LDV = d | 1, LDZ = k | 1;
+  float* Vs = smb;               // [d][LDV]  reflector i in row i
+  float* Zs = Vs + d * LDV;      // [d][LDZ]
+  float* part = Zs + d * LDZ;    // [4][SMALL_MAX]
+  float* wv = part + 4 * SMALL_MAX;  // [SMALL_MAX]
+  float* ts = wv + SMALL_MAX;        // [SMALL_MAX] taus (a global load per reflector would be an L2
+                                     // round trip on the critical path of every iteration)
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < d; idx += SMALL_THREADS) ts[idx] = taus[idx];
+  for (int idx = tid; idx < d * d; idx += SMALL_THREADS) {
+    const int r = idx / d, c = idx - r * d;
+    Vs[r * LDV + c] = (r + 1 < d) ? VT[static_cast<long long>(r) * ldvt + c] : 0.f;
+  }
+  for (int idx = tid; idx < d * k; idx += SMALL_THREADS) {
+    const int r = idx / k, c = idx - r * k;
+    Zs[r * LDZ + c] = U[static_cast<long long>(r) * ldu + c];
+  }
+  __syncthreads();
+  const int grp = tid >> 7, c = tid & 127;  // 4 row groups x up to 128 columns
+  for (int i = d - 2; i >= 0; --i) {
+    const float tau = ts[i];
+    if (tau == 0.f) continue;  // uniform
+    const float* vi = Vs + i * LDV;
+    float s = 0.f;
+    if (c < k)
+      for (int r = i + 1 + grp; r < d; r += 4) s += vi[r] * Zs[r * LDZ + c];
+    part[grp * SMALL_MAX + c] = s;
+    __syncthreads();
+    if (tid < k)
+      wv[tid] = tau * (part[tid] + part[SMALL_MAX + tid] + part[2 * SMALL_MAX + tid] + part[3 * SMALL_MAX + tid]);
+    __syncthreads();
+    if (c < k) {
+      const float w = wv[c];
+      for (int r = i + 1 + grp; r < d; r += 4) Zs[r * LDZ + c] -= vi[r] * w;
+    }
+    // the next reflector's dots read rows written by other row groups
+    __syncthreads();
+  }
+  for (int idx = tid; idx < d * k; idx += SMALL_THREADS) {
+    const int r = idx / k, cc = idx - r * k;
+    U[static_cast<long long>(r) * ldu + cc] = Zs[r * LDZ + cc];
+  }
+}
+
 // Compact-WY factor of one panel of reflectors stored as ROWS of VT (the resident kernel's
 // layout): T[a][b] = -tau_b * sum_{c=a}^{b-1} T[a][c] (v_c . v_b), T[b][b] = tau_b (LAPACK larft,
 // forward / columnwise; the panel kernel builds the same T on the fly). One CTA per panel.
@@ -1888,6 +2062,8 @@ static int g_panel_prof = 0;
 static int g_res_enable = 1;  // 0: blocked panel kernel all the way (round-1 path)
 static int g_res_rows = 4;    // target rows per CTA of the resident kernel (grid = m0 / rows, <= SMs)
 static int g_jacobi_max = JACOBI_DEFAULT;
+static int g_small_enable = 1;  // d <= 128: single-CTA tridiagonalisation instead of the resident kernel
+void eigh_debug_small(int on) { g_small_enable = on; }
 // From this d on the multisection would use 4 lanes per eigenvalue instead of 16. Measured on a
 // B200 (d = 2048 / 4096): 4 lanes are 1.5-2 ms SLOWER -- the stage is bound by the chain of d
 // dependent fp64 divisions per pass, not by the fp64 pipe, so fewer, wider passes win. Kept as a
@@ -2062,6 +2238,7 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
     }
   }
 
+  const bool small_path = rs.valid && rs.j0 == 0 && d <= SMALL_MAX && g_small_enable;
   if (rs.valid) {
     // The rest of the reduction in ONE launch with the trailing block resident in shared memory.
     cudaMemsetAsync(p.VT, 0, static_cast<size_t>(rs.m0) * p.ldvt * sizeof(float), st);
@@ -2073,17 +2250,32 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
     g.xP = p.xbuf; g.xR = p.xbuf + 2 * static_cast<size_t>(rs.L); g.ctr = p.rctr;
     g.prof = g_panel_prof;
     void* args[] = {&g};
-    if (cudaLaunchCooperativeKernel(reinterpret_cast<void*>(sytd2_resident_kernel), dim3(rs.G),
-                                    dim3(RES_THREADS), args, rs.smem, st) != cudaSuccess)
+    if (small_path) {
+      const size_t smem = (static_cast<size_t>(d) * (d | 1) + 2 * SMALL_MAX) * sizeof(float);
+      bool* sattr = attr_flag(2);
+      if (!*sattr) {
+        if (cudaFuncSetAttribute(sytd2_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (SMALL_MAX * (SMALL_MAX | 1) + 2 * SMALL_MAX) * 4) != cudaSuccess)
+          return -12;
+        *sattr = true;
+      }
+      sytd2_small_kernel<<<1, SMALL_THREADS, smem, st>>>(p.Aw, p.ldA, d, rs.L, p.VT, p.ldvt, p.dvec,
+                                                         p.evec, p.taus, g_panel_prof);
+      PTD_CHECK_LAUNCH();
+    } else if (cudaLaunchCooperativeKernel(reinterpret_cast<void*>(sytd2_resident_kernel), dim3(rs.G),
+                                           dim3(RES_THREADS), args, rs.smem, st) != cudaSuccess) {
       return -5;
-    const int rpanels = (rs.m0 + NB - 1) / NB;
-    larft_rows_kernel<<<rpanels, 256, 0, st>>>(p.VT, p.ldvt, rs.m0, rs.L, p.taus + rs.j0,
-                                               p.Tmats + static_cast<size_t>(rs.j0 / NB) * NB * NB);
-    PTD_CHECK_LAUNCH();
-    dim3 sgrid(static_cast<unsigned>((rs.m0 + 31) / 32), static_cast<unsigned>((rs.m0 + 31) / 32));
-    vt_split_kernel<<<sgrid, dim3(32, 8), 0, st>>>(p.VT, p.ldvt, rs.m0, rs.j0, p.Vs, p.ldv,
-                                                   static_cast<long long>(d) * p.ldv);
-    PTD_CHECK_LAUNCH();
+    }
+    if (!small_path) {  // (the one-CTA back-transformation reads VT and the taus directly)
+      const int rpanels = (rs.m0 + NB - 1) / NB;
+      larft_rows_kernel<<<rpanels, 256, 0, st>>>(p.VT, p.ldvt, rs.m0, rs.L, p.taus + rs.j0,
+                                                 p.Tmats + static_cast<size_t>(rs.j0 / NB) * NB * NB);
+      PTD_CHECK_LAUNCH();
+      dim3 sgrid(static_cast<unsigned>((rs.m0 + 31) / 32), static_cast<unsigned>((rs.m0 + 31) / 32));
+      vt_split_kernel<<<sgrid, dim3(32, 8), 0, st>>>(p.VT, p.ldvt, rs.m0, rs.j0, p.Vs, p.ldv,
+                                                     static_cast<long long>(d) * p.ldv);
+      PTD_CHECK_LAUNCH();
+    }
   }
 
   // ---- (2) tridiagonal eigenproblem in fp64
@@ -2115,6 +2307,20 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
   }
 
   // ---- (3) back-transformation: U <- (I - V_p T_p V_p^T) U for p = last .. first
+  if (small_path) {
+    const size_t smem = (static_cast<size_t>(d) * (d | 1) + static_cast<size_t>(d) * (k | 1) + 6 * SMALL_MAX) *
+                        sizeof(float);
+    bool* battr = attr_flag(3);
+    if (!*battr) {
+      if (cudaFuncSetAttribute(backtransform_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (2 * SMALL_MAX * (SMALL_MAX | 1) + 6 * SMALL_MAX) * 4) != cudaSuccess)
+        return -12;
+      *battr = true;
+    }
+    backtransform_small_kernel<<<1, SMALL_THREADS, smem, st>>>(p.VT, p.ldvt, p.taus, d, k, U, ldu);
+    PTD_CHECK_LAUNCH();
+    return 0;
+  }
   const long long zseg = static_cast<long long>(d) * p.kp;
   const long long xseg = static_cast<long long>(NB) * p.kp;
   for (int pi = p.npanels - 1; pi >= 0; --pi) {

@@ -41,5 +41,6 @@ void eigh_debug_resident(int enable, int rows_target, int jacobi_max);
 void eigh_debug_bisect_narrow(int d);
 // Debug: 1 = ratio-form (division) Sturm count instead of the product form.
 void eigh_debug_sturm_ratio(int on);
+void eigh_debug_small(int on);
 
 }  // namespace ptd
