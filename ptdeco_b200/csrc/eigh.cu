@@ -1128,48 +1128,57 @@ __global__ void __launch_bounds__(RES_THREADS, 1) sytd2_resident_kernel(const Re
 
 // ---------------------------------------------------------------------------- d <= 128: one CTA
 // The whole matrix fits one SM's shared memory, so the reduction needs no grid-wide exchange at
-// all: unblocked sytd2 (LAPACK, lower) with three block barriers per column, every warp owning
-// rows {warp, warp + 16, ...} of the trailing block for both the symv dots and the rank-2 update
-// (lanes run over columns: conflict-free, warp-synchronous reductions). Same outputs as the
-// resident kernel (d / e / tau, reflectors as rows of VT), so T factors, the tridiagonal stage and
-// the back-transformation are shared. fp32 working precision like the other two kernels.
+// all: unblocked sytd2 (LAPACK, lower) with three block barriers per column. One SM is bound by
+// instruction issue and shared-memory bandwidth (the scalar version: 4.9 k cycles per column at
+// d = 96, 16 warps x ~300 instructions through 4 schedulers), so the symv dots and the rank-2 update
+// work on 16-byte vectors: a warp instruction covers 4 rows x 32 columns (8 lanes per row; every
+// group of 8 lanes reads 128 contiguous bytes: conflict-free for any row stride). Same outputs as
+// the resident kernel (d / e / tau, reflectors as rows of VT). fp32 working precision like the
+// other two kernels.
 constexpr int SMALL_MAX = 128;
 constexpr int SMALL_THREADS = 512;
+constexpr int SMALL_LD = SMALL_MAX + 4;
+__device__ __forceinline__ int small_ld(int n) { return ((n + 3) & ~3) + 4; }
+
 __global__ void __launch_bounds__(SMALL_THREADS, 1)
 sytd2_small_kernel(const float* __restrict__ A, long long ldA, int d, int L, float* __restrict__ VT,
                    long long ldvt, float* __restrict__ dvec, float* __restrict__ evec,
                    float* __restrict__ taus, int prof_on) {
-  extern __shared__ float sma[];
-  const int LD = d | 1;  // odd row stride: column walks are conflict-free too
+  extern __shared__ __align__(16) float sma[];
+  const int LD = small_ld(d);      // multiple of 4: rows are 16-byte aligned; columns >= d hold zeros
   float* As = sma;                 // [d][LD]
-  float* v = As + d * LD;          // [SMALL_MAX]
-  float* pvec = v + SMALL_MAX;     // [SMALL_MAX]
+  float* v = As + d * LD;          // [SMALL_LD]  zero outside (i, d)
+  float* pvec = v + SMALL_LD;      // [SMALL_LD]
   __shared__ float s_tau;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rg = lane >> 3, ch = lane & 7;  // row within the warp's group of 4, 16-byte chunk of 32 columns
   constexpr int NW = SMALL_THREADS / 32;
-  for (int idx = tid; idx < d * d; idx += SMALL_THREADS) {
-    const int r = idx / d, c = idx - r * d;
-    As[r * LD + c] = A[static_cast<long long>(r) * ldA + c];
+  for (int idx = tid; idx < d * LD; idx += SMALL_THREADS) {
+    const int r = idx / LD, c = idx - r * LD;
+    As[idx] = c < d ? A[static_cast<long long>(r) * ldA + c] : 0.f;
   }
+  for (int idx = tid; idx < 2 * SMALL_LD; idx += SMALL_THREADS) v[idx] = 0.f;
   __syncthreads();
   const bool prof = prof_on && tid == 32;  // a thread outside warp 0: sees warp 0's phase as barrier wait
   long long tp = prof ? clock64() : 0, pc[6] = {0, 0, 0, 0, 0, 0};
-#define SM_PHASE(kk)               \
-  if (prof) {                      \
+#define SM_PHASE(kk)                \
+  if (prof) {                       \
     const long long tn = clock64(); \
-    pc[kk] += tn - tp;             \
-    tp = tn;                       \
+    pc[kk] += tn - tp;              \
+    tp = tn;                        \
   }
   for (int i = 0; i + 1 < d; ++i) {
-    // ---- reflector of column i (warp 0), v into shared memory and into row i of VT
+    // ---- reflector of column i (warp 0; column i below the diagonal == row i right of it: the
+    // trailing square is kept fully symmetric), v into shared memory and into row i of VT
     if (warp == 0) {
+      const float* rowi = As + i * LD;
       float part = 0.f;
       for (int r = i + 2 + lane; r < d; r += 32) {
-        const float a = As[r * LD + i];
+        const float a = rowi[r];
         part += a * a;
       }
       const float xnorm2 = warp_sum(part);
-      const float alpha = As[(i + 1) * LD + i];
+      const float alpha = rowi[i + 1];
       float beta = alpha, tau = 0.f, scale = 0.f;
       if (xnorm2 > 0.f) {
         beta = -copysignf(sqrtf(alpha * alpha + xnorm2), alpha);
@@ -1177,12 +1186,12 @@ sytd2_small_kernel(const float* __restrict__ A, long long ldA, int d, int L, flo
         scale = 1.f / (alpha - beta);
       }
       for (int c = lane; c < L; c += 32) {
-        const float x = (c >= i + 2 && c < d) ? As[c * LD + i] * scale : (c == i + 1 ? 1.f : 0.f);
-        if (c < SMALL_MAX) v[c] = x;
+        const float x = (c >= i + 2 && c < d) ? rowi[c] * scale : (c == i + 1 ? 1.f : 0.f);
+        v[c] = x;
         VT[static_cast<long long>(i) * ldvt + c] = x;
       }
       if (lane == 0) {
-        dvec[i] = As[i * LD + i];
+        dvec[i] = rowi[i];
         evec[i] = beta;
         taus[i] = tau;
         s_tau = tau;
@@ -1191,27 +1200,24 @@ sytd2_small_kernel(const float* __restrict__ A, long long ldA, int d, int L, flo
     __syncthreads();
     SM_PHASE(0)
     const float tau = s_tau;
+    const int cb = (i + 1) & ~3;  // first 16-byte chunk with a live column (v is zero left of i + 1)
     if (tau != 0.f) {
-      // ---- p = A22 v (rows of this warp; full symmetric storage). d <= 128: at most 8 rows per
-      // warp, kept as independent accumulators and reduced together (9 shuffles instead of 40)
-      {
-        float part[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) part[u] = 0.f;
-        for (int c = i + 1 + lane; c < d; c += 32) {
-          const float vc = v[c];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int r = i + 1 + warp + u * NW;
-            if (r < d) part[u] += As[r * LD + c] * vc;
+      // ---- p = A22 v
+      for (int r0 = i + 1 + warp * 4; r0 < d; r0 += NW * 4) {
+        const int r = r0 + rg;
+        float part = 0.f;
+        if (r < d) {
+          const float* arow = As + r * LD;
+          for (int c = cb + ch * 4; c < d; c += 32) {
+            const float4 a4 = *reinterpret_cast<const float4*>(arow + c);
+            const float4 v4 = *reinterpret_cast<const float4*>(v + c);
+            part += a4.x * v4.x + a4.y * v4.y + a4.z * v4.z + a4.w * v4.w;
           }
         }
-        const float rsum = reduce8_packed(part, lane);
-        if ((lane & 3) == 0) {
-          const int u = (((lane >> 4) & 1) << 2) + (((lane >> 3) & 1) << 1) + ((lane >> 2) & 1);
-          const int r = i + 1 + warp + u * NW;
-          if (r < d) pvec[r] = rsum;
-        }
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        part += __shfl_xor_sync(0xffffffffu, part, 4);
+        if (ch == 0 && r < d) pvec[r] = part;
       }
       SM_PHASE(1)
       __syncthreads();
@@ -1221,19 +1227,27 @@ sytd2_small_kernel(const float* __restrict__ A, long long ldA, int d, int L, flo
       for (int c = i + 1 + lane; c < d; c += 32) pv += pvec[c] * v[c];
       pv = warp_sum(pv);
       const float alpha2 = -0.5f * tau * tau * pv;
-      float vr[8], wr[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int r = i + 1 + warp + u * NW;
-        vr[u] = r < d ? v[r] : 0.f;
-        wr[u] = r < d ? tau * pvec[r] + alpha2 * vr[u] : 0.f;
-      }
-      for (int c = i + 1 + lane; c < d; c += 32) {
-        const float vc = v[c], wc = tau * pvec[c] + alpha2 * vc;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int r = i + 1 + warp + u * NW;
-          if (r < d) As[r * LD + c] -= vr[u] * wc + wr[u] * vc;
+      for (int r0 = i + 1 + warp * 4; r0 < d; r0 += NW * 4) {
+        const int r = r0 + rg;
+        if (r < d) {
+          const float vr = v[r], wr = tau * pvec[r] + alpha2 * vr;
+          float* arow = As + r * LD;
+          for (int c = cb + ch * 4; c < d; c += 32) {
+            float4 a4 = *reinterpret_cast<float4*>(arow + c);
+            const float4 v4 = *reinterpret_cast<const float4*>(v + c);
+            const float4 p4 = *reinterpret_cast<const float4*>(pvec + c);
+            // columns left of i + 1 (same chunk) and right of d - 1 stay as they are: v = 0 there,
+            // and w is masked (pvec holds stale / no values outside the live range)
+            const float w0 = (c >= i + 1 && c < d) ? tau * p4.x + alpha2 * v4.x : 0.f;
+            const float w1 = (c + 1 >= i + 1 && c + 1 < d) ? tau * p4.y + alpha2 * v4.y : 0.f;
+            const float w2 = (c + 2 >= i + 1 && c + 2 < d) ? tau * p4.z + alpha2 * v4.z : 0.f;
+            const float w3 = (c + 3 >= i + 1 && c + 3 < d) ? tau * p4.w + alpha2 * v4.w : 0.f;
+            a4.x -= vr * w0 + wr * v4.x;
+            a4.y -= vr * w1 + wr * v4.y;
+            a4.z -= vr * w2 + wr * v4.z;
+            a4.w -= vr * w3 + wr * v4.w;
+            *reinterpret_cast<float4*>(arow + c) = a4;
+          }
         }
       }
     }
@@ -1251,47 +1265,69 @@ sytd2_small_kernel(const float* __restrict__ A, long long ldA, int d, int L, flo
 // of VT) and Z = U both resident in shared memory, one reflector at a time (w = v^T Z, Z -= tau v w^T;
 // 2 d^2 k FLOP in all: 2.4 MFLOP at d = k = 96). Replaces, at these sizes, the T factors, the
 // bf16x3 reflector store and four launches per panel of the compact-WY path, which cost ~100 us
-// of launch latency and tiny GEMMs for the same arithmetic.
+// of launch latency and tiny GEMMs for the same arithmetic. Warps own rows {warp, warp + 16, ...};
+// a lane owns four columns (16-byte accesses).
 __global__ void __launch_bounds__(SMALL_THREADS, 1)
 backtransform_small_kernel(const float* __restrict__ VT, long long ldvt, const float* __restrict__ taus,
                            int d, int k, float* __restrict__ U, long long ldu) {
-  extern __shared__ float smb[];
-  const int LDV = d | 1, LDZ = k | 1;
-  float* Vs = smb;               // [d][LDV]  reflector i in row i
-  float* Zs = Vs + d * LDV;      // [d][LDZ]
-  float* part = Zs + d * LDZ;    // [4][SMALL_MAX]
-  float* wv = part + 4 * SMALL_MAX;  // [SMALL_MAX]
-  float* ts = wv + SMALL_MAX;        // [SMALL_MAX] taus (a global load per reflector would be an L2
-                                     // round trip on the critical path of every iteration)
-  const int tid = threadIdx.x;
+  extern __shared__ __align__(16) float smb[];
+  constexpr int NW = SMALL_THREADS / 32;
+  const int LDV = d | 1, LDZ = small_ld(k);
+  float* Zs = smb;                    // [d][LDZ]   (first: 16-byte aligned rows)
+  float* part = Zs + d * LDZ;         // [NW][SMALL_MAX]
+  float* wv = part + NW * SMALL_MAX;  // [SMALL_MAX]
+  float* ts = wv + SMALL_MAX;         // [SMALL_MAX] taus (a global load per reflector would be an L2
+                                      // round trip on the critical path of every iteration)
+  float* Vs = ts + SMALL_MAX;         // [d][LDV]   reflector i in row i (scalar broadcast reads)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int idx = tid; idx < d; idx += SMALL_THREADS) ts[idx] = taus[idx];
   for (int idx = tid; idx < d * d; idx += SMALL_THREADS) {
     const int r = idx / d, c = idx - r * d;
     Vs[r * LDV + c] = (r + 1 < d) ? VT[static_cast<long long>(r) * ldvt + c] : 0.f;
   }
-  for (int idx = tid; idx < d * k; idx += SMALL_THREADS) {
-    const int r = idx / k, c = idx - r * k;
-    Zs[r * LDZ + c] = U[static_cast<long long>(r) * ldu + c];
+  for (int idx = tid; idx < d * LDZ; idx += SMALL_THREADS) {
+    const int r = idx / LDZ, c = idx - r * LDZ;
+    Zs[idx] = c < k ? U[static_cast<long long>(r) * ldu + c] : 0.f;
   }
   __syncthreads();
-  const int grp = tid >> 7, c = tid & 127;  // 4 row groups x up to 128 columns
+  const int c4 = lane * 4;
+  const bool colive = c4 < k;
   for (int i = d - 2; i >= 0; --i) {
     const float tau = ts[i];
     if (tau == 0.f) continue;  // uniform
     const float* vi = Vs + i * LDV;
-    float s = 0.f;
-    if (c < k)
-      for (int r = i + 1 + grp; r < d; r += 4) s += vi[r] * Zs[r * LDZ + c];
-    part[grp * SMALL_MAX + c] = s;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (colive)
+      for (int r = i + 1 + warp; r < d; r += NW) {
+        const float vr = vi[r];
+        const float4 z = *reinterpret_cast<const float4*>(Zs + r * LDZ + c4);
+        s.x += vr * z.x;
+        s.y += vr * z.y;
+        s.z += vr * z.z;
+        s.w += vr * z.w;
+      }
+    *reinterpret_cast<float4*>(part + warp * SMALL_MAX + c4) = s;
     __syncthreads();
-    if (tid < k)
-      wv[tid] = tau * (part[tid] + part[SMALL_MAX + tid] + part[2 * SMALL_MAX + tid] + part[3 * SMALL_MAX + tid]);
-    __syncthreads();
-    if (c < k) {
-      const float w = wv[c];
-      for (int r = i + 1 + grp; r < d; r += 4) Zs[r * LDZ + c] -= vi[r] * w;
+    if (tid < SMALL_MAX) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) t += part[w * SMALL_MAX + tid];
+      wv[tid] = tau * t;
     }
-    // the next reflector's dots read rows written by other row groups
+    __syncthreads();
+    if (colive) {
+      const float4 w4 = *reinterpret_cast<const float4*>(wv + c4);
+      for (int r = i + 1 + warp; r < d; r += NW) {
+        const float vr = vi[r];
+        float4 z = *reinterpret_cast<float4*>(Zs + r * LDZ + c4);
+        z.x -= vr * w4.x;
+        z.y -= vr * w4.y;
+        z.z -= vr * w4.z;
+        z.w -= vr * w4.w;
+        *reinterpret_cast<float4*>(Zs + r * LDZ + c4) = z;
+      }
+    }
+    // the next reflector's dots read rows written by other warps
     __syncthreads();
   }
   for (int idx = tid; idx < d * k; idx += SMALL_THREADS) {
@@ -2251,11 +2287,11 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
     g.prof = g_panel_prof;
     void* args[] = {&g};
     if (small_path) {
-      const size_t smem = (static_cast<size_t>(d) * (d | 1) + 2 * SMALL_MAX) * sizeof(float);
+      const size_t smem = (static_cast<size_t>(d) * (((d + 3) & ~3) + 4) + 2 * SMALL_LD) * sizeof(float);
       bool* sattr = attr_flag(2);
       if (!*sattr) {
         if (cudaFuncSetAttribute(sytd2_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (SMALL_MAX * (SMALL_MAX | 1) + 2 * SMALL_MAX) * 4) != cudaSuccess)
+                                 (SMALL_MAX * SMALL_LD + 2 * SMALL_LD) * 4) != cudaSuccess)
           return -12;
         *sattr = true;
       }
@@ -2308,12 +2344,13 @@ int eigh(const float* A, int d, long long lda, int k, float* evals, float* U, lo
 
   // ---- (3) back-transformation: U <- (I - V_p T_p V_p^T) U for p = last .. first
   if (small_path) {
-    const size_t smem = (static_cast<size_t>(d) * (d | 1) + static_cast<size_t>(d) * (k | 1) + 6 * SMALL_MAX) *
-                        sizeof(float);
+    const size_t smem = (static_cast<size_t>(d) * (d | 1) + static_cast<size_t>(d) * (((k + 3) & ~3) + 4) +
+                         (SMALL_THREADS / 32 + 2) * SMALL_MAX) * sizeof(float);
     bool* battr = attr_flag(3);
     if (!*battr) {
       if (cudaFuncSetAttribute(backtransform_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (2 * SMALL_MAX * (SMALL_MAX | 1) + 6 * SMALL_MAX) * 4) != cudaSuccess)
+                               (SMALL_MAX * (SMALL_MAX | 1) + SMALL_MAX * SMALL_LD +
+                                (SMALL_THREADS / 32 + 2) * SMALL_MAX) * 4) != cudaSuccess)
         return -12;
       *battr = true;
     }
