@@ -185,3 +185,97 @@ def test_decompose_dwain_task_end_to_end(tmp_path, finetune):
     # same weights; the run evaluated them through the fused two-factor kernel, this model through
     # two F.linear calls: bf16 rounding of the rank-k intermediate differs
     assert abs(ppl - summary["perplexity_final"]) <= 2e-2 * summary["perplexity_final"]
+
+
+EXV = os.path.join(ROOT, "examples", "trainer_vision")
+
+FALOR_CFG = {
+    "task": "decompose_falor", "imagenet_root_dir": "synthetic", "trn_imagenet_classes_fname": None,
+    "val_imagenet_classes_fname": None, "batch_size": 4, "normalization": "imagenet", "input_h_w": [64, 64],
+    "decompose_model_name": "torchvision.convnext_tiny", "nsr_final_threshold": 0.05, "kl_final_threshold": 0.05,
+    "proportion_threshold": 10.0, "num_data_steps": 3, "num_metric_steps": 2, "blacklisted_modules": [],
+    "use_float64": False,
+}
+
+
+def _vision_modules():
+    """The two example directories reuse module names (builder, configurator, run): load the vision
+    ones under their own names."""
+    import importlib.util
+    mods = {}
+    sys.path.insert(0, EXV)
+    try:
+        for name in ("configurator", "builder", "run_decompose_falor", "run"):
+            spec = importlib.util.spec_from_file_location(f"vision_{name}", os.path.join(EXV, f"{name}.py"))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[spec.name] = mod  # pydantic resolves annotations through sys.modules
+            saved = {k: sys.modules.get(k) for k in ("configurator", "builder", "run_decompose_falor")}
+            for k in saved:
+                if f"vision_{k}" in mods:
+                    sys.modules[k] = mods[f"vision_{k}"]
+            spec.loader.exec_module(mod)
+            for k, v in saved.items():
+                if v is None:
+                    sys.modules.pop(k, None)
+                else:
+                    sys.modules[k] = v
+            mods[f"vision_{name}"] = mod
+    finally:
+        sys.path.remove(EXV)
+    return mods
+
+
+def test_vision_example_config_and_dispatch(tmp_path):
+    import pathlib
+
+    import pydantic
+    m = _vision_modules()
+    cfg = m["vision_configurator"].DecomposeFALORConfig(**FALOR_CFG)
+    assert cfg.input_h_w == (64, 64) and cfg.task == "decompose_falor"
+    # the reference's examples_config/decompose_falor.yaml fields
+    ref = dict(FALOR_CFG, imagenet_root_dir="/nas/datasets/ImageNet", trn_imagenet_classes_fname="train_es.txt",
+               val_imagenet_classes_fname="val.txt", batch_size=8, input_h_w=[224, 224],
+               decompose_model_name="timm.swinv2_cr_tiny_ns_224.sw_in1k")
+    ref.pop("use_float64")
+    assert m["vision_configurator"].DecomposeFALORConfig(**ref).use_float64 is False
+    with pytest.raises(pydantic.ValidationError):
+        m["vision_configurator"].DecomposeFALORConfig(**dict(FALOR_CFG, nope=1))
+    with pytest.raises(ValueError, match="Unknown config.task"):
+        m["vision_run"].dispatch({"task": "x"}, pathlib.Path(tmp_path))
+    with pytest.raises(ValueError, match="timm"):
+        m["vision_builder"].make_model("timm.swinv2_cr_tiny_ns_224.sw_in1k")
+    it = m["vision_run_decompose_falor"].make_image_iterator(2, (8, 8), "imagenet", 3)
+    a, b = next(it), next(it)
+    it2 = m["vision_run_decompose_falor"].make_image_iterator(2, (8, 8), "imagenet", 3)
+    assert a.shape == (2, 3, 8, 8) and torch.equal(a, next(it2)) and not torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_vision_decompose_falor_task_end_to_end(tmp_path):
+    """falor through the vision example on a random-init torchvision ConvNeXt-tiny (small synthetic
+    images): artifacts under the reference's names load into a freshly built model that then
+    produces the decomposed model's logits."""
+    import pathlib
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    m = _vision_modules()
+    out = pathlib.Path(tmp_path)
+    sys.modules["builder"], sys.modules["configurator"] = m["vision_builder"], m["vision_configurator"]
+    try:
+        summary = m["vision_run_decompose_falor"].main(config_raw=dict(FALOR_CFG), output_path=out)
+    finally:
+        sys.modules.pop("builder", None)
+        sys.modules.pop("configurator", None)
+    assert summary["modules_decomposed"] >= 1 and summary["mparams_final"] < summary["mparams_initial"]
+    deco = json.load(open(out / "decompose_config.json"))
+    assert len(deco) == summary["modules_decomposed"] and all(v["type"] == "Sequential" for v in deco.values())
+    dev = torch.device("cuda", 0)
+    fresh = m["vision_builder"].make_model(FALOR_CFG["decompose_model_name"])
+    m["vision_builder"].apply_decompose_config_and_state_dict_in_place(
+        model=fresh, decompose_config_path=str(out / "decompose_config.json"),
+        state_dict_path=str(out / "decompose_state_dict.pt"), device=dev)
+    assert abs(m["vision_builder"].get_model_stats(fresh)["mparams"] - summary["mparams_final"]) < 1e-9
+    x = next(m["vision_run_decompose_falor"].make_image_iterator(4, (64, 64), "imagenet", 1)).to(dev)
+    with torch.no_grad():
+        y = fresh(x)
+    assert torch.isfinite(y).all() and y.shape == (4, 1000)
