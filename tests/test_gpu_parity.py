@@ -1189,3 +1189,40 @@ def test_full_size_decode_forward_70b_shapes(dev):
         y2 = linalg.lowrank_forward((2 * x), w1, w2, None).float()  # exact in bf16: doubling x
         y1 = linalg.lowrank_forward(x, w1, w2, None).float()
         assert float((y2 - 2 * y1).abs().max() / y2.abs().max()) <= 1e-2
+
+
+def test_config_round_trip_on_a_torchvision_model(dev):
+    """The reference's tests/test_config_torchvision_timm.py::check_config with falor producing the
+    config (lockd, which that test uses, is out of scope): decompose model 1, rebuild the architecture
+    of an untouched model 2 from the returned decompose_config, load model 1's state dict strictly,
+    and both must give the same output."""
+    import torchvision
+
+    import ptdeco_b200.falor as falor
+    from ptdeco_b200 import modules, utils
+    from synth import streams
+    torch.manual_seed(271828)
+    model1 = torchvision.models.get_model("convnext_tiny", weights=None, num_classes=10).to(dev).eval()
+    model2 = torchvision.models.get_model("convnext_tiny", weights=None, num_classes=10).to(dev).eval()
+    data = streams.IndexedStream(lambda i: torch.rand(4, 3, 64, 64, generator=torch.Generator().manual_seed(1314159 + i)))
+    dc = falor.decompose_in_place(
+        module=model1, device=dev, data_iterator=data, proportion_threshold=10.0, nsr_final_threshold=0.05,
+        kl_final_threshold=0.05, num_data_steps=2, num_metric_steps=1, use_float64=False, use_mean=False,
+        use_damping=True)
+    assert len(dc) >= 5
+    json.loads(json.dumps(dc))  # JSON-serialisable like the reference's
+    sd = model1.state_dict()
+    x = torch.rand(5, 3, 64, 64, generator=torch.Generator().manual_seed(5)).to(dev)
+    with torch.no_grad():
+        y1 = model1(x)
+    utils.apply_decompose_config_in_place(model2, dc)
+    model2.load_state_dict(sd, strict=True)
+    model2.to(dev).eval()
+    with torch.no_grad():
+        y2 = model2(x)
+    # model 1 holds LowRankSequential modules (fused kernel, fp32 operands through the bf16x3 split),
+    # model 2 plain nn.Sequential pairs on cuBLAS: same weights, fp32 rounding apart
+    torch.testing.assert_close(y1, y2, rtol=1e-4, atol=1e-4)
+    assert modules.fuse_decomposed_modules_in_place(model2) == len(dc)
+    with torch.no_grad():
+        torch.testing.assert_close(model2(x), y1, rtol=1e-4, atol=1e-4)
